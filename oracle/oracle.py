@@ -1,0 +1,206 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT PATH.
+
+ctypes front end of oracle/ibt_oracle.c, the plain-C restatement of the OpenCV-internal
+arithmetic that the reference's tracking loop resolves to
+(/root/reference/s1_lucaskanade_tracking.py:296-450,
+/root/reference/s0_1_test_lucaskanade_tracking.py:57-181; OpenCV pinned 4.9.0 / 4.10.0
+in environment.yml:254 / s0_1.yml:199, wheel here 4.13.0.92).  Function names and
+signatures follow cv2's so parity tests read like calls of the reference.
+
+Pinning: the reference ships no tests or golden vectors for this path; the oracle is
+pinned against outputs of the cv2 wheel recorded in tests/golden/ (make_golden.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libibt_oracle.so")
+
+COLOR_BGR2GRAY = 6
+TERM_CRITERIA_COUNT = 1
+TERM_CRITERIA_EPS = 2
+OPTFLOW_USE_INITIAL_FLOW = 4
+OPTFLOW_LK_GET_MIN_EIGENVALS = 8
+
+
+def build(force=False):
+    """Compile the C restatement with gcc (oracle/Makefile)."""
+    src = os.path.join(_HERE, "ibt_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_pyramid_levels.restype = C.c_int
+        _lib.orc_gftt_select.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def cvtColor(src, code=COLOR_BGR2GRAY, coeffset=0):
+    """A.1; cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) at s1:311."""
+    assert code == COLOR_BGR2GRAY
+    src = np.ascontiguousarray(src)
+    assert src.dtype == np.uint8 and src.ndim == 3 and src.shape[2] in (3, 4)
+    dst = np.empty(src.shape[:2], np.uint8)
+    lib().orc_gray_u8(_p(src), C.c_int64(dst.size), C.c_int(src.shape[2]), C.c_int(coeffset), _p(dst))
+    return dst
+
+
+def pyrDown(src):
+    """A.2."""
+    src = np.ascontiguousarray(src)
+    assert src.dtype == np.uint8 and src.ndim == 2
+    h, w = src.shape
+    dst = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().orc_pyrdown_u8(_p(src), C.c_int(h), C.c_int(w), _p(dst))
+    return dst
+
+
+def scharr_deriv(src):
+    """A.4; (h,w,2) int16, channel 0 = dx, 1 = dy."""
+    src = np.ascontiguousarray(src)
+    h, w = src.shape
+    dst = np.empty((h, w, 2), np.int16)
+    lib().orc_scharr_i16(_p(src), C.c_int(h), C.c_int(w), _p(dst))
+    return dst
+
+
+def pyramid_sizes(h, w, winSize, maxLevel):
+    sizes = (C.c_int * (2 * (maxLevel + 1)))()
+    ml = lib().orc_pyramid_levels(C.c_int(h), C.c_int(w), C.c_int(winSize[0]), C.c_int(winSize[1]),
+                                  C.c_int(maxLevel), sizes)
+    return ml, [(sizes[2 * i], sizes[2 * i + 1]) for i in range(ml + 1)]
+
+
+def buildOpticalFlowPyramid(img, winSize, maxLevel, withDerivatives=True):
+    """A.3; returns (maxLevelOut, [L0, D0, L1, D1, ...]) like cv2 (unpadded arrays)."""
+    img = np.ascontiguousarray(img)
+    ml, sizes = pyramid_sizes(img.shape[0], img.shape[1], winSize, maxLevel)
+    out = []
+    lvl = img
+    for l in range(ml + 1):
+        if l > 0:
+            lvl = pyrDown(lvl)
+        out.append(lvl)
+        if withDerivatives:
+            out.append(scharr_deriv(lvl))
+    return ml, out
+
+
+def _criteria(criteria):
+    typ, cnt, eps = criteria
+    if not (typ & TERM_CRITERIA_COUNT):
+        cnt = 30
+    if not (typ & TERM_CRITERIA_EPS):
+        eps = 0.01
+    return int(cnt), float(eps)
+
+
+def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, winSize=(21, 21), maxLevel=3,
+                         criteria=(TERM_CRITERIA_COUNT | TERM_CRITERIA_EPS, 30, 0.01), flags=0,
+                         minEigThreshold=1e-4, return_iters=False):
+    """A.5; same call as s1:323 / s1:326.  With return_iters also returns the (N, L+1)
+    int32 per-level iteration counts (column l = pyramid level l)."""
+    prevPts = np.asarray(prevPts)
+    assert prevPts.dtype == np.float32, "prevPts must be float32 (cv2 asserts the same)"
+    shp = prevPts.shape
+    pts = np.ascontiguousarray(prevPts.reshape(-1, 2))
+    n = pts.shape[0]
+    if n == 0:
+        return (None, None, None) + ((None,) if return_iters else ())
+    ml, pI = buildOpticalFlowPyramid(prevImg, winSize, maxLevel, True)
+    ml2, pJ = buildOpticalFlowPyramid(nextImg, winSize, maxLevel, False)
+    assert ml == ml2
+    L = ml + 1
+    lvI = [pI[2 * l] for l in range(L)]
+    dvI = [pI[2 * l + 1] for l in range(L)]
+    lvJ = pJ
+    arrI = (C.c_void_p * L)(*[a.ctypes.data for a in lvI])
+    arrJ = (C.c_void_p * L)(*[a.ctypes.data for a in lvJ])
+    arrD = (C.c_void_p * L)(*[a.ctypes.data for a in dvI])
+    hs = (C.c_int * L)(*[a.shape[0] for a in lvI])
+    ws = (C.c_int * L)(*[a.shape[1] for a in lvI])
+    use_init = bool(flags & OPTFLOW_USE_INITIAL_FLOW)
+    if use_init:
+        nxt = np.ascontiguousarray(np.asarray(nextPts, np.float32).reshape(-1, 2)).copy()
+    else:
+        nxt = np.zeros((n, 2), np.float32)
+    st = np.empty(n, np.uint8)
+    err = np.empty(n, np.float32)
+    iters = np.zeros((n, L), np.int32)
+    cnt, eps = _criteria(criteria)
+    lib().orc_lk(arrI, arrJ, arrD, hs, ws, C.c_int(ml), _p(pts), _p(nxt), C.c_int(n),
+                 C.c_int(winSize[0]), C.c_int(winSize[1]), C.c_int(cnt), C.c_double(eps),
+                 C.c_double(minEigThreshold), C.c_int(use_init),
+                 C.c_int(bool(flags & OPTFLOW_LK_GET_MIN_EIGENVALS)), _p(st), _p(err), _p(iters))
+    res = (nxt.reshape(shp), st.reshape(n, 1), err.reshape(n, 1))
+    return res + ((iters,) if return_iters else ())
+
+
+def cornerMinEigenVal(img, blockSize, ksize=3):
+    """A.6 steps 1-3."""
+    assert ksize == 3
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    eig = np.empty((h, w), np.float32)
+    lib().orc_mineig_f32(_p(img), C.c_int(h), C.c_int(w), C.c_int(blockSize), _p(eig))
+    return eig
+
+
+def gftt_select(eig, mask, maxCorners, qualityLevel, minDistance):
+    """A.6 steps 4-8 on a given eig map (not modified)."""
+    eig = np.array(eig, np.float32, copy=True, order="C")
+    h, w = eig.shape
+    if mask is not None:
+        mask = np.ascontiguousarray(mask)
+        assert mask.shape == eig.shape and mask.dtype == np.uint8
+    cap = max(1024, eig.size // 4)
+    out = np.empty((cap, 2), np.float32)
+    n = lib().orc_gftt_select(_p(eig), _p(mask) if mask is not None else None, C.c_int(h), C.c_int(w),
+                              C.c_int(int(maxCorners)), C.c_double(qualityLevel), C.c_double(minDistance),
+                              _p(out), C.c_int(cap))
+    if n == 0:
+        return None
+    return out[:n].reshape(-1, 1, 2).copy()
+
+
+def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None, blockSize=3,
+                        useHarrisDetector=False, k=0.04):
+    """A.6; same call as s1:437."""
+    assert not useHarrisDetector
+    return gftt_select(cornerMinEigenVal(image, blockSize), mask, maxCorners, qualityLevel, minDistance)
+
+
+def photo_to_utm(xy, cam):
+    """A.9; Camera.photocords_cropped_to_uncropped + Camera.photo_to_utm
+    (imports/camtools.py:414-421, 286-332).  cam = 12 float64, see ibt_oracle.c."""
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    cam = np.ascontiguousarray(cam, np.float64)
+    out = np.empty_like(xy)
+    lib().orc_photo_to_utm(_p(xy), C.c_int64(xy.shape[0]), _p(cam), _p(out))
+    return out
+
+
+def fb_check(p0, p0r, threshold=1.0):
+    """A.7 (s1:329-333): FB distance and validity; status/err are not consulted."""
+    diff = np.abs(np.asarray(p0, np.float32) - np.asarray(p0r, np.float32)).reshape(-1, 2)
+    dist = np.hypot(diff[:, 0], diff[:, 1])
+    return dist, dist < threshold
