@@ -1,0 +1,86 @@
+"""ctypes binding of libibt.so (include/ibt.h).  This is the ONLY compute back end of the package:
+there is no CPU or PyTorch fallback -- if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libibt.so")
+
+IBT_MAX_LEVELS = 8
+IBT_MAX_WIN = 63
+IBT_OK, IBT_E_INVALID, IBT_E_CUDA, IBT_E_WORKSPACE, IBT_E_CAPACITY = 0, -1, -2, -3, -4
+
+
+class IbtError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__("%s failed: %s%s" % (where, _errstr(code), (" -- " + detail) if detail else ""))
+
+
+class ibt_pyramid_t(C.Structure):
+    """HOST mirror of `struct ibt_pyramid` in include/ibt.h."""
+    _fields_ = [
+        ("nlevels", C.c_int32),
+        ("rows", C.c_int32 * IBT_MAX_LEVELS),
+        ("cols", C.c_int32 * IBT_MAX_LEVELS),
+        ("img", C.c_void_p * IBT_MAX_LEVELS),
+        ("img_pitch", C.c_int64 * IBT_MAX_LEVELS),
+        ("deriv", C.c_void_p * IBT_MAX_LEVELS),
+        ("deriv_pitch", C.c_int64 * IBT_MAX_LEVELS),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/ibt.h declares
+_vp, _i, _i64, _d, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_size_t
+_PYR = C.POINTER(ibt_pyramid_t)
+SIGNATURES = {
+    "ibt_version": (_i, []),
+    "ibt_error_string": (C.c_char_p, [_i]),
+    "ibt_last_cuda_error": (C.c_char_p, []),
+    "ibt_gray_u8": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp]),
+    "ibt_pyramid_levels": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
+    "ibt_pyr_level_u8": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "ibt_pyramid_build": (_i, [_PYR, _i, _vp]),
+    "ibt_lk": (_i, [_PYR, _PYR, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),
+    "ibt_lk_fb": (_i, [_PYR, _PYR, _vp, _i, _i, _i, _i, _d, _d, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                       _vp, _vp]),
+    "ibt_min_eigen_f32": (_i, [_vp, _i, _i, _i64, _i, _vp, _i64, _vp]),
+    "ibt_gftt_workspace_bytes": (_sz, [_i, _i]),
+    "ibt_gftt": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _d, _d, _i, _vp, _sz, _vp, _i, C.POINTER(C.c_int), _vp]),
+    "ibt_tracks_compact": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(C.c_int), _vp]),
+    "ibt_photo_to_utm": (_i, [_vp, _i64, C.POINTER(C.c_double), _vp, _vp]),
+    "ibt_polygon_mask": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libibt.so (once).  Raises ImportError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libibt.so is missing (%s). Build it with `python -m iceberg_tracking_code_b200.build` "
+                "(needs nvcc); there is no CPU fallback." % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)       # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _errstr(code):
+    try:
+        return lib().ibt_error_string(code).decode()
+    except Exception:
+        return "error %d" % code
+
+
+def check(rc, where):
+    if rc != IBT_OK:
+        detail = lib().ibt_last_cuda_error().decode() if rc == IBT_E_CUDA else ""
+        raise IbtError(rc, where, detail)

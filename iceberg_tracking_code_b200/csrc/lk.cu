@@ -1,0 +1,371 @@
+// K3: pyramidal Lucas-Kanade, one warp per feature point, all levels and iterations, forward and
+// backward pass plus the forward-backward check in one launch.
+// Replaces the two cv2.calcOpticalFlowPyrLK calls and the numpy FB arithmetic at
+// s1_lucaskanade_tracking.py:323-333 (s0_1_test_lucaskanade_tracking.py:92-102).
+//
+// Mapping.  Lane L of the warp owns tap column L of a strip of <= 31 window columns (a strip
+// needs one more tap column than it has window columns, so 32 lanes cover 31 columns; winSize
+// 31 is exactly one strip).  The warp walks down the winH+1 tap rows: each lane loads ONE byte
+// of the row (32 contiguous bytes per warp, read through L1), gets its right-hand neighbour
+// with a shuffle and keeps the previous row in registers, so every bilinear sample costs one
+// load + one shuffle instead of four gathers.  The template window (Iw, Ix, Iy as int16, OpenCV's
+// 5-fractional-bit fixed point) is built once per level into a per-warp shared-memory slab and
+// re-read with conflict-free 8-byte loads in every Newton iteration.  The 2x2 structure tensor
+// and the mismatch vector are accumulated exactly (int32 per lane, int64 across the warp by
+// shuffles) and rounded to float once; OpenCV accumulates in float SIMD lanes, which differs in
+// the last bits only.  All float arithmetic that OpenCV does unfused is compiled with -fmad=false.
+#include "common.cuh"
+#include <string.h>
+
+namespace ibt {
+
+struct LKLevel {
+    const uint8_t *img;
+    const uint32_t *deriv;      // packed (dx | dy << 16), may be null for a J-only pyramid
+    int img_pitch;              // bytes
+    int deriv_pitch;            // 4-byte elements
+    int rows, cols;
+};
+struct LKPyr {
+    LKLevel lv[IBT_MAX_LEVELS];
+    int nlevels;
+};
+struct LKArgs {
+    LKPyr A, B;                 // A = prev, B = next
+    const float *p0;
+    int n;
+    int winW, winH, nstrips, strip_cols;
+    int maxCount;
+    float eps2, minEigThr;
+    int flags;
+    int fb;                     // 0: single pass A->B ; 1: forward + backward + FB check
+    float fb_thresh;
+    float *p1; uint8_t *st1; float *err1;
+    float *p0r; uint8_t *st0; float *err0;
+    float *fbdist; uint8_t *alive; int32_t *iters; unsigned long long *iter_total;
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int cv_floor(float v)
+{
+    return __float2int_rd(v);
+}
+
+__device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11)
+{
+    const float oa = __fsub_rn(1.f, a), ob = __fsub_rn(1.f, b);
+    iw00 = __float2int_rn(__fmul_rn(__fmul_rn(oa, ob), 16384.f));
+    iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, ob), 16384.f));
+    iw10 = __float2int_rn(__fmul_rn(__fmul_rn(oa, b), 16384.f));
+    iw11 = 16384 - iw00 - iw01 - iw10;
+}
+
+__device__ __forceinline__ bool window_oob(int ix, int iy, int winW, int winH, int rows, int cols)
+{
+    return ix < -winW || ix >= cols || iy < -winH || iy >= rows;
+}
+
+// Sum over the window of  diff*Ix, diff*Iy  (MODE 0)  or  |diff|  (MODE 1), where
+// diff = bilinear(J at (ix+x, iy+y)) >> 9  -  Iw.   INSIDE: all taps lie inside the image.
+template <int MODE, bool INSIDE>
+__device__ __forceinline__ void window_pass(const LKLevel &LJ, const LKArgs &a, int ix, int iy,
+                                            int iw00, int iw01, int iw10, int iw11,
+                                            const uint2 *__restrict__ win, int lane,
+                                            long long &S1, long long &S2)
+{
+    const int rows = LJ.rows, cols = LJ.cols;
+    long long t1 = 0, t2 = 0;
+    for (int s = 0; s < a.nstrips; s++) {
+        const int cs = s * a.strip_cols;
+        const int xcol = ix + cs + lane;
+        const int xr = INSIDE ? min(xcol, cols - 1) : r101(xcol, cols);
+        const uint8_t *colp = LJ.img + xr;
+        const uint2 *wrow = win + (s * a.winH) * 32 + lane;
+        const bool active = lane < min(a.strip_cols, a.winW - cs);
+        int b1 = 0, b2 = 0;
+        int jp = __ldg(colp + (int64_t)(INSIDE ? iy : r101(iy, rows)) * LJ.img_pitch);
+        int jpr = __shfl_down_sync(0xffffffffu, jp, 1);
+#pragma unroll 4
+        for (int r = 1; r <= a.winH; r++) {
+            const int y = iy + r;
+            const int jc = __ldg(colp + (int64_t)(INSIDE ? y : r101(y, rows)) * LJ.img_pitch);
+            const int jcr = __shfl_down_sync(0xffffffffu, jc, 1);
+            const uint2 t = wrow[(r - 1) * 32];
+            const int Iw = (int)(t.x & 0xffffu);
+            const int v = jp * iw00 + jpr * iw01 + jc * iw10 + jcr * iw11;
+            const int diff = ((v + 256) >> 9) - Iw;
+            if (MODE == 0) {
+                const int Ix = ((int)t.x) >> 16, Iy = (int)t.y;   // zero on inactive lanes
+                b1 += diff * Ix; b2 += diff * Iy;
+            } else {
+                b2 += active ? abs(diff) : 0;
+            }
+            jp = jc; jpr = jcr;
+        }
+        t1 += b1; t2 += b2;
+    }
+    S1 = warp_sum_ll(t1);
+    S2 = warp_sum_ll(t2);
+}
+
+// One pyramidal pass for one point.  On entry (ox, oy) holds the initial flow if use_init.
+// On exit (ox, oy) = nextPts[k], status/err as cv2 (err = 0 where status == 0).
+__device__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, float ptx, float pty, bool use_init,
+                         float &ox, float &oy, int &status, float &err, int &iters, uint2 *win, int lane)
+{
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const int winW = a.winW, winH = a.winH;
+    const float halfx = (winW - 1) * 0.5f, halfy = (winH - 1) * 0.5f;
+    status = 1; err = 0.f;
+    const int L = PI.nlevels;
+    for (int level = L - 1; level >= 0; --level) {
+        const LKLevel &LI = PI.lv[level];
+        const LKLevel &LJ = PJ.lv[level];
+        const int rows = LI.rows, cols = LI.cols;
+        const float sc = __int_as_float((127 - level) << 23);       // 2^-level
+        float ppx = __fmul_rn(ptx, sc), ppy = __fmul_rn(pty, sc);
+        float nx, ny;
+        if (level == L - 1) {
+            if (use_init) { nx = __fmul_rn(ox, sc); ny = __fmul_rn(oy, sc); }
+            else { nx = ppx; ny = ppy; }
+        } else { nx = __fmul_rn(ox, 2.f); ny = __fmul_rn(oy, 2.f); }
+        ox = nx; oy = ny;
+
+        ppx = __fsub_rn(ppx, halfx); ppy = __fsub_rn(ppy, halfy);
+        const int ipx = cv_floor(ppx), ipy = cv_floor(ppy);
+        if (window_oob(ipx, ipy, winW, winH, rows, cols)) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        int iw00, iw01, iw10, iw11;
+        bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
+
+        // ---- template window: Iw (5 fractional bits), Ix, Iy; structure tensor -------------------
+        long long sA11 = 0, sA12 = 0, sA22 = 0;
+        for (int s = 0; s < a.nstrips; s++) {
+            const int cs = s * a.strip_cols;
+            const int nc = min(a.strip_cols, winW - cs);             // window columns in this strip
+            const int xcol = ipx + cs + lane;
+            const int xr = r101(xcol, cols);
+            const bool xin = (xcol >= 0) && (xcol < cols);
+            const bool active = lane < nc;
+            int a11 = 0, a12 = 0, a22 = 0;
+            int ip = 0, ipr = 0;
+            uint32_t dp = 0, dpr = 0;
+            uint2 *wrow = win + (s * winH) * 32 + lane;
+#pragma unroll 2
+            for (int r = 0; r <= winH; r++) {
+                const int y = ipy + r;
+                const bool yin = (y >= 0) && (y < rows);
+                const int ic = __ldg(LI.img + (int64_t)r101(y, rows) * LI.img_pitch + xr);
+                uint32_t dc = 0;                                     // derivative planes are zero outside the image
+                if (xin && yin) dc = __ldg(LI.deriv + (int64_t)y * LI.deriv_pitch + xcol);
+                const int icr = __shfl_down_sync(0xffffffffu, ic, 1);
+                const uint32_t dcr = __shfl_down_sync(0xffffffffu, dc, 1);
+                if (r > 0) {
+                    const int v = ip * iw00 + ipr * iw01 + ic * iw10 + icr * iw11;
+                    const int d00x = (int)(short)(dp & 0xffff), d00y = ((int)dp) >> 16;
+                    const int d01x = (int)(short)(dpr & 0xffff), d01y = ((int)dpr) >> 16;
+                    const int d10x = (int)(short)(dc & 0xffff), d10y = ((int)dc) >> 16;
+                    const int d11x = (int)(short)(dcr & 0xffff), d11y = ((int)dcr) >> 16;
+                    int Iw = (v + 256) >> 9;
+                    int Ix = (d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
+                    int Iy = (d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
+                    if (!active) { Iw = 0; Ix = 0; Iy = 0; }
+                    // word0 = Iw | Ix << 16 ; word1 = Iy
+                    uint2 t;
+                    t.x = ((uint32_t)Iw & 0xffffu) | ((uint32_t)Ix << 16);
+                    t.y = (uint32_t)Iy;
+                    wrow[(r - 1) * 32] = t;
+                    a11 += Ix * Ix; a12 += Ix * Iy; a22 += Iy * Iy;
+                }
+                ip = ic; ipr = icr; dp = dc; dpr = dcr;
+            }
+            sA11 += a11; sA12 += a12; sA22 += a22;
+        }
+        __syncwarp();
+        sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
+        const float A11 = __fmul_rn(__ll2float_rn(sA11), FLT_SCALE);
+        const float A12 = __fmul_rn(__ll2float_rn(sA12), FLT_SCALE);
+        const float A22 = __fmul_rn(__ll2float_rn(sA22), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * winW * winH));
+        if (a.flags & IBT_LK_GET_MIN_EIGENVALS) err = minEig;
+        if (minEig < a.minEigThr || D < 1.1920929e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, halfx); ny = __fsub_rn(ny, halfy);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < a.maxCount; j++) {
+            const int inx = cv_floor(nx), iny = cv_floor(ny);
+            if (window_oob(inx, iny, winW, winH, rows, cols)) {
+                if (level == 0) status = 0;
+                break;
+            }
+            bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
+            long long sb1, sb2;
+            const bool inside = inx >= 0 && iny >= 0 && inx + winW < cols && iny + winH < rows;
+            if (inside) window_pass<0, true>(LJ, a, inx, iny, iw00, iw01, iw10, iw11, win, lane, sb1, sb2);
+            else window_pass<0, false>(LJ, a, inx, iny, iw00, iw01, iw10, iw11, win, lane, sb1, sb2);
+            ++iters;
+            const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE);
+            const float b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            ox = __fadd_rn(nx, halfx); oy = __fadd_rn(ny, halfy);
+            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= a.eps2) break;
+            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) < 0.01f && fabsf(__fadd_rn(dy, pdy)) < 0.01f) {
+                ox = __fsub_rn(ox, __fmul_rn(dx, 0.5f)); oy = __fsub_rn(oy, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0 && !(a.flags & IBT_LK_GET_MIN_EIGENVALS)) {
+            const float qx = __fsub_rn(ox, halfx), qy = __fsub_rn(oy, halfy);
+            const int iqx = cv_floor(qx), iqy = cv_floor(qy);
+            if (window_oob(iqx, iqy, winW, winH, rows, cols)) { status = 0; err = 0.f; continue; }
+            bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), iw00, iw01, iw10, iw11);
+            long long s1, s2;
+            window_pass<1, false>(LJ, a, iqx, iqy, iw00, iw01, iw10, iw11, win, lane, s1, s2);
+            err = __fdiv_rn(__ll2float_rn(s2), (float)(32 * winW * winH));
+        }
+        __syncwarp();
+    }
+    if (!status && !(a.flags & IBT_LK_GET_MIN_EIGENVALS)) err = 0.f;
+}
+
+__global__ void __launch_bounds__(128)
+lk_kernel(const __grid_constant__ LKArgs a)
+{
+    extern __shared__ uint2 lk_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int k = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (k >= a.n) return;
+    if (a.alive && !a.alive[k]) return;
+    uint2 *win = lk_smem + (size_t)wib * (a.nstrips * a.winH * 32);
+
+    const float p0x = a.p0[2 * k], p0y = a.p0[2 * k + 1];
+    float ox = 0.f, oy = 0.f, err;
+    int status, it_f = 0, it_b = 0;
+    const bool use_init = (a.flags & IBT_LK_USE_INITIAL_FLOW) != 0;
+    if (use_init) { ox = a.p1[2 * k]; oy = a.p1[2 * k + 1]; }
+    lk_point(a.A, a.B, a, p0x, p0y, use_init, ox, oy, status, err, it_f, win, lane);
+    if (lane == 0) {
+        a.p1[2 * k] = ox; a.p1[2 * k + 1] = oy;
+        if (a.st1) a.st1[k] = (uint8_t)status;
+        if (a.err1) a.err1[k] = err;
+    }
+    if (a.fb) {
+        const float p1x = ox, p1y = oy;
+        float rx = 0.f, ry = 0.f;
+        lk_point(a.B, a.A, a, p1x, p1y, false, rx, ry, status, err, it_b, win, lane);
+        if (lane == 0) {
+            if (a.p0r) { a.p0r[2 * k] = rx; a.p0r[2 * k + 1] = ry; }
+            if (a.st0) a.st0[k] = (uint8_t)status;
+            if (a.err0) a.err0[k] = err;
+            const float d = hypotf(fabsf(__fsub_rn(p0x, rx)), fabsf(__fsub_rn(p0y, ry)));
+            if (a.fbdist) a.fbdist[k] = d;
+            if (a.alive) a.alive[k] = (d < a.fb_thresh) ? 1 : 0;
+        }
+    }
+    if (lane == 0) {
+        if (a.iters) {
+            if (a.fb) { a.iters[2 * k] = it_f; a.iters[2 * k + 1] = it_b; }
+            else a.iters[k] = it_f;
+        }
+        if (a.iter_total) atomicAdd(a.iter_total, (unsigned long long)(it_f + it_b));
+    }
+}
+
+static int fill_pyr(const ibt_pyramid_t *p, LKPyr &o, bool need_deriv)
+{
+    if (!p || p->nlevels < 1 || p->nlevels > IBT_MAX_LEVELS) return IBT_E_INVALID;
+    o.nlevels = p->nlevels;
+    for (int l = 0; l < p->nlevels; l++) {
+        if (!p->img[l] || p->rows[l] <= 0 || p->cols[l] <= 0 || p->img_pitch[l] < p->cols[l] ||
+            p->img_pitch[l] > 0x7fffffff)
+            return IBT_E_INVALID;
+        if (need_deriv && (!p->deriv[l] || p->deriv_pitch[l] % 4 != 0 || p->deriv_pitch[l] < (int64_t)p->cols[l] * 4 ||
+                           reinterpret_cast<uintptr_t>(p->deriv[l]) % 4 != 0))
+            return IBT_E_INVALID;
+        o.lv[l].img = p->img[l];
+        o.lv[l].deriv = reinterpret_cast<const uint32_t *>(p->deriv[l]);
+        o.lv[l].img_pitch = (int)p->img_pitch[l];
+        o.lv[l].deriv_pitch = (int)(p->deriv_pitch[l] / 4);
+        o.lv[l].rows = p->rows[l];
+        o.lv[l].cols = p->cols[l];
+    }
+    return IBT_OK;
+}
+
+static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, int winW, int winH, int max_count,
+                     double epsilon, double min_eig, cudaStream_t st)
+{
+    if (a.n < 0 || winW < 3 || winH < 3 || winW > IBT_MAX_WIN || winH > IBT_MAX_WIN) return IBT_E_INVALID;
+    if (a.n == 0) return IBT_OK;
+    if (!a.p0 || !a.p1) return IBT_E_INVALID;
+    int rc = fill_pyr(A, a.A, true);
+    if (rc) return rc;
+    rc = fill_pyr(B, a.B, a.fb != 0);
+    if (rc) return rc;
+    if (A->nlevels != B->nlevels) return IBT_E_INVALID;
+    for (int l = 0; l < A->nlevels; l++)
+        if (A->rows[l] != B->rows[l] || A->cols[l] != B->cols[l]) return IBT_E_INVALID;
+    a.winW = winW; a.winH = winH;
+    a.nstrips = (winW + 30) / 31;
+    a.strip_cols = (winW + a.nstrips - 1) / a.nstrips;
+    a.maxCount = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
+    if (epsilon < 0) epsilon = 0;
+    if (epsilon > 10) epsilon = 10;
+    a.eps2 = (float)(epsilon * epsilon);
+    a.minEigThr = (float)min_eig;
+    const size_t per_warp = (size_t)a.nstrips * winH * 32 * sizeof(uint2);
+    int wpc = 4;
+    while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
+    const size_t smem = per_warp * wpc;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        smem_set = 200 * 1024;
+    }
+    const int blocks = (a.n + wpc - 1) / wpc;
+    lk_kernel<<<blocks, wpc * 32, smem, st>>>(a);
+    return check_launch("ibt_lk");
+}
+
+} // namespace ibt
+
+IBT_API int ibt_lk(const ibt_pyramid_t *pyrI, const ibt_pyramid_t *pyrJ, const float *pts, float *next_pts, int N,
+                   int winW, int winH, int max_count, double epsilon, double min_eig_threshold, int flags,
+                   uint8_t *status, float *err, int32_t *iters, void *stream)
+{
+    ibt::LKArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p0 = pts; a.n = N; a.flags = flags; a.fb = 0;
+    a.p1 = next_pts; a.st1 = status; a.err1 = err; a.iters = iters;
+    return ibt::launch_lk(a, pyrI, pyrJ, winW, winH, max_count, epsilon, min_eig_threshold, static_cast<cudaStream_t>(stream));
+}
+
+IBT_API int ibt_lk_fb(const ibt_pyramid_t *prev, const ibt_pyramid_t *next, const float *p0, int N, int winW, int winH,
+                      int max_count, double epsilon, double min_eig_threshold, float fb_threshold, float *p1,
+                      uint8_t *st1, float *err1, float *p0r, uint8_t *st0, float *err0, float *fbdist, uint8_t *alive,
+                      int32_t *iters, unsigned long long *iter_total, void *stream)
+{
+    ibt::LKArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p0 = p0; a.n = N; a.flags = 0; a.fb = 1; a.fb_thresh = fb_threshold;
+    a.p1 = p1; a.st1 = st1; a.err1 = err1; a.p0r = p0r; a.st0 = st0; a.err0 = err0;
+    a.fbdist = fbdist; a.alive = alive; a.iters = iters; a.iter_total = iter_total;
+    return ibt::launch_lk(a, prev, next, winW, winH, max_count, epsilon, min_eig_threshold, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,288 @@
+"""The reference's frame loop on the GPU, behind the reference's own worker signatures.
+
+    SequenceTracker            device-resident state of one tracking group (seed frame + track_len pairs)
+    track_sequence(...)        s1_lucaskanade_tracking.py:296-450 (loop, FB prune, group save, re-seed)
+    lucaskanade_tracking(...)  s1_lucaskanade_tracking.py:234-236 (same positional arguments)
+    LucasKanade(...).run()     s0_1_test_lucaskanade_tracking.py:29-181 (same constructor, same printed counts)
+
+What differs from the reference by design (SURVEY.md Appendix C "N"): every frame's pyramid + Scharr planes are
+built once and cached (the reference rebuilds them 4x per pair inside cv2); forward LK, backward LK and the FB check
+are one kernel launch; tracks live in time-major device arrays with an alive mask and become the (M,T+1,2)/(M,T)
+float32 arrays of the .npz file by one compaction at the group boundary instead of per-track Python lists.
+Plotting, movie making and JPEG deletion (s1:397-434, 452-479) are outside the hot path and are not implemented.
+"""
+import ctypes as C
+import datetime as dt
+import glob
+import os
+import os.path as osp
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import cv
+
+# s1_lucaskanade_tracking.py:240-248 == s0_1_test_lucaskanade_tracking.py:37-45
+FEATURE_PARAMS = dict(maxCorners=50000000, qualityLevel=0.007, minDistance=10, blockSize=10)
+LK_PARAMS = dict(winSize=(35, 35), maxLevel=4,
+                 criteria=(cv.TERM_CRITERIA_EPS | cv.TERM_CRITERIA_COUNT, 25, 0.03))
+
+
+def load_image(path):
+    """np.array(Image.open(image)) (s1:310): (H,W,3) u8 RGB on the host.  `.npy` frames are accepted too."""
+    path = str(path)
+    if path.endswith(".npy"):
+        return np.load(path)
+    from PIL import Image
+    return np.array(Image.open(path))
+
+
+class FrameStager:
+    """Pinned double buffer + copy stream: the host->device copy of frame t+1 overlaps the kernels of frame t."""
+
+    def __init__(self, device):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self._pinned = [None, None]
+        self._k = 0
+
+    def upload(self, frame):
+        """host (H,W,C) u8 numpy / torch CPU tensor -> device tensor, asynchronously on the copy stream.
+        Returns (device_tensor, event); wait on the event before consuming."""
+        t = torch.from_numpy(np.ascontiguousarray(frame)) if isinstance(frame, np.ndarray) else frame.contiguous()
+        k = self._k
+        self._k ^= 1
+        buf = self._pinned[k]
+        if buf is None or buf[0].shape != t.shape:
+            buf = (torch.empty(t.shape, dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+            self._pinned[k] = buf
+        host, free_ev = buf
+        free_ev.synchronize()                    # the previous copy out of this pinned buffer has finished
+        host.copy_(t)
+        with torch.cuda.stream(self.copy_stream):
+            dev = host.to(self.device, non_blocking=True)
+            free_ev.record(self.copy_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return dev, ev
+
+
+class SequenceTracker:
+    """Device-side state of the tracking loop.  One instance per GPU."""
+
+    def __init__(self, feature_params=None, lk_params=None, fb_threshold=1.0, device=None, count_iterations=False):
+        self.feature_params = dict(FEATURE_PARAMS if feature_params is None else feature_params)
+        self.lk_params = dict(LK_PARAMS if lk_params is None else lk_params)
+        self.fb_threshold = float(fb_threshold)
+        self.device = cv._device() if device is None else torch.device(device)
+        self.stager = FrameStager(self.device)
+        self.iter_total = torch.zeros((1,), dtype=torch.int64, device=self.device) if count_iterations else None
+        self.n = 0                 # seeds of the current group
+        self.steps = 0             # pairs tracked in the current group
+        self.T = 0
+        self._tracks = self._quality = self._alive = None
+
+    # -- frames ---------------------------------------------------------------------------------------
+    def prepare(self, frame):
+        """frame (H,W,3|4) u8 RGB (host numpy / device tensor) or (H,W) u8 gray -> FramePyramid with derivatives.
+        = np.array(Image.open(...)) upload + cv2.cvtColor (s1:310-311) + the pyramids cv2 builds inside LK."""
+        if isinstance(frame, np.ndarray) or (isinstance(frame, torch.Tensor) and not frame.is_cuda):
+            dev, ev = self.stager.upload(frame)
+            torch.cuda.current_stream().wait_event(ev)
+            dev.record_stream(torch.cuda.current_stream())
+            frame = dev
+        gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY) if frame.ndim == 3 else frame
+        return cv.FramePyramid(gray, self.lk_params["winSize"], self.lk_params["maxLevel"], True)
+
+    # -- group life cycle -----------------------------------------------------------------------------
+    def seed(self, pyr, mask=None, track_len=2, points=None):
+        """Re-seed (s1:437-448): Shi-Tomasi corners of the frame (or the given (N,1,2) points) start a new group."""
+        if points is None:
+            p = cv.goodFeaturesToTrack(pyr.levels[0], mask=mask, **self.feature_params)
+        else:
+            p = cv._to_dev(points, np.float32, "seed points")
+        self.T = int(track_len)
+        self.steps = 0
+        self.n = 0 if p is None else p.numel() // 2
+        n = self.n
+        if n == 0:
+            self._tracks = self._quality = self._alive = None
+            return 0
+        self._tracks = torch.empty((self.T + 1, n, 2), dtype=torch.float32, device=self.device)
+        self._tracks[0] = p.reshape(n, 2)
+        self._quality = torch.zeros((self.T, n), dtype=torch.float32, device=self.device)
+        self._alive = torch.ones((n,), dtype=torch.uint8, device=self.device)
+        return n
+
+    def track(self, prev_pyr, cur_pyr):
+        """One frame pair (s1:313-359): LK forward, LK backward, FB distance, prune -- one kernel launch."""
+        if self.n == 0:
+            return
+        if self.steps >= self.T:
+            raise RuntimeError("group is full: seed() again (the reference re-seeds every track_len frames, s1:362)")
+        t = self.steps
+        cnt, eps = cv._criteria(self.lk_params["criteria"])
+        w = self.lk_params["winSize"]
+        p = cv._ptr
+        N.check(N.lib().ibt_lk_fb(C.byref(prev_pyr.c), C.byref(cur_pyr.c), p(self._tracks[t]), self.n, int(w[0]), int(w[1]),
+                                  cnt, eps, float(self.lk_params.get("minEigThreshold", 1e-4)), self.fb_threshold,
+                                  p(self._tracks[t + 1]), None, None, None, None, None, p(self._quality[t]),
+                                  p(self._alive), None, p(self.iter_total), cv._stream()), "ibt_lk_fb")
+        self.steps += 1
+
+    def harvest(self, to_host=True):
+        """Surviving tracks of the current group: tracks (M, steps+1, 2) f32, trackquality (M, steps) f32 in seed order
+        (what np.savez receives at s1:395).  M == 0 -> two empty (0,) float64 arrays, like np.array([])."""
+        empty = (np.zeros((0,), np.float64), np.zeros((0,), np.float64))
+        if self.n == 0:
+            return empty
+        if self.steps == 0:
+            tr = self._tracks[0].reshape(self.n, 1, 2)
+            q = torch.zeros((self.n, 0), dtype=torch.float32, device=self.device)
+            return (tr.cpu().numpy(), q.cpu().numpy()) if to_host else (tr, q)
+        n, k = self.n, self.steps
+        scratch = torch.empty((n + 1,), dtype=torch.int32, device=self.device)
+        out_t = torch.empty((n, k + 1, 2), dtype=torch.float32, device=self.device)
+        out_q = torch.empty((n, k), dtype=torch.float32, device=self.device)
+        cnt = C.c_int(0)
+        p = cv._ptr
+        N.check(N.lib().ibt_tracks_compact(p(self._tracks), p(self._quality), p(self._alive), n, k, p(scratch), p(out_t),
+                                           p(out_q), C.byref(cnt), cv._stream()), "ibt_tracks_compact")
+        m = cnt.value
+        if m == 0:
+            return empty
+        if to_host:
+            return out_t[:m].cpu().numpy(), out_q[:m].cpu().numpy()
+        return out_t[:m], out_q[:m]
+
+    def alive_count(self):
+        return 0 if self.n == 0 else int(self._alive.sum().item())
+
+
+# -----------------------------------------------------------------------------------------------------
+def npz_name(seed_path, track_len, track_len_sec):
+    """s1:394 -- note path.split('.')[0] (kept: dotted directory names break it in the reference too)."""
+    return '{}_{}sec_at_{}sec_tracks.npz'.format(str(seed_path).split('.')[0], track_len * track_len_sec, track_len_sec)
+
+
+def group_time_ok(paths, track_len_sec):
+    """s1:368-390: every consecutive gap of the group's frames must be track_len_sec + {-2..2} s, parsed from
+    '%Y%m%d-%H%M%S.jpg' names; uses timedelta.seconds like the reference."""
+    times = [dt.datetime.strptime(osp.basename(str(p)), '%Y%m%d-%H%M%S.jpg') for p in paths]
+    for a, b in zip(times[:-1], times[1:]):
+        if (b - a).seconds not in [track_len_sec - 2, track_len_sec - 1, track_len_sec, track_len_sec + 1, track_len_sec + 2]:
+            return False
+    return True
+
+
+def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), feature_params=None, lk_params=None,
+                   save=True, loader=load_image, tracker=None, check_time=True, on_group=None, first_group=0,
+                   n_groups=None):
+    """The loop of s1:296-450 over `imagelist` (paths, or in-memory frames when loader is None).
+    Returns the list of (seed_index, npz_path_or_None, tracks, trackquality) of every completed group.
+
+    first_group / n_groups select a contiguous block of groups (time-block sharding): group g of start s
+    covers frames s+g*T .. s+(g+1)*T; a block needs one halo frame shared with the next block."""
+    T = int(track_len)
+    trk = tracker or SequenceTracker(feature_params, lk_params)
+    if mask is not None:
+        mask = cv._to_dev(mask, np.uint8, "mask")
+    results = []
+    for start in startlist:
+        frames = imagelist[start:]
+        total_groups = max(0, (len(frames) - 1) // T)
+        g0 = first_group
+        g1 = total_groups if n_groups is None else min(total_groups, first_group + n_groups)
+        if g1 <= g0:
+            continue
+        prev = None
+        seed_idx = None
+        for counter in range(g0 * T, g1 * T + 1):
+            item = frames[counter]
+            cur = trk.prepare(loader(item) if loader is not None else item)
+            if prev is not None and trk.n > 0:
+                trk.track(prev, cur)
+            if (counter - g0 * T) % T == 0:
+                if seed_idx is not None:
+                    tracks, quality = trk.harvest()
+                    path = None
+                    ok = True
+                    if check_time and loader is not None:
+                        ok = group_time_ok(frames[counter - T: counter + 1], track_len_sec)
+                    if ok and save and loader is not None:
+                        path = npz_name(frames[seed_idx], T, track_len_sec)
+                        np.savez(path, tracks=tracks, trackquality=quality)
+                    if ok:
+                        results.append((start + seed_idx, path, tracks, quality))
+                        if on_group is not None:
+                            on_group(start + seed_idx, tracks, quality)
+                if counter < g1 * T:
+                    trk.seed(cur, mask, T)
+                    seed_idx = counter
+            prev = cur
+    return results
+
+
+def lucaskanade_tracking(file_path, ws_source, ws_target, camname, track_len, track_len_sec, startlist, mask_switch,
+                         plot_switch, movie_switch, delete_jpgs_switch, paramfile_path, n_proc, camera=None):
+    """Same positional signature as s1_lucaskanade_tracking.py:234-236; side effect = the .npz files of SURVEY A.8.
+    `camera` (keyword, optional) injects a ready camera.Camera instead of reading `paramfile_path`.
+    plot_switch / movie_switch / delete_jpgs_switch are accepted and ignored (matplotlib / mencoder work, out of scope)."""
+    from .camera import Camera
+    ws_source, ws_target = str(ws_source), str(ws_target)
+    datestring = osp.basename(ws_source)
+    cam = camera or Camera(camname=camname, date=datestring, paramfile_path=paramfile_path, mask=mask_switch)
+    imagelist = sorted(glob.glob(ws_source + '/*.jpg'))
+    if len(imagelist) <= track_len:                                    # s1:262
+        return
+    if not osp.isdir(ws_target):
+        os.makedirs(ws_target)
+    cam.crop_image_parallel(imagelist, ws_target, n_proc)              # s1:272
+    imagelist = sorted(glob.glob(ws_target + '/*.jpg'))                # s1:278
+    first = load_image(imagelist[0])
+    h, w = first.shape[:2]
+    if mask_switch == 1:                                               # s1:285-294
+        mask = cam.mask_image(h, w)
+    else:
+        mask = np.full((h, w), 255, np.uint8)
+    track_sequence(imagelist, mask, track_len, track_len_sec, startlist)
+
+
+class LucasKanade:
+    """s0_1_test_lucaskanade_tracking.py:29-181 without the plots: same constructor, same printed track counts,
+    `self.tracks` ends up as the same list of lists of (x, y) vertices."""
+
+    def __init__(self, workspace, detect_interval, time_spacing):
+        from pathlib import Path
+        workspace = Path(workspace)
+        self.detect_interval = detect_interval
+        self.time_spacing = time_spacing
+        self.feature_params = dict(FEATURE_PARAMS)
+        self.lk_params = dict(LK_PARAMS)
+        self.track_len = self.detect_interval
+        self.tracks = []
+        self.imagelist = sorted(workspace.glob('*.jpg'))
+        self.distthreshold = 1.0
+        self.mask = 0
+        self.date = workspace.parts[-1]
+        self.workspace = workspace
+        self.track_counts = []
+
+    def run(self):
+        trk = SequenceTracker(self.feature_params, self.lk_params, fb_threshold=self.distthreshold)
+        prev = None
+        for counter, image in enumerate(self.imagelist):
+            cur = trk.prepare(load_image(image))
+            if prev is not None and trk.n > 0:
+                trk.track(prev, cur)
+            if counter % self.detect_interval == 0:
+                n_alive = trk.alive_count() if counter > 0 else 0
+                self.track_counts.append(n_alive)
+                print('{} tracks'.format(n_alive))
+                trk.seed(cur, None, self.track_len)      # mask is all-255 in the reference (s0_1:73-74)
+            prev = cur
+            self.prev_gray = cur.levels[0]
+            print('{} / {} done...'.format(counter + 1, len(self.imagelist)))
+        tracks, _ = trk.harvest()
+        self.tracks = [[(x, y) for x, y in tr] for tr in tracks] if tracks.ndim == 3 else []

@@ -1,0 +1,157 @@
+/*
+ * ibt.h -- C ABI of libibt.so, the B200 (sm_100a) implementation of the tracking hot path of
+ * glacierbliss/iceberg_tracking_code.
+ *
+ * The reference has no FFI layer on this path: its seam is the Python call boundary of three
+ * OpenCV functions plus the numpy forward-backward arithmetic around them.  Every entry point
+ * below names the reference call site (file:line under /root/reference) it replaces; the
+ * Python host (iceberg_tracking_code_b200/cv.py, tracking.py) binds them with ctypes and keeps
+ * cv2's signatures.  INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter comment says HOST;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) unless stated;
+ *   - no hidden device allocation: scratch comes from the caller (`*_workspace_bytes`);
+ *   - return value 0 = ok, negative = IBT_E_* (ibt_error_string gives text);
+ *   - pitches are in BYTES.
+ */
+#ifndef IBT_H_
+#define IBT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBT_MAX_LEVELS 8          /* maxLevel <= 7 */
+#define IBT_MAX_WIN 63            /* winSize components 3..63 */
+
+#define IBT_OK 0
+#define IBT_E_INVALID (-1)        /* bad argument (shape, range, null pointer) */
+#define IBT_E_CUDA (-2)           /* a CUDA runtime call / kernel launch failed */
+#define IBT_E_WORKSPACE (-3)      /* workspace too small */
+#define IBT_E_CAPACITY (-4)       /* output capacity too small (count is still reported) */
+
+/* flags of ibt_lk / ibt_lk_fb: same values as cv2.OPTFLOW_* */
+#define IBT_LK_USE_INITIAL_FLOW 4
+#define IBT_LK_GET_MIN_EIGENVALS 8
+
+/* coefficient sets of ibt_gray_u8 */
+#define IBT_GRAY_CV4_15BIT 0      /* OpenCV 4.x: (c0*3735 + c1*19235 + c2*9798 + 2^14) >> 15 */
+#define IBT_GRAY_CV3_14BIT 1      /* OpenCV 3.x: (c0*1868 + c1*9617 + c2*4899 + 2^13) >> 14  */
+
+int ibt_version(void);
+const char *ibt_error_string(int code);
+/* text of the last CUDA error seen by this library on the calling thread (HOST string) */
+const char *ibt_last_cuda_error(void);
+
+/* ---- K0: cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)  s1_lucaskanade_tracking.py:283,311;
+ *      s0_1_test_lucaskanade_tracking.py:71,80.  src (H,W,cn) u8, cn = 3 or 4; channel 0
+ *      takes the "B" weight whatever it holds (the reference feeds PIL RGB). */
+int ibt_gray_u8(const uint8_t *src, int H, int W, int cn, int64_t src_pitch,
+                uint8_t *dst, int64_t dst_pitch, int coeffset, void *stream);
+
+/* ---- K1: Gaussian pyramid + Scharr derivative, built inside cv2.calcOpticalFlowPyrLK
+ *      (s1:323,326; s0_1:92,95) == cv2.buildOpticalFlowPyramid / cv2.pyrDown.
+ * ibt_pyramid_levels: HOST helper.  sizes_hw (HOST, 2*(maxLevel+1) ints) receives (h,w) of
+ *      each level kept; returns the effective maxLevel (level l+1 kept only while both dims
+ *      exceed the window, strictly). */
+int ibt_pyramid_levels(int H, int W, int winW, int winH, int maxLevel, int *sizes_hw);
+
+/* One fused level step: reads level l (h x w, u8) once; writes its Scharr planes
+ * (h x w, interleaved int16 dx,dy; pass NULL to skip) and level l+1 (((h+1)/2) x ((w+1)/2), u8;
+ * pass NULL to skip).  Borders REFLECT_101.  deriv_pitch % 16 == 0 and deriv % 16 == 0 enable
+ * the vector store path (any pitch works). */
+int ibt_pyr_level_u8(const uint8_t *src, int h, int w, int64_t src_pitch,
+                     int16_t *deriv, int64_t deriv_pitch,
+                     uint8_t *down, int64_t down_pitch, void *stream);
+
+/* A pyramid as the LK solver consumes it.  HOST struct, passed by pointer, copied at launch. */
+typedef struct ibt_pyramid {
+    int32_t nlevels;                              /* effective maxLevel + 1 */
+    int32_t rows[IBT_MAX_LEVELS], cols[IBT_MAX_LEVELS];
+    const uint8_t *img[IBT_MAX_LEVELS];           /* level images, u8 */
+    int64_t img_pitch[IBT_MAX_LEVELS];
+    const int16_t *deriv[IBT_MAX_LEVELS];         /* Scharr planes (may be NULL for a J-only pyramid) */
+    int64_t deriv_pitch[IBT_MAX_LEVELS];          /* bytes, multiple of 4 */
+} ibt_pyramid_t;
+
+/* Whole pyramid of one frame: pyr->img[0] is the caller's gray frame (not copied);
+ * pyr->img[1..] and pyr->deriv[0..] are caller-allocated outputs.  with_derivs = 0 skips
+ * the Scharr planes. */
+int ibt_pyramid_build(const ibt_pyramid_t *pyr, int with_derivs, void *stream);
+
+/* ---- K3: cv2.calcOpticalFlowPyrLK(img0, img1, p0, None, **lk_params)  s1:323 (forward),
+ *      s1:326 (backward); s0_1:92,95.  One pass, I = pyrI (needs deriv), J = pyrJ.
+ *      pts (N,2) f32; next_pts (N,2) f32 out (in/out with IBT_LK_USE_INITIAL_FLOW);
+ *      status (N) u8; err (N) f32 (0 where status == 0; cv2 leaves garbage there);
+ *      iters (N) i32 or NULL: inner Newton iterations executed, summed over levels.
+ *      max_count/epsilon are the TERM_CRITERIA values after cv2's defaults were applied
+ *      (clamped here to [0,100] / [0,10] like cv2). */
+int ibt_lk(const ibt_pyramid_t *pyrI, const ibt_pyramid_t *pyrJ,
+           const float *pts, float *next_pts, int N,
+           int winW, int winH, int max_count, double epsilon, double min_eig_threshold, int flags,
+           uint8_t *status, float *err, int32_t *iters, void *stream);
+
+/* Forward + backward pass and the forward-backward check in ONE launch:
+ *   p1,st1,err1   = LK(prev -> next, p0)             s1:323
+ *   p0r,st0,err0  = LK(next -> prev, p1)             s1:326
+ *   fbdist        = hypot(|p0 - p0r|)                s1:329-330 (status is NOT consulted, as in the reference)
+ *   alive[k]     &= fbdist < fb_threshold            s1:333, 340-359 (track kept or dropped)
+ * alive (N) u8 in/out or NULL (all alive; no write).  Points with alive == 0 are skipped and
+ * their outputs left untouched.  iters (N,2) i32 or NULL (fwd, bwd).  iter_total: one u64 or
+ * NULL, atomically incremented by the iterations executed (the BASELINE.md unit).
+ * Any of st1, err1, st0, err0 may be NULL. */
+int ibt_lk_fb(const ibt_pyramid_t *prev, const ibt_pyramid_t *next,
+              const float *p0, int N,
+              int winW, int winH, int max_count, double epsilon, double min_eig_threshold,
+              float fb_threshold,
+              float *p1, uint8_t *st1, float *err1,
+              float *p0r, uint8_t *st0, float *err0,
+              float *fbdist, uint8_t *alive, int32_t *iters, unsigned long long *iter_total,
+              void *stream);
+
+/* ---- K2: cv2.goodFeaturesToTrack(frame_gray, mask=mask, **feature_params)  s1:437; s0_1:167.
+ * cornerMinEigenVal test hook (Sobel3 -> products -> blockSize^2 box sum -> lambda_min). */
+int ibt_min_eigen_f32(const uint8_t *gray, int H, int W, int64_t pitch, int blockSize,
+                      float *eig, int64_t eig_pitch, void *stream);
+
+size_t ibt_gftt_workspace_bytes(int H, int W);
+/* mask may be NULL (all allowed).  out_xy (cap,2) f32 receives integer-valued x,y ordered by
+ * response (ties: higher linear address first), culled by minDistance on cv2's cell grid and
+ * truncated to maxCorners (<= 0: unlimited).  out_count: HOST int*.  SYNCHRONISES `stream`
+ * (the corner count decides the shapes the caller allocates next, like cv2's return value).
+ * Returns IBT_E_CAPACITY (and the full count) if cap was too small. */
+int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
+             int H, int W, int maxCorners, double qualityLevel, double minDistance, int blockSize,
+             void *workspace, size_t workspace_bytes,
+             float *out_xy, int cap, int *out_count, void *stream);
+
+/* ---- track bookkeeping at a group boundary (s1:362-395): stable compaction of the live
+ * tracks.  tracks_tm (T+1, N, 2) f32 time-major, quality_tm (T, N) f32, alive (N) u8 ->
+ * out_tracks (M, T+1, 2) f32, out_quality (M, T) f32 in seed order.  scratch: (N+1) int32.
+ * out_count: HOST int*; SYNCHRONISES `stream`. */
+int ibt_tracks_compact(const float *tracks_tm, const float *quality_tm, const uint8_t *alive,
+                       int N, int T, int32_t *scratch, float *out_tracks, float *out_quality,
+                       int *out_count, void *stream);
+
+/* ---- K4: Camera.photocords_cropped_to_uncropped + Camera.photo_to_utm
+ *      imports/camtools.py:414-421, 286-332, called per vertex at s2_cam_to_utm.py:247-254.
+ * xy (n,2) f32 track vertices in cropped-image pixels; cam: HOST, 12 doubles
+ * { crop_left, crop_top, image_width, image_height, sigma_px, H_cam, theta, phi, psi (radians),
+ *   easting, northing, reserved }.  EN (n,2) f64.  All arithmetic in fp64. */
+int ibt_photo_to_utm(const float *xy, int64_t n, const double *cam, double *EN, void *stream);
+
+/* ---- mask: Camera.mask_meshgrid (imports/camtools.py:184-211) as used at s1:285-294: rasterise the (already
+ *      crop-shifted) water polygon over the H x W pixel centres.  poly_xy: DEVICE (E,2) f64, 3 <= E <= 2048,
+ *      implicitly closed; crossing-number rule of matplotlib.path.Path.contains_points (radius 0).
+ *      out[y*pitch + x] = inside ? inside_value : 0. */
+int ibt_polygon_mask(const double *poly_xy, int E, int H, int W, uint8_t *out, int64_t pitch, int inside_value,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBT_H_ */
