@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- tracking hot path throughput on B200 (contract: see the task prompt / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload = BASELINE.json configs[1]: 24 MP (6000x4000) synthetic frames, 20 000 Shi-Tomasi points, winSize 31,
+maxLevel 4, criteria (EPS|COUNT, 30, 0.01), forward-backward check < 1 px.
+
+One STEP = the body of the reference's frame loop for one new frame (s1_lucaskanade_tracking.py:310-359):
+    cvtColor(new frame)  ->  [pyramid + Scharr planes of the new frame]  ->  LK forward  ->  LK backward  ->  FB check
+against the previous frame, on 20 000 points.  goodFeaturesToTrack runs once per track_len frames in the reference; it
+is timed separately ("gftt_ms").  metric = tracked points / s (= 20 000 x frame pairs / s).
+
+  value : inputs (RGB frames, points) resident in HBM; CUDA events on the launch stream; max over ranks.
+  e2e   : the public host API (SequenceTracker.upload/prepare/track) with PINNED HOST frames: every step copies its
+          72 MB RGB frame host->device and reads p1 / FB distance / alive back to the host, inside the timed region.
+  --impl reference : the reference's own CPU implementation of the same step -- the cv2 calls of s1:311,323,326 +
+          the numpy FB arithmetic of s1:329-333 -- on the host cores (falls back to the C oracle port when cv2 is absent).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, NPTS = 4000, 6000, 20000
+LK = dict(winSize=(31, 31), maxLevel=4, criteria=(3, 30, 0.01))
+GFTT = dict(maxCorners=NPTS, qualityLevel=0.007, minDistance=10, blockSize=10)
+NFRAMES = 6                    # distinct frames in rotation: 6 x 72 MB RGB = 432 MB  >  126 MB L2
+SEED = 7
+WORKLOAD = "config2: 6000x4000 synthetic pair stream, 20k Shi-Tomasi pts, win 31, maxLevel 4, (3,30,0.01), FB<1px"
+
+
+def pingpong(i):
+    """frame index sequence 0,1,..,F-1,F-2,..,1,0,1,.. : consecutive frames always differ by one time step"""
+    p = 2 * (NFRAMES - 1)
+    k = i % p
+    return k if k < NFRAMES else p - k
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (NVML; nvidia-smi as fallback)."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                      # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:                   # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:                       # noqa: BLE001
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def make_frames(device):
+    """NFRAMES RGB frames (H,W,3) u8 generated ON DEVICE (never shipped from the host in the device-timed loop)."""
+    import torch
+    from iceberg_tracking_code_b200 import synthetic as syn
+    base = syn.base_texture(H, W, SEED, device=device)
+    frames = [syn.frame_rgb(base, t, seed=SEED) for t in range(NFRAMES)]
+    del base
+    torch.cuda.empty_cache()
+    return frames
+
+
+def cpu_step_fn():
+    """The reference's per-frame CPU work (s1:311,323,326,329-333) as a callable; prefers cv2 (the dependency the
+    reference itself calls), else the C oracle port."""
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count())
+        kind, cores = "reference", cv2.getNumThreads()
+        m = cv2
+        desc = "cv2 %s (the OpenCV the reference calls), %d threads" % (cv2.__version__, cores)
+    except Exception:                               # noqa: BLE001
+        from oracle import oracle as m
+        m.build()
+        kind, cores = "port", 1
+        desc = "oracle/ibt_oracle.c scalar port, 1 thread"
+
+    def step(prev_gray, rgb, p0):
+        gray = m.cvtColor(rgb, 6)
+        p1, st, err = m.calcOpticalFlowPyrLK(prev_gray, gray, p0, None, **LK)
+        p0r, st, err = m.calcOpticalFlowPyrLK(gray, prev_gray, p1, None, **LK)
+        diff = abs(p0 - p0r).reshape(-1, 2)
+        dist = np.hypot(diff[:, 0], diff[:, 1])
+        return gray, p1, dist < 1
+    return step, m, kind, cores, desc
+
+
+def run_cpu(frames_np, grays_np, pts_np, steps, warmup, budget_s=None):
+    step, m, kind, cores, desc = cpu_step_fn()
+    t_total, done = 0.0, 0
+    for i in range(warmup + steps):
+        a, b = pingpong(i), pingpong(i + 1)
+        t0 = time.perf_counter()
+        step(grays_np[a], frames_np[b], pts_np[a])
+        dt_ = time.perf_counter() - t0
+        if i >= warmup:
+            t_total += dt_
+            done += 1
+            if budget_s is not None and t_total > budget_s:
+                break
+    return dict(value=NPTS * done / t_total, unit="points/s", cores=cores, kind=kind,
+                sample="%d frame pairs of the same workload (%s), %.2f s" % (done, desc, t_total),
+                pairs_per_s=done / t_total), done, t_total
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = max(1, args.steps), max(3, args.warmup) if args.impl == "ours" else max(0, args.warmup)
+
+    import torch
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return main_reference(args, steps, warmup)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from iceberg_tracking_code_b200 import build
+    build.build()
+    from iceberg_tracking_code_b200 import cv
+    from iceberg_tracking_code_b200.tracking import SequenceTracker
+
+    # ---- setup (untimed): frames on device, per-frame seeds, pyramids ------------------------------------------
+    frames = make_frames(dev)
+    grays = [cv.cvtColor(f, cv.COLOR_BGR2GRAY) for f in frames]
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    pts, gftt_ms = [], []
+    for g in grays:
+        t0.record()
+        p = cv.goodFeaturesToTrack(g, **GFTT)
+        t1.record(); torch.cuda.synchronize()
+        gftt_ms.append(t0.elapsed_time(t1))
+        assert p is not None and p.shape[0] == NPTS, "synthetic scene must yield %d corners" % NPTS
+        pts.append(p.reshape(NPTS, 2).contiguous())
+    trk = SequenceTracker(GFTT, LK, count_iterations=True)
+    pyr = [cv.FramePyramid(grays[0], LK["winSize"], LK["maxLevel"], True),
+           cv.FramePyramid(grays[1], LK["winSize"], LK["maxLevel"], True)]
+    nlev = pyr[0].maxLevel + 1
+    p1 = torch.empty((NPTS, 2), dtype=torch.float32, device=dev)
+    fbd = torch.empty((NPTS,), dtype=torch.float32, device=dev)
+
+    def device_step(i, slot, probe=None):
+        """prev pyramid = pyr[slot^1] (frame a), new frame b -> pyr[slot]"""
+        a, b = pingpong(i), pingpong(i + 1)
+        cur = trk.prepare(frames[b], reuse=pyr[slot], probe=probe)
+        cv.lk_fb_into(pyr[slot ^ 1], cur, pts[a], LK, p1, fbd, None, trk.iter_total)
+
+    # pyr[0] must hold frame pingpong(0) before step 0 writes frame pingpong(1) into pyr[1]
+    pyr[0].rebuild(grays[pingpong(0)])
+    own_launches_per_step = 1 + nlev + 1          # gray, one fused pyrDown+Scharr launch per level, fused LK fwd+bwd+FB
+    for i in range(warmup):
+        device_step(i, (i + 1) & 1)
+    torch.cuda.synchronize()
+    # ---- timed region: device-resident inputs ---------------------------------------------------------------------
+    probes = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(local_rank)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    trk.iter_total.zero_()
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(steps):
+        i = warmup + k
+        device_step(i, (i + 1) & 1, probe=probes[k])
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    iters = int(trk.iter_total.item())
+    alive_frac = float((fbd < 1).float().mean().item())
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in probes]))
+
+    # ---- e2e: public API, pinned host frames, H2D + D2H inside the timed region ----------------------------------------
+    host_frames = [f.cpu().pin_memory() for f in frames]
+    h_p1 = torch.empty((NPTS, 2), dtype=torch.float32).pin_memory()
+    h_fbd = torch.empty((NPTS,), dtype=torch.float32).pin_memory()
+
+    def e2e_loop(n, first):
+        handle = trk.upload(host_frames[pingpong(first + 1)])
+        for k in range(n):
+            i = first + k
+            slot = (i + 1) & 1
+            cur = trk.prepare(handle, reuse=pyr[slot])
+            if k + 1 < n:
+                handle = trk.upload(host_frames[pingpong(i + 2)])         # prefetch overlaps this step's kernels
+            cv.lk_fb_into(pyr[slot ^ 1], cur, pts[pingpong(i)], LK, p1, fbd, None, None)
+            h_p1.copy_(p1, non_blocking=True); h_fbd.copy_(fbd, non_blocking=True)
+            torch.cuda.current_stream().synchronize()                     # the caller consumes the step's result
+    pyr[0].rebuild(grays[pingpong(0)])
+    e2e_loop(max(3, warmup // 2) * 2, 0)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    pyr[0].rebuild(grays[pingpong(0)])
+    torch.cuda.synchronize()
+    tw0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(steps, 0)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_wall = (time.perf_counter() - tw0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall)
+    h2d = int(host_frames[0].numel())
+    d2h = int(h_p1.numel() * 4 + h_fbd.numel() * 4)
+
+    # ---- reduce over ranks (max time) -------------------------------------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([ms, e2e_ms, k1_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, k1_ms = [float(v) for v in t.tolist()]
+        it_t = torch.tensor([iters], dtype=torch.int64, device=dev)
+        dist.all_reduce(it_t)
+        iters = int(it_t.item())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:                               # noqa: BLE001
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s")
+    n0 = H * W
+    h1, w1 = (H + 1) // 2, (W + 1) // 2
+    k1_bytes = n0 + 4 * n0 + h1 * w1               # read level 0 once, write (dx,dy) int16, write level 1
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+    value = world * NPTS * steps / (ms * 1e-3)
+    out = {
+        "metric": "tracked points/sec (24MP frame pairs, 20k pts, LK fwd+bwd+FB)", "value": value, "unit": "points/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 2x2 solve", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_in_rotation": NFRAMES,
+                   "l2_policy": "inputs larger than L2: %d distinct 72 MB RGB frames in ping-pong rotation" % NFRAMES,
+                   "step": "cvtColor(new) + pyramid/Scharr(new) + fused LK fwd+bwd+FB vs cached previous pyramid",
+                   "sharding": "independent frame-pair streams per rank, no data-path collective"},
+        "frame_pairs_per_s": world * steps / (ms * 1e-3),
+        "feature_pair_iterations_per_s": iters / (ms * 1e-3),
+        "iterations_per_point_pair": iters / (world * NPTS * steps),
+        "fb_valid_fraction_last_step": alive_frac,
+        "gftt_ms": float(np.median(gftt_ms)),
+        "gpu_launches": own_launches_per_step * steps,
+        "clocks": clocks,
+        "e2e": {"value": world * NPTS * steps / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
+                "api": "SequenceTracker.upload/prepare + fused LK, pinned host frames, p1 + FB distance read back every step"},
+        "roofline": {"kernel": "pyr_level_kernel<deriv,down> level 0 (fused pyrDown + Scharr)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "bytes_per_launch": k1_bytes, "avg_launch_ms": k1_ms, "traffic": None},
+        "lk": {"kernel": "lk_kernel (fwd+bwd+FB, warp per point)", "bound": "issue/shared-memory (not HBM)",
+               "iterations_per_s": iters / (ms * 1e-3), "target_iterations_per_s": 200e6},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            out["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        except Exception:                           # noqa: BLE001
+            pass
+    if world == 1 and not args.no_cpu_baseline:
+        frames_np = [f.numpy() for f in host_frames]
+        grays_np = [g.cpu().numpy() for g in grays]
+        pts_np = [p.cpu().numpy().reshape(-1, 1, 2) for p in pts]
+        cb, _, _ = run_cpu(frames_np, grays_np, pts_np, steps=30, warmup=1, budget_s=15.0)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main_reference(args, steps, warmup):
+    """Reference arm: the CPU path of the reference on this box's host cores, same config / metric / unit."""
+    import torch
+    from iceberg_tracking_code_b200 import synthetic as syn
+    dev = "cuda" if torch.cuda.is_available() else "cpu"          # frame SYNTHESIS only; the timed path is pure CPU
+    base = syn.base_texture(H, W, SEED, device=dev)
+    frames_np = [syn.frame_rgb(base, t, seed=SEED).cpu().numpy() for t in range(NFRAMES)]
+    del base
+    step, m, kind, cores, desc = cpu_step_fn()
+    grays_np = [m.cvtColor(f, 6) for f in frames_np]
+    pts_np = []
+    for g in grays_np:
+        p = m.goodFeaturesToTrack(g, **GFTT)
+        pts_np.append(np.ascontiguousarray(p, np.float32).reshape(-1, 1, 2))
+    steps = min(steps, 40)
+    cb, done, t_total = run_cpu(frames_np, grays_np, pts_np, steps=steps, warmup=min(warmup, 2), budget_s=120.0)
+    out = {
+        "impl": "reference", "metric": "tracked points/sec (24MP frame pairs, 20k pts, LK fwd+bwd+FB)",
+        "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus, "steps": done, "warmup": min(warmup, 2),
+        "ms_per_step": t_total / done * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int16 fixed point + f32 (OpenCV CPU)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_in_rotation": NFRAMES,
+                   "step": "cv2.cvtColor + cv2.calcOpticalFlowPyrLK fwd + bwd + numpy FB (s1:311,323,326,329-333)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

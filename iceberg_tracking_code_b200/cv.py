@@ -150,7 +150,35 @@ class FramePyramid:
                 st.deriv[l] = dbuf.data_ptr()
                 st.deriv_pitch[l] = dpitch
         self.c = st
-        N.check(N.lib().ibt_pyramid_build(C.byref(self.c), 1 if self.with_derivs else 0, _stream()), "ibt_pyramid_build")
+        self._build(None)
+
+    def _build(self, probe):
+        if probe is None:
+            N.check(N.lib().ibt_pyramid_build(C.byref(self.c), 1 if self.with_derivs else 0, _stream()), "ibt_pyramid_build")
+            return
+        # same launches issued level by level so that CUDA events can bracket the level-0 launch (bench.py roofline)
+        c, L = self.c, self.maxLevel + 1
+        for l in range(L):
+            if l == 0:
+                probe[0].record()
+            N.check(N.lib().ibt_pyr_level_u8(c.img[l], c.rows[l], c.cols[l], c.img_pitch[l],
+                                             c.deriv[l] if self.with_derivs else None, c.deriv_pitch[l],
+                                             c.img[l + 1] if l + 1 < L else None, c.img_pitch[l + 1] if l + 1 < L else 0,
+                                             _stream()), "ibt_pyr_level_u8")
+            if l == 0:
+                probe[1].record()
+
+    def rebuild(self, gray, probe=None):
+        """Recompute this pyramid in place for another frame of the same size (no allocation: steady-state loop).
+        probe = (start_event, end_event) records CUDA events around the level-0 launch."""
+        g = _to_dev(gray, np.uint8, "FramePyramid gray")
+        if tuple(g.shape) != tuple(self.sizes[0]):
+            raise error("FramePyramid.rebuild: frame size changed")
+        self._img_buf[0] = g
+        self.levels[0] = g
+        self.c.img[0] = g.data_ptr()
+        self._build(probe)
+        return self
 
     @property
     def shape(self):
@@ -282,6 +310,18 @@ def calcOpticalFlowPyrLK_FB(prev, next, p0, winSize=(21, 21), maxLevel=3,
     if return_iters:
         r["iters"] = _out(iters, as_np)
     return r
+
+
+def lk_fb_into(prev, next, p0, lk_params, p1, fbdist, alive=None, iter_total=None):
+    """Allocation-free form of calcOpticalFlowPyrLK_FB for steady-state loops: prev / next are FramePyramids with
+    derivatives, p0 (N,2) f32, p1 (N,2) f32 and fbdist (N,) f32 are preallocated device tensors; alive (N,) u8 is
+    updated in place when given; iter_total (1,) int64 accumulates the inner iterations executed."""
+    cnt, eps = _criteria(lk_params["criteria"])
+    w = lk_params["winSize"]
+    n = p0.shape[0]
+    N.check(N.lib().ibt_lk_fb(C.byref(prev.c), C.byref(next.c), _ptr(p0), n, int(w[0]), int(w[1]), cnt, eps,
+                              float(lk_params.get("minEigThreshold", 1e-4)), 1.0, _ptr(p1), None, None, None, None, None,
+                              _ptr(fbdist), _ptr(alive), None, _ptr(iter_total), _stream()), "ibt_lk_fb")
 
 
 # ---------------------------------------------------------------------------------------------------

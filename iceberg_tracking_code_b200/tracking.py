@@ -49,20 +49,26 @@ class FrameStager:
 
     def upload(self, frame):
         """host (H,W,C) u8 numpy / torch CPU tensor -> device tensor, asynchronously on the copy stream.
-        Returns (device_tensor, event); wait on the event before consuming."""
+        Returns (device_tensor, event); wait on the event before consuming.  A tensor that is already pinned is
+        copied straight from its own memory (the caller keeps it alive and unchanged until the event fires)."""
         t = torch.from_numpy(np.ascontiguousarray(frame)) if isinstance(frame, np.ndarray) else frame.contiguous()
-        k = self._k
-        self._k ^= 1
-        buf = self._pinned[k]
-        if buf is None or buf[0].shape != t.shape:
-            buf = (torch.empty(t.shape, dtype=torch.uint8).pin_memory(), torch.cuda.Event())
-            self._pinned[k] = buf
-        host, free_ev = buf
-        free_ev.synchronize()                    # the previous copy out of this pinned buffer has finished
-        host.copy_(t)
+        if t.is_pinned():
+            host = t
+            free_ev = None
+        else:
+            k = self._k
+            self._k ^= 1
+            buf = self._pinned[k]
+            if buf is None or buf[0].shape != t.shape:
+                buf = (torch.empty(t.shape, dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+                self._pinned[k] = buf
+            host, free_ev = buf
+            free_ev.synchronize()                # the previous copy out of this pinned buffer has finished
+            host.copy_(t)
         with torch.cuda.stream(self.copy_stream):
             dev = host.to(self.device, non_blocking=True)
-            free_ev.record(self.copy_stream)
+            if free_ev is not None:
+                free_ev.record(self.copy_stream)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         return dev, ev
@@ -84,15 +90,27 @@ class SequenceTracker:
         self._tracks = self._quality = self._alive = None
 
     # -- frames ---------------------------------------------------------------------------------------
-    def prepare(self, frame):
-        """frame (H,W,3|4) u8 RGB (host numpy / device tensor) or (H,W) u8 gray -> FramePyramid with derivatives.
-        = np.array(Image.open(...)) upload + cv2.cvtColor (s1:310-311) + the pyramids cv2 builds inside LK."""
-        if isinstance(frame, np.ndarray) or (isinstance(frame, torch.Tensor) and not frame.is_cuda):
-            dev, ev = self.stager.upload(frame)
+    def upload(self, frame):
+        """Start the host->device copy of a frame on the copy stream; pass the returned handle to prepare()."""
+        return self.stager.upload(frame)
+
+    def prepare(self, frame, reuse=None, probe=None):
+        """frame (H,W,3|4) u8 RGB (host numpy / device tensor / upload() handle) or (H,W) u8 gray -> FramePyramid with
+        derivatives = np.array(Image.open(...)) upload + cv2.cvtColor (s1:310-311) + the pyramids cv2 builds inside LK.
+        reuse: a FramePyramid of the same frame size to rebuild in place (steady state allocates nothing)."""
+        if isinstance(frame, tuple):
+            handle = frame
+        elif isinstance(frame, np.ndarray) or (isinstance(frame, torch.Tensor) and not frame.is_cuda):
+            handle = self.stager.upload(frame)
+        else:
+            handle = None
+        if handle is not None:
+            frame, ev = handle
             torch.cuda.current_stream().wait_event(ev)
-            dev.record_stream(torch.cuda.current_stream())
-            frame = dev
+            frame.record_stream(torch.cuda.current_stream())
         gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY) if frame.ndim == 3 else frame
+        if reuse is not None:
+            return reuse.rebuild(gray, probe)
         return cv.FramePyramid(gray, self.lk_params["winSize"], self.lk_params["maxLevel"], True)
 
     # -- group life cycle -----------------------------------------------------------------------------
