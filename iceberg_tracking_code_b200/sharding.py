@@ -1,0 +1,115 @@
+"""Time-block sharding of the tracking loop across the GPUs of one box.
+
+A *group* = one seed frame + track_len frame pairs (s1_lucaskanade_tracking.py:304-307, 362, 437-448): seeds come from
+the seed frame alone, tracks never outlive the group, the .npz is named after the seed frame -- so groups are
+independent units.  Rank r of R takes a contiguous block of groups (= a contiguous time block of frames plus ONE halo
+frame shared with the next rank) and there is no data-path communication.  The only collective is the final gather
+of the per-group track arrays to rank 0 (`gather_results`; NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+import torch
+
+
+def n_groups(n_frames, track_len, start=0):
+    """Completed groups of a sequence: the loop of s1:307 saves at counter = T, 2T, ... <= n-1."""
+    return max(0, (n_frames - start - 1) // int(track_len))
+
+
+def shard_groups(total_groups, rank, world):
+    """Contiguous block [g0, g0+n) of rank `rank`; the remainder goes to the first ranks."""
+    base, rem = divmod(int(total_groups), int(world))
+    n = base + (1 if rank < rem else 0)
+    g0 = rank * base + min(rank, rem)
+    return g0, n
+
+
+def frame_range(g0, n, track_len, start=0):
+    """Inclusive frame index range [first, last] a block of groups needs (last = halo / next block's seed frame)."""
+    if n <= 0:
+        return None
+    return start + g0 * track_len, start + (g0 + n) * track_len
+
+
+def pack_results(results, track_len):
+    """[(seed_index, path, tracks (M,T+1,2) f32 | (0,) f64, quality)] -> (meta int64 (G,2), tracks f32 (SM,T+1,2),
+    quality f32 (SM,T))."""
+    T = int(track_len)
+    meta = np.zeros((len(results), 2), np.int64)
+    tr, qu = [], []
+    for i, (seed, _path, tracks, quality) in enumerate(results):
+        m = 0 if tracks.ndim != 3 else tracks.shape[0]
+        meta[i] = (seed, m)
+        if m:
+            tr.append(np.asarray(tracks, np.float32).reshape(m, T + 1, 2))
+            qu.append(np.asarray(quality, np.float32).reshape(m, T))
+    tracks = np.concatenate(tr, 0) if tr else np.zeros((0, T + 1, 2), np.float32)
+    quality = np.concatenate(qu, 0) if qu else np.zeros((0, T), np.float32)
+    return meta, tracks, quality
+
+
+def unpack_results(meta, tracks, quality):
+    out, o = [], 0
+    for seed, m in meta.tolist():
+        if m:
+            out.append((int(seed), tracks[o:o + m], quality[o:o + m]))
+        else:
+            out.append((int(seed), np.zeros((0,), np.float64), np.zeros((0,), np.float64)))
+        o += m
+    return out
+
+
+def gather_results(results, track_len, device=None):
+    """The single collective of the path: every rank contributes its groups' track arrays; returns, on EVERY rank,
+    the list [(seed_index, tracks, trackquality)] of all ranks in time order (all_gather of sizes, then all_gather of
+    the padded payloads).  Without an initialised process group this is the identity."""
+    import torch.distributed as dist
+    meta, tracks, quality = pack_results(results, track_len)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return unpack_results(meta, tracks, quality)
+    world = dist.get_world_size()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    T = int(track_len)
+    sizes = torch.tensor([meta.shape[0], tracks.shape[0]], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    gmax, mmax = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+
+    def padded(a, n, dtype):
+        t = torch.zeros((n,) + a.shape[1:], dtype=dtype, device=device)
+        if a.shape[0]:
+            t[:a.shape[0]] = torch.from_numpy(a).to(device)
+        return t
+
+    def allg(t):
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.cpu().numpy() for o in out]
+
+    metas = allg(padded(meta, gmax, torch.int64))
+    trs = allg(padded(tracks, mmax, torch.float32)) if mmax else [np.zeros((0, T + 1, 2), np.float32)] * world
+    qus = allg(padded(quality, mmax, torch.float32)) if mmax else [np.zeros((0, T), np.float32)] * world
+    out = []
+    for r in range(world):
+        g, m = int(all_sizes[r, 0]), int(all_sizes[r, 1])
+        out += unpack_results(metas[r][:g], trs[r][:m], qus[r][:m])
+    out.sort(key=lambda x: x[0])
+    return out
+
+
+def track_sequence_sharded(imagelist, mask, track_len, track_len_sec, start=0, rank=None, world=None, gather=True, **kw):
+    """Run this rank's block of groups of `imagelist` (tracking.track_sequence) and, if asked, gather all ranks'
+    tracks.  Each rank writes its own .npz files (the file set is disjoint by construction)."""
+    import torch.distributed as dist
+    from .tracking import track_sequence
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    total = n_groups(len(imagelist), track_len, start)
+    g0, n = shard_groups(total, rank, world)
+    res = track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(start,), first_group=g0, n_groups=n, **kw) if n else []
+    if not gather:
+        return [(s, t, q) for s, _p, t, q in res]
+    return gather_results(res, track_len)

@@ -1,0 +1,89 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU and exports exactly what include/ibt.h declares."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def so_path():
+    from iceberg_tracking_code_b200 import build
+    return build.build()
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "ibt.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ibt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(so_path):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so_path], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    declared = header_symbols()
+    assert len(declared) >= 15
+    missing = [s for s in declared if s not in exported]
+    assert not missing, "declared in include/ibt.h but not exported: %s" % missing
+    extra = sorted(s for s in exported if s.startswith("ibt_") and s not in declared)
+    assert not extra, "exported but not declared in include/ibt.h: %s" % extra
+
+
+def test_binding_covers_header(so_path):
+    from iceberg_tracking_code_b200 import _native
+    assert sorted(_native.SIGNATURES) == header_symbols()
+    lib = _native.lib()                    # resolves every symbol
+    assert lib.ibt_version() >= 100
+    assert lib.ibt_error_string(0) == b"ok"
+    assert b"invalid" in lib.ibt_error_string(-1)
+
+
+def test_host_only_entry_points(so_path):
+    """ibt_pyramid_levels is pure host code: the level rule of SURVEY A.3 (strict >, both dims)."""
+    from iceberg_tracking_code_b200 import _native
+    lib = _native.lib()
+    sizes = (C.c_int * 16)()
+    assert lib.ibt_pyramid_levels(4000, 6000, 31, 31, 4, sizes) == 4
+    assert list(sizes)[:10] == [4000, 6000, 2000, 3000, 1000, 1500, 500, 750, 250, 375]
+    assert lib.ibt_pyramid_levels(140, 140, 35, 35, 4, sizes) == 1
+    assert lib.ibt_pyramid_levels(142, 142, 35, 35, 4, sizes) == 2
+    assert lib.ibt_pyramid_levels(100, 120, 35, 35, 4, sizes) == 1
+    assert lib.ibt_pyramid_levels(10, 10, 35, 35, 9, sizes) == _native.IBT_E_INVALID
+
+
+def test_struct_layout_matches_header():
+    from iceberg_tracking_code_b200 import _native
+    # int32 nlevels + 2*8 int32 + pad to 8 + 4 * 8 * 8 bytes
+    assert C.sizeof(_native.ibt_pyramid_t) == 4 + 64 + 4 + 4 * 64
+    assert _native.ibt_pyramid_t.img.offset == 72
+
+
+def test_sass_is_sm100(so_path):
+    out = subprocess.run(["cuobjdump", "-lelf", so_path], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out.stdout
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    from iceberg_tracking_code_b200 import cv
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cv.cvtColor(np.zeros((4, 4, 3), np.uint8), cv.COLOR_BGR2GRAY)
+
+
+def test_product_does_not_import_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may reference it."""
+    pkg = os.path.join(ROOT, "iceberg_tracking_code_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "ibt_oracle" not in src, f
+                assert "import cv2" not in src, f
