@@ -3,21 +3,26 @@
 // Replaces the two cv2.calcOpticalFlowPyrLK calls and the numpy FB arithmetic at
 // s1_lucaskanade_tracking.py:323-333 (s0_1_test_lucaskanade_tracking.py:92-102).
 //
-// Mapping.  Lane L of the warp owns tap column L of a strip of <= 31 window columns (a strip
-// needs one more tap column than it has window columns, so 32 lanes cover 31 columns; winSize
-// 31 is exactly one strip).  The warp walks down the winH+1 tap rows: each lane loads ONE byte
-// of the row (32 contiguous bytes per warp, read through L1), gets its right-hand neighbour
-// with a shuffle and keeps the previous row in registers, so every bilinear sample costs one
-// load + one shuffle instead of four gathers.  The template window (Iw, Ix, Iy as int16, OpenCV's
-// 5-fractional-bit fixed point) is built once per level into a per-warp shared-memory slab and
-// re-read with conflict-free 8-byte loads in every Newton iteration.  The 2x2 structure tensor
-// and the mismatch vector are accumulated exactly (int32 per lane, int64 across the warp by
-// shuffles) and rounded to float once; OpenCV accumulates in float SIMD lanes, which differs in
-// the last bits only.  All float arithmetic that OpenCV does unfused is compiled with -fmad=false.
+// Mapping.  Lane L of the warp owns window column L of a strip of <= 31 window columns and walks down the
+// rows, keeping the previous row's (J[x], J[x+1]) byte pair in a register, so a bilinear sample is two
+// dp2a instructions: OpenCV's four 14-bit integer weights are packed as two 16-bit pairs (top, bottom).
+//   template (once per level)   I window and Scharr planes are gathered from global memory (each tap is read
+//                               once); per window pixel the slab keeps  T0 = 256 - (Iw << 9)  and (Ix, Iy) packed
+//                               as int16 pair, so that  diff = dp2a(wbot, Jpair1, dp2a(wtop, Jpair0, T0)) >> 9
+//                               is exactly OpenCV's  DESCALE(J taps, 9) - Iw  (the shift distributes over the
+//                               multiple of 512).
+//   search patch (per level)    the J region the Newton iterations can reach (window + 1 + 2*MARGIN px per side) is
+//                               staged in shared memory once, REFLECT_101 resolved while staging, and re-staged
+//                               only if the window drifts out of it; iterations never touch global memory.
+// The 2x2 structure tensor and the mismatch vector are accumulated exactly (int32 per lane, int64 across the warp)
+// and rounded to float once; OpenCV accumulates in float SIMD lanes, which differs in the last bits only.
+// All float arithmetic that OpenCV does unfused is compiled with -fmad=false.
 #include "common.cuh"
 #include <string.h>
 
 namespace ibt {
+
+constexpr int LK_MARGIN = 3;        // px the window may drift inside a staged patch, each direction
 
 struct LKLevel {
     const uint8_t *img;
@@ -25,16 +30,19 @@ struct LKLevel {
     int img_pitch;              // bytes
     int deriv_pitch;            // 4-byte elements
     int rows, cols;
+    int word_ok;                // img and img_pitch are 4-byte aligned: patch staging may use word loads
 };
 struct LKPyr {
     LKLevel lv[IBT_MAX_LEVELS];
     int nlevels;
 };
 struct LKArgs {
-    LKPyr A, B;                 // A = prev, B = next
+    LKPyr pyr[2];               // [0] = prev, [1] = next
     const float *p0;
     int n;
     int winW, winH, nstrips, strip_cols;
+    int patch_w, patch_h, patch_pitch;      // staged columns / rows, smem row pitch (bytes, multiple of 4)
+    int tmpl_elems, warp_smem;              // uint2 elements of the template slab; bytes of smem per warp
     int maxCount;
     float eps2, minEigThr;
     int flags;
@@ -52,18 +60,28 @@ __device__ __forceinline__ long long warp_sum_ll(long long v)
     return v;
 }
 
-__device__ __forceinline__ int cv_floor(float v)
+__device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
+
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 with SIGNED 16-bit weights (iw11 = 2^14 - iw00 - iw01 - iw10 can be -1
+// after rounding) and UNSIGNED pixel bytes.
+__device__ __forceinline__ uint32_t dp2a_s16u8(uint32_t a, uint32_t b, uint32_t c)
 {
-    return __float2int_rd(v);
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
+    return (uint32_t)d;
 }
 
-__device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11)
+// OpenCV's integer bilinear weights, packed for dp2a: wtop = iw00 | iw01 << 16, wbot = iw10 | iw11 << 16.
+__device__ __forceinline__ void bilinear_weights(float a, float b, uint32_t &wtop, uint32_t &wbot,
+                                                 int &iw00, int &iw01, int &iw10, int &iw11)
 {
     const float oa = __fsub_rn(1.f, a), ob = __fsub_rn(1.f, b);
     iw00 = __float2int_rn(__fmul_rn(__fmul_rn(oa, ob), 16384.f));
     iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, ob), 16384.f));
     iw10 = __float2int_rn(__fmul_rn(__fmul_rn(oa, b), 16384.f));
     iw11 = 16384 - iw00 - iw01 - iw10;
+    wtop = ((uint32_t)iw00 & 0xffffu) | ((uint32_t)iw01 << 16);
+    wbot = ((uint32_t)iw10 & 0xffffu) | ((uint32_t)iw11 << 16);
 }
 
 __device__ __forceinline__ bool window_oob(int ix, int iy, int winW, int winH, int rows, int cols)
@@ -71,42 +89,67 @@ __device__ __forceinline__ bool window_oob(int ix, int iy, int winW, int winH, i
     return ix < -winW || ix >= cols || iy < -winH || iy >= rows;
 }
 
-// Sum over the window of  diff*Ix, diff*Iy  (MODE 0)  or  |diff|  (MODE 1), where
-// diff = bilinear(J at (ix+x, iy+y)) >> 9  -  Iw.   INSIDE: all taps lie inside the image.
-template <int MODE, bool INSIDE>
-__device__ __forceinline__ void window_pass(const LKLevel &LJ, const LKArgs &a, int ix, int iy,
-                                            int iw00, int iw01, int iw10, int iw11,
-                                            const uint2 *__restrict__ win, int lane,
+// ---- search patch ------------------------------------------------------------------------------------
+// Stage J[py0 .. py0+patch_h) x [px0 .. px0+patch_w) into `patch` (row pitch a.patch_pitch), REFLECT_101 applied.
+__device__ __noinline__ void stage_patch(const LKLevel &LJ, const LKArgs &a, int px0, int py0, uint8_t *patch, int lane)
+{
+    const int PP = a.patch_pitch, PH = a.patch_h;
+    const int ppw = PP >> 2;                                  // words per patch row
+    const bool interior = LJ.word_ok && px0 >= 0 && py0 >= 0 && py0 + PH <= LJ.rows && px0 + PP + 8 <= LJ.cols;
+    if (interior) {
+        const int rpp = 32 / ppw;                             // patch rows per pass
+        const int sr = lane / ppw, sw = lane - sr * ppw;
+        const int al = (px0 & 3) * 8;                         // img, pitch are word aligned: same shift on every row
+        const uint8_t *src = LJ.img + (px0 & ~3) + 4 * sw;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(patch) + sw;
+        if (sr < rpp) {
+            for (int r = sr; r < PH; r += rpp) {
+                const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (int64_t)(py0 + r) * LJ.img_pitch);
+                const uint32_t lo = __ldg(s), hi = __ldg(s + 1);
+                dst[r * ppw] = __funnelshift_r(lo, hi, al);
+            }
+        }
+    } else {
+        const int PW = a.patch_w;
+        for (int r = 0; r < PH; r++) {
+            const uint8_t *s = LJ.img + (int64_t)r101(py0 + r, LJ.rows) * LJ.img_pitch;
+            for (int c = lane; c < PW; c += 32) patch[r * PP + c] = __ldg(s + r101(px0 + c, LJ.cols));
+        }
+    }
+    __syncwarp();
+}
+
+// Sum over the window of  diff*Ix, diff*Iy  (MODE 0)  or  |diff|  (MODE 1),
+// diff = DESCALE(bilinear J at window origin (ox, oy) inside the patch, 9) - Iw.
+template <int MODE>
+__device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__restrict__ patch, int ox, int oy,
+                                            uint32_t wtop, uint32_t wbot, const uint2 *__restrict__ win, int lane,
                                             long long &S1, long long &S2)
 {
-    const int rows = LJ.rows, cols = LJ.cols;
+    const int PP = a.patch_pitch;
     long long t1 = 0, t2 = 0;
     for (int s = 0; s < a.nstrips; s++) {
         const int cs = s * a.strip_cols;
-        const int xcol = ix + cs + lane;
-        const int xr = INSIDE ? min(xcol, cols - 1) : r101(xcol, cols);
-        const uint8_t *colp = LJ.img + xr;
+        const uint8_t *p = patch + oy * PP + ox + cs + lane;
         const uint2 *wrow = win + (s * a.winH) * 32 + lane;
         const bool active = lane < min(a.strip_cols, a.winW - cs);
         int b1 = 0, b2 = 0;
-        int jp = __ldg(colp + (int64_t)(INSIDE ? iy : r101(iy, rows)) * LJ.img_pitch);
-        int jpr = __shfl_down_sync(0xffffffffu, jp, 1);
+        uint32_t prev = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
 #pragma unroll 4
-        for (int r = 1; r <= a.winH; r++) {
-            const int y = iy + r;
-            const int jc = __ldg(colp + (int64_t)(INSIDE ? y : r101(y, rows)) * LJ.img_pitch);
-            const int jcr = __shfl_down_sync(0xffffffffu, jc, 1);
-            const uint2 t = wrow[(r - 1) * 32];
-            const int Iw = (int)(t.x & 0xffffu);
-            const int v = jp * iw00 + jpr * iw01 + jc * iw10 + jcr * iw11;
-            const int diff = ((v + 256) >> 9) - Iw;
+        for (int r = 0; r < a.winH; r++) {
+            p += PP;
+            const uint32_t cur = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+            const uint2 t = wrow[r * 32];
+            uint32_t v = dp2a_s16u8(wtop, prev, t.x);
+            v = dp2a_s16u8(wbot, cur, v);
+            const int diff = (int)v >> 9;
             if (MODE == 0) {
-                const int Ix = ((int)t.x) >> 16, Iy = (int)t.y;   // zero on inactive lanes
-                b1 += diff * Ix; b2 += diff * Iy;
+                b1 += diff * ((int)t.y >> 16);                 // Ix, Iy are zero on inactive lanes
+                b2 += diff * (int)(short)(t.y & 0xffffu);
             } else {
                 b2 += active ? abs(diff) : 0;
             }
-            jp = jc; jpr = jcr;
+            prev = cur;
         }
         t1 += b1; t2 += b2;
     }
@@ -116,8 +159,9 @@ __device__ __forceinline__ void window_pass(const LKLevel &LJ, const LKArgs &a, 
 
 // One pyramidal pass for one point.  On entry (ox, oy) holds the initial flow if use_init.
 // On exit (ox, oy) = nextPts[k], status/err as cv2 (err = 0 where status == 0).
-__device__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, float ptx, float pty, bool use_init,
-                         float &ox, float &oy, int &status, float &err, int &iters, uint2 *win, int lane)
+__device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, float ptx, float pty,
+                                      bool use_init, float &ox, float &oy, int &status, float &err, int &iters,
+                                      uint2 *win, uint8_t *patch, int lane)
 {
     const float FLT_SCALE = 1.f / (1 << 20);
     const int winW = a.winW, winH = a.winH;
@@ -143,49 +187,49 @@ __device__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, floa
             if (level == 0) { status = 0; err = 0.f; }
             continue;
         }
+        uint32_t wtop, wbot;
         int iw00, iw01, iw10, iw11;
-        bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
+        bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), wtop, wbot, iw00, iw01, iw10, iw11);
 
-        // ---- template window: Iw (5 fractional bits), Ix, Iy; structure tensor -------------------
+        // ---- template window: T0 = 256 - (Iw << 9), (Ix, Iy); structure tensor ------------------------------
         long long sA11 = 0, sA12 = 0, sA22 = 0;
         for (int s = 0; s < a.nstrips; s++) {
             const int cs = s * a.strip_cols;
-            const int nc = min(a.strip_cols, winW - cs);             // window columns in this strip
             const int xcol = ipx + cs + lane;
             const int xr = r101(xcol, cols);
             const bool xin = (xcol >= 0) && (xcol < cols);
-            const bool active = lane < nc;
+            const bool active = lane < min(a.strip_cols, winW - cs);
+            const uint8_t *icol = LI.img + xr;
+            const uint32_t *dcol = LI.deriv + xcol;
             int a11 = 0, a12 = 0, a22 = 0;
-            int ip = 0, ipr = 0;
-            uint32_t dp = 0, dpr = 0;
+            uint32_t ipair = 0;
+            int d00x = 0, d00y = 0, d01x = 0, d01y = 0;
             uint2 *wrow = win + (s * winH) * 32 + lane;
-#pragma unroll 2
+#pragma unroll 4
             for (int r = 0; r <= winH; r++) {
                 const int y = ipy + r;
                 const bool yin = (y >= 0) && (y < rows);
-                const int ic = __ldg(LI.img + (int64_t)r101(y, rows) * LI.img_pitch + xr);
+                const uint32_t ic = __ldg(icol + (int64_t)r101(y, rows) * LI.img_pitch);
                 uint32_t dc = 0;                                     // derivative planes are zero outside the image
-                if (xin && yin) dc = __ldg(LI.deriv + (int64_t)y * LI.deriv_pitch + xcol);
-                const int icr = __shfl_down_sync(0xffffffffu, ic, 1);
+                if (xin && yin) dc = __ldg(dcol + (int64_t)y * LI.deriv_pitch);
+                const uint32_t icr = __shfl_down_sync(0xffffffffu, ic, 1);
                 const uint32_t dcr = __shfl_down_sync(0xffffffffu, dc, 1);
+                const uint32_t cpair = ic | (icr << 8);
+                const int d10x = (int)(short)(dc & 0xffffu), d10y = (int)dc >> 16;
+                const int d11x = (int)(short)(dcr & 0xffffu), d11y = (int)dcr >> 16;
                 if (r > 0) {
-                    const int v = ip * iw00 + ipr * iw01 + ic * iw10 + icr * iw11;
-                    const int d00x = (int)(short)(dp & 0xffff), d00y = ((int)dp) >> 16;
-                    const int d01x = (int)(short)(dpr & 0xffff), d01y = ((int)dpr) >> 16;
-                    const int d10x = (int)(short)(dc & 0xffff), d10y = ((int)dc) >> 16;
-                    const int d11x = (int)(short)(dcr & 0xffff), d11y = ((int)dcr) >> 16;
-                    int Iw = (v + 256) >> 9;
+                    uint32_t v = dp2a_s16u8(wtop, ipair, 256u);
+                    v = dp2a_s16u8(wbot, cpair, v);                    // v = taps + 256; Iw = v >> 9
                     int Ix = (d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
                     int Iy = (d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
-                    if (!active) { Iw = 0; Ix = 0; Iy = 0; }
-                    // word0 = Iw | Ix << 16 ; word1 = Iy
                     uint2 t;
-                    t.x = ((uint32_t)Iw & 0xffffu) | ((uint32_t)Ix << 16);
-                    t.y = (uint32_t)Iy;
+                    t.x = 256u - (v & 0xfffffe00u);
+                    if (!active) { Ix = 0; Iy = 0; }
+                    t.y = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
                     wrow[(r - 1) * 32] = t;
                     a11 += Ix * Ix; a12 += Ix * Iy; a22 += Iy * Iy;
                 }
-                ip = ic; ipr = icr; dp = dc; dpr = dcr;
+                ipair = cpair; d00x = d10x; d00y = d10y; d01x = d11x; d01y = d11y;
             }
             sA11 += a11; sA12 += a12; sA22 += a22;
         }
@@ -206,17 +250,23 @@ __device__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, floa
         D = __fdiv_rn(1.f, D);
         nx = __fsub_rn(nx, halfx); ny = __fsub_rn(ny, halfy);
         float pdx = 0.f, pdy = 0.f;
+        int px0 = 0, py0 = 0;
+        bool staged = false;
         for (int j = 0; j < a.maxCount; j++) {
             const int inx = cv_floor(nx), iny = cv_floor(ny);
             if (window_oob(inx, iny, winW, winH, rows, cols)) {
                 if (level == 0) status = 0;
                 break;
             }
-            bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
+            if (!staged || (unsigned)(inx - px0) > 2u * LK_MARGIN || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
+                px0 = inx - LK_MARGIN; py0 = iny - LK_MARGIN;
+                __syncwarp();
+                stage_patch(LJ, a, px0, py0, patch, lane);
+                staged = true;
+            }
+            bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wtop, wbot, iw00, iw01, iw10, iw11);
             long long sb1, sb2;
-            const bool inside = inx >= 0 && iny >= 0 && inx + winW < cols && iny + winH < rows;
-            if (inside) window_pass<0, true>(LJ, a, inx, iny, iw00, iw01, iw10, iw11, win, lane, sb1, sb2);
-            else window_pass<0, false>(LJ, a, inx, iny, iw00, iw01, iw10, iw11, win, lane, sb1, sb2);
+            window_pass<0>(a, patch, inx - px0, iny - py0, wtop, wbot, win, lane, sb1, sb2);
             ++iters;
             const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE);
             const float b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
@@ -235,9 +285,14 @@ __device__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, floa
             const float qx = __fsub_rn(ox, halfx), qy = __fsub_rn(oy, halfy);
             const int iqx = cv_floor(qx), iqy = cv_floor(qy);
             if (window_oob(iqx, iqy, winW, winH, rows, cols)) { status = 0; err = 0.f; continue; }
-            bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), iw00, iw01, iw10, iw11);
+            if (!staged || (unsigned)(iqx - px0) > 2u * LK_MARGIN || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
+                px0 = iqx - LK_MARGIN; py0 = iqy - LK_MARGIN;
+                __syncwarp();
+                stage_patch(LJ, a, px0, py0, patch, lane);
+            }
+            bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), wtop, wbot, iw00, iw01, iw10, iw11);
             long long s1, s2;
-            window_pass<1, false>(LJ, a, iqx, iqy, iw00, iw01, iw10, iw11, win, lane, s1, s2);
+            window_pass<1>(a, patch, iqx - px0, iqy - py0, wtop, wbot, win, lane, s1, s2);
             err = __fdiv_rn(__ll2float_rn(s2), (float)(32 * winW * winH));
         }
         __syncwarp();
@@ -248,36 +303,40 @@ __device__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, floa
 __global__ void __launch_bounds__(128)
 lk_kernel(const __grid_constant__ LKArgs a)
 {
-    extern __shared__ uint2 lk_smem[];
+    extern __shared__ __align__(16) unsigned char lk_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * (blockDim.x >> 5) + wib;
     if (k >= a.n) return;
     if (a.alive && !a.alive[k]) return;
-    uint2 *win = lk_smem + (size_t)wib * (a.nstrips * a.winH * 32);
+    uint2 *win = reinterpret_cast<uint2 *>(lk_smem + (size_t)wib * a.warp_smem);
+    uint8_t *patch = reinterpret_cast<uint8_t *>(win + a.tmpl_elems);
 
     const float p0x = a.p0[2 * k], p0y = a.p0[2 * k + 1];
-    float ox = 0.f, oy = 0.f, err;
-    int status, it_f = 0, it_b = 0;
-    const bool use_init = (a.flags & IBT_LK_USE_INITIAL_FLOW) != 0;
-    if (use_init) { ox = a.p1[2 * k]; oy = a.p1[2 * k + 1]; }
-    lk_point(a.A, a.B, a, p0x, p0y, use_init, ox, oy, status, err, it_f, win, lane);
-    if (lane == 0) {
-        a.p1[2 * k] = ox; a.p1[2 * k + 1] = oy;
-        if (a.st1) a.st1[k] = (uint8_t)status;
-        if (a.err1) a.err1[k] = err;
-    }
-    if (a.fb) {
-        const float p1x = ox, p1y = oy;
-        float rx = 0.f, ry = 0.f;
-        lk_point(a.B, a.A, a, p1x, p1y, false, rx, ry, status, err, it_b, win, lane);
+    float ptx = p0x, pty = p0y;
+    int it_f = 0, it_b = 0;
+    const int npass = a.fb ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {          // one copy of the solver body: pass 1 swaps the pyramids
+        float ox = 0.f, oy = 0.f, err;
+        int status, iters = 0;
+        const bool use_init = pass == 0 && (a.flags & IBT_LK_USE_INITIAL_FLOW) != 0;
+        if (use_init) { ox = a.p1[2 * k]; oy = a.p1[2 * k + 1]; }
+        lk_point(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, ox, oy, status, err, iters, win, patch, lane);
+        if (pass == 0) it_f = iters; else it_b = iters;
         if (lane == 0) {
-            if (a.p0r) { a.p0r[2 * k] = rx; a.p0r[2 * k + 1] = ry; }
-            if (a.st0) a.st0[k] = (uint8_t)status;
-            if (a.err0) a.err0[k] = err;
-            const float d = hypotf(fabsf(__fsub_rn(p0x, rx)), fabsf(__fsub_rn(p0y, ry)));
-            if (a.fbdist) a.fbdist[k] = d;
-            if (a.alive) a.alive[k] = (d < a.fb_thresh) ? 1 : 0;
+            if (pass == 0) {
+                a.p1[2 * k] = ox; a.p1[2 * k + 1] = oy;
+                if (a.st1) a.st1[k] = (uint8_t)status;
+                if (a.err1) a.err1[k] = err;
+            } else {
+                if (a.p0r) { a.p0r[2 * k] = ox; a.p0r[2 * k + 1] = oy; }
+                if (a.st0) a.st0[k] = (uint8_t)status;
+                if (a.err0) a.err0[k] = err;
+                const float d = hypotf(fabsf(__fsub_rn(p0x, ox)), fabsf(__fsub_rn(p0y, oy)));
+                if (a.fbdist) a.fbdist[k] = d;
+                if (a.alive) a.alive[k] = (d < a.fb_thresh) ? 1 : 0;
+            }
         }
+        ptx = ox; pty = oy;                             // the backward pass starts from p1 (s1:326)
     }
     if (lane == 0) {
         if (a.iters) {
@@ -305,6 +364,7 @@ static int fill_pyr(const ibt_pyramid_t *p, LKPyr &o, bool need_deriv)
         o.lv[l].deriv_pitch = (int)(p->deriv_pitch[l] / 4);
         o.lv[l].rows = p->rows[l];
         o.lv[l].cols = p->cols[l];
+        o.lv[l].word_ok = (reinterpret_cast<uintptr_t>(p->img[l]) % 4 == 0) && (p->img_pitch[l] % 4 == 0);
     }
     return IBT_OK;
 }
@@ -315,9 +375,9 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     if (a.n < 0 || winW < 3 || winH < 3 || winW > IBT_MAX_WIN || winH > IBT_MAX_WIN) return IBT_E_INVALID;
     if (a.n == 0) return IBT_OK;
     if (!a.p0 || !a.p1) return IBT_E_INVALID;
-    int rc = fill_pyr(A, a.A, true);
+    int rc = fill_pyr(A, a.pyr[0], true);
     if (rc) return rc;
-    rc = fill_pyr(B, a.B, a.fb != 0);
+    rc = fill_pyr(B, a.pyr[1], a.fb != 0);
     if (rc) return rc;
     if (A->nlevels != B->nlevels) return IBT_E_INVALID;
     for (int l = 0; l < A->nlevels; l++)
@@ -325,19 +385,25 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     a.winW = winW; a.winH = winH;
     a.nstrips = (winW + 30) / 31;
     a.strip_cols = (winW + a.nstrips - 1) / a.nstrips;
+    a.patch_w = winW + 1 + 2 * LK_MARGIN;
+    a.patch_h = winH + 1 + 2 * LK_MARGIN;
+    // every lane of every strip reads two bytes per row, active or not: keep those reads inside the slab
+    const int reach = 2 * LK_MARGIN + (a.nstrips - 1) * a.strip_cols + 33;
+    a.patch_pitch = ((reach > a.patch_w ? reach : a.patch_w) + 3) & ~3;
+    a.tmpl_elems = a.nstrips * winH * 32;
+    a.warp_smem = (int)((a.tmpl_elems * sizeof(uint2) + (size_t)a.patch_h * a.patch_pitch + 15) & ~(size_t)15);
     a.maxCount = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
     if (epsilon < 0) epsilon = 0;
     if (epsilon > 10) epsilon = 10;
     a.eps2 = (float)(epsilon * epsilon);
     a.minEigThr = (float)min_eig;
-    const size_t per_warp = (size_t)a.nstrips * winH * 32 * sizeof(uint2);
     int wpc = 4;
-    while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
-    const size_t smem = per_warp * wpc;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    while (wpc > 1 && (size_t)a.warp_smem * wpc > 100 * 1024) wpc >>= 1;
+    const size_t smem = (size_t)a.warp_smem * wpc;
+    static bool attr_set = false;
+    if (!attr_set) {
         IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        smem_set = 200 * 1024;
+        attr_set = true;
     }
     const int blocks = (a.n + wpc - 1) / wpc;
     lk_kernel<<<blocks, wpc * 32, smem, st>>>(a);
