@@ -3,18 +3,20 @@
 // Replaces the two cv2.calcOpticalFlowPyrLK calls and the numpy FB arithmetic at
 // s1_lucaskanade_tracking.py:323-333 (s0_1_test_lucaskanade_tracking.py:92-102).
 //
-// Mapping.  Lane L of the warp owns window column L of a strip of <= 31 window columns and walks down the
-// rows, keeping the previous row's (J[x], J[x+1]) byte pair in a register, so a bilinear sample is two
-// dp2a instructions: OpenCV's four 14-bit integer weights are packed as two 16-bit pairs (top, bottom).
-//   template (once per level)   I window and Scharr planes are gathered from global memory (each tap is read
-//                               once); per window pixel the slab keeps  T0 = 256 - (Iw << 9)  and (Ix, Iy) packed
-//                               as int16 pair, so that  diff = dp2a(wbot, Jpair1, dp2a(wtop, Jpair0, T0)) >> 9
-//                               is exactly OpenCV's  DESCALE(J taps, 9) - Iw  (the shift distributes over the
-//                               multiple of 512).
-//   search patch (per level)    the J region the Newton iterations can reach (window + 1 + 2*MARGIN px per side) is
-//                               staged in shared memory once, REFLECT_101 resolved while staging, and re-staged
-//                               only if the window drifts out of it; iterations never touch global memory.
-// The 2x2 structure tensor and the mismatch vector are accumulated exactly (int32 per lane, int64 across the warp)
+// Per level a warp (a) issues cp.async copies of everything the level can touch -- the I window, its Scharr
+// planes, and the J search patch around the propagated guess -- into its private shared-memory slab in one
+// burst (one exposed L2 latency per level instead of one per row), (b) builds the template from shared memory,
+// (c) runs the Newton iterations entirely out of shared memory.
+//   mapping     lane L owns window column L of a strip of <= 32 columns and walks down the rows, keeping the
+//               previous row's (J[x], J[x+1]) byte pair in a register; a bilinear sample is two dp2a
+//               instructions: OpenCV's four 14-bit integer weights are packed as two int16 pairs (top, bottom).
+//   template    per window pixel the slab keeps  T0 = 256 - (Iw << 9)  and (Ix, Iy) packed as int16 pair, so that
+//               diff = dp2a(wbot, Jpair1, dp2a(wtop, Jpair0, T0)) >> 9  is exactly OpenCV's
+//               DESCALE(J taps, 9) - Iw  (the arithmetic shift distributes over the multiple of 512).
+//   borders     intensities REFLECT_101 (resolved while staging, synchronous gather path), derivatives ZERO outside
+//               the image (cp.async zero-fill), as inside OpenCV's padded pyramids.
+//   patch       window + 1 + 2*MARGIN(+3 alignment) px; re-staged only if the window drifts out of it.
+// The 2x2 structure tensor and the mismatch vector are accumulated exactly (int32 per lane, REDUX across the warp)
 // and rounded to float once; OpenCV accumulates in float SIMD lanes, which differs in the last bits only.
 // All float arithmetic that OpenCV does unfused is compiled with -fmad=false.
 #include "common.cuh"
@@ -30,7 +32,7 @@ struct LKLevel {
     int img_pitch;              // bytes
     int deriv_pitch;            // 4-byte elements
     int rows, cols;
-    int word_ok;                // img and img_pitch are 4-byte aligned: patch staging may use word loads
+    int word_ok;                // img and img_pitch are 4-byte aligned: patch staging may use 4-byte cp.async
 };
 struct LKPyr {
     LKLevel lv[IBT_MAX_LEVELS];
@@ -41,8 +43,14 @@ struct LKArgs {
     const float *p0;
     int n;
     int winW, winH, nstrips, strip_cols;
-    int patch_w, patch_h, patch_pitch;      // staged columns / rows, smem row pitch (bytes, multiple of 4)
-    int tmpl_elems, warp_smem;              // uint2 elements of the template slab; bytes of smem per warp
+    // per-warp shared-memory slab: [template uint2 x tmpl_elems][deriv patch][I patch][J patch]
+    int tmpl_elems;
+    int dpitch;                 // deriv patch row pitch, words
+    int ipitch;                 // I patch row pitch, bytes (multiple of 4)
+    int jpitch, jrows;          // J patch row pitch (bytes, multiple of 4) and rows
+    int irpp, jrpp;             // patch rows covered per cp.async pass (32 / words per row)
+    unsigned int *work_counter; // next point index (dynamic point -> warp assignment)
+    int off_deriv, off_ipatch, off_jpatch, warp_smem;     // bytes
     int maxCount;
     float eps2, minEigThr;
     int flags;
@@ -53,11 +61,12 @@ struct LKArgs {
     float *fbdist; uint8_t *alive; int32_t *iters; unsigned long long *iter_total;
 };
 
-__device__ __forceinline__ long long warp_sum_ll(long long v)
+// exact warp sum of int32 lane values (|v| < 2^31) as int64: two REDUX instead of ten shuffles
+__device__ __forceinline__ long long warp_sum_wide(int v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const int lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return ((long long)hi << 16) + lo;
 }
 
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
@@ -70,6 +79,15 @@ __device__ __forceinline__ uint32_t dp2a_s16u8(uint32_t a, uint32_t b, uint32_t 
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
     return (uint32_t)d;
 }
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, int src_size)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // OpenCV's integer bilinear weights, packed for dp2a: wtop = iw00 | iw01 << 16, wbot = iw10 | iw11 << 16.
 __device__ __forceinline__ void bilinear_weights(float a, float b, uint32_t &wtop, uint32_t &wbot,
@@ -89,45 +107,77 @@ __device__ __forceinline__ bool window_oob(int ix, int iy, int winW, int winH, i
     return ix < -winW || ix >= cols || iy < -winH || iy >= rows;
 }
 
-// ---- search patch ------------------------------------------------------------------------------------
-// Stage J[py0 .. py0+patch_h) x [px0 .. px0+patch_w) into `patch` (row pitch a.patch_pitch), REFLECT_101 applied.
-__device__ __noinline__ void stage_patch(const LKLevel &LJ, const LKArgs &a, int px0, int py0, uint8_t *patch, int lane)
+// ---- staging ---------------------------------------------------------------------------------------------
+// Stage image rows [y0, y0+nrows) x bytes [x0a, x0a+pitch) (x0a a multiple of 4) into dst (row pitch `pitch`).
+// Interior patches go as 4-byte cp.async (lane -> (row sr + k*rpp, word sw)); patches that touch the border are
+// gathered through REFLECT_101 (column indices resolved once per lane, rows batched four at a time).
+// The caller commits / waits.
+__device__ __forceinline__ void stage_bytes(const LKLevel &L, int x0a, int y0, int nrows, int pitch, int rpp, int sr, int sw,
+                                            uint8_t *dst, int lane)
 {
-    const int PP = a.patch_pitch, PH = a.patch_h;
-    const int ppw = PP >> 2;                                  // words per patch row
-    const bool interior = LJ.word_ok && px0 >= 0 && py0 >= 0 && py0 + PH <= LJ.rows && px0 + PP + 8 <= LJ.cols;
+    const bool interior = L.word_ok && x0a >= 0 && y0 >= 0 && y0 + nrows <= L.rows && x0a + pitch <= L.cols;
     if (interior) {
-        const int rpp = 32 / ppw;                             // patch rows per pass
-        const int sr = lane / ppw, sw = lane - sr * ppw;
-        const int al = (px0 & 3) * 8;                         // img, pitch are word aligned: same shift on every row
-        const uint8_t *src = LJ.img + (px0 & ~3) + 4 * sw;
-        uint32_t *dst = reinterpret_cast<uint32_t *>(patch) + sw;
         if (sr < rpp) {
-            for (int r = sr; r < PH; r += rpp) {
-                const uint32_t *s = reinterpret_cast<const uint32_t *>(src + (int64_t)(py0 + r) * LJ.img_pitch);
-                const uint32_t lo = __ldg(s), hi = __ldg(s + 1);
-                dst[r * ppw] = __funnelshift_r(lo, hi, al);
+            const uint8_t *src = L.img + (int64_t)(y0 + sr) * L.img_pitch + x0a + 4 * sw;
+            uint8_t *d = dst + sr * pitch + 4 * sw;
+            const int64_t sstep = (int64_t)rpp * L.img_pitch;
+            const int dstep = rpp * pitch;
+#pragma unroll 4
+            for (int r = sr; r < nrows; r += rpp) {
+                cp_async4(d, src, 4);
+                src += sstep; d += dstep;
             }
         }
     } else {
-        const int PW = a.patch_w;
-        for (int r = 0; r < PH; r++) {
-            const uint8_t *s = LJ.img + (int64_t)r101(py0 + r, LJ.rows) * LJ.img_pitch;
-            for (int c = lane; c < PW; c += 32) patch[r * PP + c] = __ldg(s + r101(px0 + c, LJ.cols));
+        for (int c = lane; c < pitch; c += 32) {
+            const uint8_t *s = L.img + r101(x0a + c, L.cols);
+            uint8_t *d = dst + c;
+            int r = 0;
+            for (; r + 4 <= nrows; r += 4) {
+                const uint8_t v0 = __ldg(s + (int64_t)r101(y0 + r, L.rows) * L.img_pitch);
+                const uint8_t v1 = __ldg(s + (int64_t)r101(y0 + r + 1, L.rows) * L.img_pitch);
+                const uint8_t v2 = __ldg(s + (int64_t)r101(y0 + r + 2, L.rows) * L.img_pitch);
+                const uint8_t v3 = __ldg(s + (int64_t)r101(y0 + r + 3, L.rows) * L.img_pitch);
+                d[r * pitch] = v0; d[(r + 1) * pitch] = v1; d[(r + 2) * pitch] = v2; d[(r + 3) * pitch] = v3;
+            }
+            for (; r < nrows; r++) d[r * pitch] = __ldg(s + (int64_t)r101(y0 + r, L.rows) * L.img_pitch);
         }
     }
-    __syncwarp();
+}
+
+// Stage the Scharr planes of the template window: rows [y0, y0+winH], columns [x0, x0+winW]; zero outside the image.
+__device__ __forceinline__ void stage_deriv(const LKLevel &L, const LKArgs &a, int x0, int y0, uint32_t *dst, int lane)
+{
+    const bool interior = x0 >= 0 && y0 >= 0 && x0 + a.winW < L.cols && y0 + a.winH < L.rows;
+    for (int c = lane; c <= a.winW; c += 32) {
+        const uint32_t *src = L.deriv + (int64_t)y0 * L.deriv_pitch + x0 + c;
+        uint32_t *d = dst + c;
+        if (interior) {
+#pragma unroll 4
+            for (int r = 0; r <= a.winH; r++) {
+                cp_async4(d, src, 4);
+                src += L.deriv_pitch; d += a.dpitch;
+            }
+        } else {
+            const bool xin = (unsigned)(x0 + c) < (unsigned)L.cols;
+            for (int r = 0; r <= a.winH; r++) {
+                const bool ok = xin && (unsigned)(y0 + r) < (unsigned)L.rows;
+                cp_async4(d, ok ? src : L.deriv, ok ? 4 : 0);
+                src += L.deriv_pitch; d += a.dpitch;
+            }
+        }
+    }
 }
 
 // Sum over the window of  diff*Ix, diff*Iy  (MODE 0)  or  |diff|  (MODE 1),
-// diff = DESCALE(bilinear J at window origin (ox, oy) inside the patch, 9) - Iw.
+// diff = DESCALE(bilinear J at byte offset (ox, oy) inside the patch, 9) - Iw.
 template <int MODE>
 __device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__restrict__ patch, int ox, int oy,
                                             uint32_t wtop, uint32_t wbot, const uint2 *__restrict__ win, int lane,
                                             long long &S1, long long &S2)
 {
-    const int PP = a.patch_pitch;
-    long long t1 = 0, t2 = 0;
+    const int PP = a.jpitch;
+    S1 = 0; S2 = 0;
     for (int s = 0; s < a.nstrips; s++) {
         const int cs = s * a.strip_cols;
         const uint8_t *p = patch + oy * PP + ox + cs + lane;
@@ -151,21 +201,24 @@ __device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__re
             }
             prev = cur;
         }
-        t1 += b1; t2 += b2;
+        if (MODE == 0) S1 += warp_sum_wide(b1);
+        S2 += warp_sum_wide(b2);
     }
-    S1 = warp_sum_ll(t1);
-    S2 = warp_sum_ll(t2);
 }
 
 // One pyramidal pass for one point.  On entry (ox, oy) holds the initial flow if use_init.
 // On exit (ox, oy) = nextPts[k], status/err as cv2 (err = 0 where status == 0).
 __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, float ptx, float pty,
-                                      bool use_init, float &ox, float &oy, int &status, float &err, int &iters,
-                                      uint2 *win, uint8_t *patch, int lane)
+                                         bool use_init, float &ox, float &oy, int &status, float &err, int &iters,
+                                         unsigned char *slab, int isr, int isw, int jsr, int jsw, int lane)
 {
     const float FLT_SCALE = 1.f / (1 << 20);
     const int winW = a.winW, winH = a.winH;
     const float halfx = (winW - 1) * 0.5f, halfy = (winH - 1) * 0.5f;
+    uint2 *win = reinterpret_cast<uint2 *>(slab);
+    uint32_t *dpatch = reinterpret_cast<uint32_t *>(slab + a.off_deriv);
+    uint8_t *ipatch = slab + a.off_ipatch;
+    uint8_t *jpatch = slab + a.off_jpatch;
     status = 1; err = 0.f;
     const int L = PI.nlevels;
     for (int level = L - 1; level >= 0; --level) {
@@ -187,54 +240,67 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             if (level == 0) { status = 0; err = 0.f; }
             continue;
         }
+        nx = __fsub_rn(nx, halfx); ny = __fsub_rn(ny, halfy);
+
+        // ---- one burst of async copies: I window, its Scharr planes (group 0), J search patch (group 1) -----------
+        const int ipxa = ipx & ~3;
+        stage_bytes(LI, ipxa, ipy, winH + 1, a.ipitch, a.irpp, isr, isw, ipatch, lane);
+        stage_deriv(LI, a, ipx, ipy, dpatch, lane);
+        cp_async_commit();
+        int px0 = 0, py0 = 0;
+        bool staged = false;
+        {
+            const int inx = cv_floor(nx), iny = cv_floor(ny);
+            if (!window_oob(inx, iny, winW, winH, rows, cols)) {
+                px0 = (inx - LK_MARGIN) & ~3; py0 = iny - LK_MARGIN;
+                stage_bytes(LJ, px0, py0, a.jrows, a.jpitch, a.jrpp, jsr, jsw, jpatch, lane);
+                staged = true;
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+
         uint32_t wtop, wbot;
         int iw00, iw01, iw10, iw11;
         bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), wtop, wbot, iw00, iw01, iw10, iw11);
 
-        // ---- template window: T0 = 256 - (Iw << 9), (Ix, Iy); structure tensor ------------------------------
+        // ---- template window: T0 = 256 - (Iw << 9), (Ix, Iy); structure tensor ------------------------------------
         long long sA11 = 0, sA12 = 0, sA22 = 0;
         for (int s = 0; s < a.nstrips; s++) {
             const int cs = s * a.strip_cols;
-            const int xcol = ipx + cs + lane;
-            const int xr = r101(xcol, cols);
-            const bool xin = (xcol >= 0) && (xcol < cols);
             const bool active = lane < min(a.strip_cols, winW - cs);
-            const uint8_t *icol = LI.img + xr;
-            const uint32_t *dcol = LI.deriv + xcol;
-            int a11 = 0, a12 = 0, a22 = 0;
-            uint32_t ipair = 0;
-            int d00x = 0, d00y = 0, d01x = 0, d01y = 0;
+            const uint8_t *ip = ipatch + (ipx - ipxa) + cs + lane;
+            const uint32_t *dp = dpatch + cs + lane;
             uint2 *wrow = win + (s * winH) * 32 + lane;
+            int a11 = 0, a12 = 0, a22 = 0;
+            uint32_t ipair = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
+            uint32_t dc = dp[0], dcr = dp[1];
+            int d00x = (int)(short)(dc & 0xffffu), d00y = (int)dc >> 16;
+            int d01x = (int)(short)(dcr & 0xffffu), d01y = (int)dcr >> 16;
 #pragma unroll 4
-            for (int r = 0; r <= winH; r++) {
-                const int y = ipy + r;
-                const bool yin = (y >= 0) && (y < rows);
-                const uint32_t ic = __ldg(icol + (int64_t)r101(y, rows) * LI.img_pitch);
-                uint32_t dc = 0;                                     // derivative planes are zero outside the image
-                if (xin && yin) dc = __ldg(dcol + (int64_t)y * LI.deriv_pitch);
-                const uint32_t icr = __shfl_down_sync(0xffffffffu, ic, 1);
-                const uint32_t dcr = __shfl_down_sync(0xffffffffu, dc, 1);
-                const uint32_t cpair = ic | (icr << 8);
+            for (int r = 0; r < winH; r++) {
+                ip += a.ipitch; dp += a.dpitch;
+                const uint32_t cpair = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
+                dc = dp[0]; dcr = dp[1];
                 const int d10x = (int)(short)(dc & 0xffffu), d10y = (int)dc >> 16;
                 const int d11x = (int)(short)(dcr & 0xffffu), d11y = (int)dcr >> 16;
-                if (r > 0) {
-                    uint32_t v = dp2a_s16u8(wtop, ipair, 256u);
-                    v = dp2a_s16u8(wbot, cpair, v);                    // v = taps + 256; Iw = v >> 9
-                    int Ix = (d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
-                    int Iy = (d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
-                    uint2 t;
-                    t.x = 256u - (v & 0xfffffe00u);
-                    if (!active) { Ix = 0; Iy = 0; }
-                    t.y = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
-                    wrow[(r - 1) * 32] = t;
-                    a11 += Ix * Ix; a12 += Ix * Iy; a22 += Iy * Iy;
-                }
+                uint32_t v = dp2a_s16u8(wtop, ipair, 256u);
+                v = dp2a_s16u8(wbot, cpair, v);                        // v = taps + 256; Iw = v >> 9
+                int Ix = (d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
+                int Iy = (d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
+                if (!active) { Ix = 0; Iy = 0; }
+                uint2 t;
+                t.x = 256u - (v & 0xfffffe00u);
+                t.y = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
+                wrow[r * 32] = t;
+                a11 += Ix * Ix; a12 += Ix * Iy; a22 += Iy * Iy;
                 ipair = cpair; d00x = d10x; d00y = d10y; d01x = d11x; d01y = d11y;
             }
-            sA11 += a11; sA12 += a12; sA22 += a22;
+            sA11 += warp_sum_wide(a11); sA12 += warp_sum_wide(a12); sA22 += warp_sum_wide(a22);
         }
+        cp_async_wait<0>();
         __syncwarp();
-        sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
         const float A11 = __fmul_rn(__ll2float_rn(sA11), FLT_SCALE);
         const float A12 = __fmul_rn(__ll2float_rn(sA12), FLT_SCALE);
         const float A22 = __fmul_rn(__ll2float_rn(sA22), FLT_SCALE);
@@ -248,25 +314,26 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             continue;
         }
         D = __fdiv_rn(1.f, D);
-        nx = __fsub_rn(nx, halfx); ny = __fsub_rn(ny, halfy);
+        const int max_off = 2 * LK_MARGIN + 3;
         float pdx = 0.f, pdy = 0.f;
-        int px0 = 0, py0 = 0;
-        bool staged = false;
         for (int j = 0; j < a.maxCount; j++) {
             const int inx = cv_floor(nx), iny = cv_floor(ny);
             if (window_oob(inx, iny, winW, winH, rows, cols)) {
                 if (level == 0) status = 0;
                 break;
             }
-            if (!staged || (unsigned)(inx - px0) > 2u * LK_MARGIN || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
-                px0 = inx - LK_MARGIN; py0 = iny - LK_MARGIN;
+            if (!staged || (unsigned)(inx - px0) > (unsigned)max_off || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
+                px0 = (inx - LK_MARGIN) & ~3; py0 = iny - LK_MARGIN;
                 __syncwarp();
-                stage_patch(LJ, a, px0, py0, patch, lane);
+                stage_bytes(LJ, px0, py0, a.jrows, a.jpitch, a.jrpp, jsr, jsw, jpatch, lane);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
                 staged = true;
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wtop, wbot, iw00, iw01, iw10, iw11);
             long long sb1, sb2;
-            window_pass<0>(a, patch, inx - px0, iny - py0, wtop, wbot, win, lane, sb1, sb2);
+            window_pass<0>(a, jpatch, inx - px0, iny - py0, wtop, wbot, win, lane, sb1, sb2);
             ++iters;
             const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE);
             const float b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
@@ -285,32 +352,42 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             const float qx = __fsub_rn(ox, halfx), qy = __fsub_rn(oy, halfy);
             const int iqx = cv_floor(qx), iqy = cv_floor(qy);
             if (window_oob(iqx, iqy, winW, winH, rows, cols)) { status = 0; err = 0.f; continue; }
-            if (!staged || (unsigned)(iqx - px0) > 2u * LK_MARGIN || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
-                px0 = iqx - LK_MARGIN; py0 = iqy - LK_MARGIN;
+            if (!staged || (unsigned)(iqx - px0) > (unsigned)max_off || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
+                px0 = (iqx - LK_MARGIN) & ~3; py0 = iqy - LK_MARGIN;
                 __syncwarp();
-                stage_patch(LJ, a, px0, py0, patch, lane);
+                stage_bytes(LJ, px0, py0, a.jrows, a.jpitch, a.jrpp, jsr, jsw, jpatch, lane);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
             }
             bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), wtop, wbot, iw00, iw01, iw10, iw11);
             long long s1, s2;
-            window_pass<1>(a, patch, iqx - px0, iqy - py0, wtop, wbot, win, lane, s1, s2);
+            window_pass<1>(a, jpatch, iqx - px0, iqy - py0, wtop, wbot, win, lane, s1, s2);
             err = __fdiv_rn(__ll2float_rn(s2), (float)(32 * winW * winH));
         }
         __syncwarp();
     }
+    cp_async_wait<0>();
     if (!status && !(a.flags & IBT_LK_GET_MIN_EIGENVALS)) err = 0.f;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 lk_kernel(const __grid_constant__ LKArgs a)
 {
     extern __shared__ __align__(16) unsigned char lk_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int k = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (k >= a.n) return;
-    if (a.alive && !a.alive[k]) return;
-    uint2 *win = reinterpret_cast<uint2 *>(lk_smem + (size_t)wib * a.warp_smem);
-    uint8_t *patch = reinterpret_cast<uint8_t *>(win + a.tmpl_elems);
+    unsigned char *slab = lk_smem + (size_t)wib * a.warp_smem;
+    // lane -> (row, word) assignment of the two byte-patch layouts
+    const int ippw = a.ipitch >> 2, jppw = a.jpitch >> 2;
+    const int isr = lane / ippw, isw = lane - isr * ippw;
+    const int jsr = lane / jppw, jsw = lane - jsr * jppw;
 
+  for (;;) {                                            // persistent warp: points are handed out dynamically
+    int k = 0;
+    if (lane == 0) k = (int)atomicAdd(a.work_counter, 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= a.n) break;
+    if (a.alive && !a.alive[k]) continue;
     const float p0x = a.p0[2 * k], p0y = a.p0[2 * k + 1];
     float ptx = p0x, pty = p0y;
     int it_f = 0, it_b = 0;
@@ -320,7 +397,8 @@ lk_kernel(const __grid_constant__ LKArgs a)
         int status, iters = 0;
         const bool use_init = pass == 0 && (a.flags & IBT_LK_USE_INITIAL_FLOW) != 0;
         if (use_init) { ox = a.p1[2 * k]; oy = a.p1[2 * k + 1]; }
-        lk_point(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, ox, oy, status, err, iters, win, patch, lane);
+        lk_point(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, ox, oy, status, err, iters, slab, isr, isw, jsr, jsw,
+                 lane);
         if (pass == 0) it_f = iters; else it_b = iters;
         if (lane == 0) {
             if (pass == 0) {
@@ -345,6 +423,8 @@ lk_kernel(const __grid_constant__ LKArgs a)
         }
         if (a.iter_total) atomicAdd(a.iter_total, (unsigned long long)(it_f + it_b));
     }
+    __syncwarp();
+  }
 }
 
 static int fill_pyr(const ibt_pyramid_t *p, LKPyr &o, bool need_deriv)
@@ -383,29 +463,52 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     for (int l = 0; l < A->nlevels; l++)
         if (A->rows[l] != B->rows[l] || A->cols[l] != B->cols[l]) return IBT_E_INVALID;
     a.winW = winW; a.winH = winH;
-    a.nstrips = (winW + 30) / 31;
+    a.nstrips = (winW + 31) / 32;
     a.strip_cols = (winW + a.nstrips - 1) / a.nstrips;
-    a.patch_w = winW + 1 + 2 * LK_MARGIN;
-    a.patch_h = winH + 1 + 2 * LK_MARGIN;
-    // every lane of every strip reads two bytes per row, active or not: keep those reads inside the slab
-    const int reach = 2 * LK_MARGIN + (a.nstrips - 1) * a.strip_cols + 33;
-    a.patch_pitch = ((reach > a.patch_w ? reach : a.patch_w) + 3) & ~3;
+    // every lane of every strip reads two adjacent elements per row, active or not: pitches keep those reads in the slab
+    const int reach = (a.nstrips - 1) * a.strip_cols + 33;
     a.tmpl_elems = a.nstrips * winH * 32;
-    a.warp_smem = (int)((a.tmpl_elems * sizeof(uint2) + (size_t)a.patch_h * a.patch_pitch + 15) & ~(size_t)15);
+    a.dpitch = reach;
+    a.ipitch = (3 + reach + 3) & ~3;
+    a.jpitch = (2 * LK_MARGIN + 3 + reach + 3) & ~3;
+    a.jrows = winH + 1 + 2 * LK_MARGIN;
+    a.irpp = 32 / (a.ipitch / 4);
+    a.jrpp = 32 / (a.jpitch / 4);
+    size_t off = (size_t)a.tmpl_elems * sizeof(uint2);
+    a.off_deriv = (int)off;  off += (size_t)(winH + 1) * a.dpitch * 4;
+    a.off_ipatch = (int)off; off += (size_t)(winH + 1) * a.ipitch;
+    a.off_jpatch = (int)off; off += (size_t)a.jrows * a.jpitch;
+    a.warp_smem = (int)((off + 15) & ~(size_t)15);
     a.maxCount = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
     if (epsilon < 0) epsilon = 0;
     if (epsilon > 10) epsilon = 10;
     a.eps2 = (float)(epsilon * epsilon);
     a.minEigThr = (float)min_eig;
-    int wpc = 4;
-    while (wpc > 1 && (size_t)a.warp_smem * wpc > 100 * 1024) wpc >>= 1;
+    // warps per CTA: the choice that keeps the most warps resident in 227 KB of shared memory per SM
+    int wpc = 1, best = 0, best_ctas = 1;
+    for (int w = 1; w <= 8; w++) {
+        const size_t per_cta = (size_t)a.warp_smem * w + 1024;
+        if (per_cta > 200 * 1024) break;
+        int ctas = (int)((227 * 1024) / per_cta);
+        if (ctas > 32) ctas = 32;
+        const int warps = ctas * w;
+        if (warps >= best) { best = warps; wpc = w; best_ctas = ctas; }
+    }
     const size_t smem = (size_t)a.warp_smem * wpc;
     static bool attr_set = false;
+    static unsigned int *counters = nullptr;           // ring of work counters: one 4-byte slot per launch in flight
+    static unsigned int next_slot = 0;
+    constexpr unsigned int kSlots = 256;
     if (!attr_set) {
         IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        IBT_CUDA_TRY(cudaMalloc(&counters, kSlots * sizeof(unsigned int)));
         attr_set = true;
     }
-    const int blocks = (a.n + wpc - 1) / wpc;
+    a.work_counter = counters + (next_slot++ % kSlots);
+    IBT_CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), st));
+    int blocks = kNumSMs * best_ctas;                   // persistent: one wave, warps pull points until none are left
+    const int need = (a.n + wpc - 1) / wpc;
+    if (blocks > need) blocks = need;
     lk_kernel<<<blocks, wpc * 32, smem, st>>>(a);
     return check_launch("ibt_lk");
 }
