@@ -26,6 +26,15 @@ namespace ibt {
 
 constexpr int LK_MARGIN = 3;        // px the window may drift inside a staged patch, each direction
 
+// slab geometry as a function of the window width (shared by host launch code and the specialised kernels)
+__host__ __device__ constexpr int lk_nstrips(int w) { return (w + 31) / 32; }
+__host__ __device__ constexpr int lk_strip_cols(int w) { return (w + lk_nstrips(w) - 1) / lk_nstrips(w); }
+// every lane of every strip reads two adjacent elements per row, active or not: pitches keep those reads in the slab
+__host__ __device__ constexpr int lk_reach(int w) { return (lk_nstrips(w) - 1) * lk_strip_cols(w) + 33; }
+__host__ __device__ constexpr int lk_dpitch(int w) { return lk_reach(w); }
+__host__ __device__ constexpr int lk_ipitch(int w) { return (3 + lk_reach(w) + 3) & ~3; }
+__host__ __device__ constexpr int lk_jpitch(int w) { return (2 * LK_MARGIN + 3 + lk_reach(w) + 3) & ~3; }
+
 struct LKLevel {
     const uint8_t *img;
     const uint32_t *deriv;      // packed (dx | dy << 16), may be null for a J-only pyramid
@@ -80,10 +89,14 @@ __device__ __forceinline__ uint32_t dp2a_s16u8(uint32_t a, uint32_t b, uint32_t 
     return (uint32_t)d;
 }
 
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, int src_size)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const void *gsrc)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(src_size) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(unsigned smem_dst, const void *gsrc, int src_size)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_size) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -119,12 +132,12 @@ __device__ __forceinline__ void stage_bytes(const LKLevel &L, int x0a, int y0, i
     if (interior) {
         if (sr < rpp) {
             const uint8_t *src = L.img + (int64_t)(y0 + sr) * L.img_pitch + x0a + 4 * sw;
-            uint8_t *d = dst + sr * pitch + 4 * sw;
+            unsigned d = smem_u32(dst) + sr * pitch + 4 * sw;
             const int64_t sstep = (int64_t)rpp * L.img_pitch;
             const int dstep = rpp * pitch;
 #pragma unroll 4
             for (int r = sr; r < nrows; r += rpp) {
-                cp_async4(d, src, 4);
+                cp_async4(d, src);
                 src += sstep; d += dstep;
             }
         }
@@ -146,24 +159,27 @@ __device__ __forceinline__ void stage_bytes(const LKLevel &L, int x0a, int y0, i
 }
 
 // Stage the Scharr planes of the template window: rows [y0, y0+winH], columns [x0, x0+winW]; zero outside the image.
+template <int WW, int WH>
 __device__ __forceinline__ void stage_deriv(const LKLevel &L, const LKArgs &a, int x0, int y0, uint32_t *dst, int lane)
 {
-    const bool interior = x0 >= 0 && y0 >= 0 && x0 + a.winW < L.cols && y0 + a.winH < L.rows;
-    for (int c = lane; c <= a.winW; c += 32) {
+    const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
+    const int DP = WW ? lk_dpitch(WW) : a.dpitch;
+    const bool interior = x0 >= 0 && y0 >= 0 && x0 + winW < L.cols && y0 + winH < L.rows;
+    for (int c = lane; c <= winW; c += 32) {
         const uint32_t *src = L.deriv + (int64_t)y0 * L.deriv_pitch + x0 + c;
-        uint32_t *d = dst + c;
+        unsigned d = smem_u32(dst + c);
         if (interior) {
-#pragma unroll 4
-            for (int r = 0; r <= a.winH; r++) {
-                cp_async4(d, src, 4);
-                src += L.deriv_pitch; d += a.dpitch;
+#pragma unroll 8
+            for (int r = 0; r <= winH; r++) {
+                cp_async4(d, src);
+                src += L.deriv_pitch; d += DP * 4;
             }
         } else {
             const bool xin = (unsigned)(x0 + c) < (unsigned)L.cols;
-            for (int r = 0; r <= a.winH; r++) {
+            for (int r = 0; r <= winH; r++) {
                 const bool ok = xin && (unsigned)(y0 + r) < (unsigned)L.rows;
-                cp_async4(d, ok ? src : L.deriv, ok ? 4 : 0);
-                src += L.deriv_pitch; d += a.dpitch;
+                cp_async4_zfill(d, ok ? src : L.deriv, ok ? 4 : 0);
+                src += L.deriv_pitch; d += DP * 4;
             }
         }
     }
@@ -171,24 +187,26 @@ __device__ __forceinline__ void stage_deriv(const LKLevel &L, const LKArgs &a, i
 
 // Sum over the window of  diff*Ix, diff*Iy  (MODE 0)  or  |diff|  (MODE 1),
 // diff = DESCALE(bilinear J at byte offset (ox, oy) inside the patch, 9) - Iw.
-template <int MODE>
+template <int MODE, int WW, int WH>
 __device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__restrict__ patch, int ox, int oy,
                                             uint32_t wtop, uint32_t wbot, const uint2 *__restrict__ win, int lane,
                                             long long &S1, long long &S2)
 {
-    const int PP = a.jpitch;
+    const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
+    const int nstrips = WW ? lk_nstrips(WW) : a.nstrips, strip_cols = WW ? lk_strip_cols(WW) : a.strip_cols;
+    const int PP = WW ? lk_jpitch(WW) : a.jpitch;
     S1 = 0; S2 = 0;
-    for (int s = 0; s < a.nstrips; s++) {
-        const int cs = s * a.strip_cols;
+#pragma unroll
+    for (int s = 0; s < nstrips; s++) {
+        const int cs = s * strip_cols;
         const uint8_t *p = patch + oy * PP + ox + cs + lane;
-        const uint2 *wrow = win + (s * a.winH) * 32 + lane;
-        const bool active = lane < min(a.strip_cols, a.winW - cs);
+        const uint2 *wrow = win + (s * winH) * 32 + lane;
+        const bool active = lane < min(strip_cols, winW - cs);
         int b1 = 0, b2 = 0;
         uint32_t prev = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
-#pragma unroll 4
-        for (int r = 0; r < a.winH; r++) {
-            p += PP;
-            const uint32_t cur = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+#pragma unroll(WH ? 8 : 4)
+        for (int r = 0; r < winH; r++) {
+            const uint32_t cur = (uint32_t)p[(r + 1) * PP] | ((uint32_t)p[(r + 1) * PP + 1] << 8);
             const uint2 t = wrow[r * 32];
             uint32_t v = dp2a_s16u8(wtop, prev, t.x);
             v = dp2a_s16u8(wbot, cur, v);
@@ -208,12 +226,18 @@ __device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__re
 
 // One pyramidal pass for one point.  On entry (ox, oy) holds the initial flow if use_init.
 // On exit (ox, oy) = nextPts[k], status/err as cv2 (err = 0 where status == 0).
+template <int WW, int WH>
 __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, float ptx, float pty,
                                          bool use_init, float &ox, float &oy, int &status, float &err, int &iters,
                                          unsigned char *slab, int isr, int isw, int jsr, int jsw, int lane)
 {
     const float FLT_SCALE = 1.f / (1 << 20);
-    const int winW = a.winW, winH = a.winH;
+    const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
+    const int nstrips = WW ? lk_nstrips(WW) : a.nstrips, strip_cols = WW ? lk_strip_cols(WW) : a.strip_cols;
+    const int IPITCH = WW ? lk_ipitch(WW) : a.ipitch, JPITCH = WW ? lk_jpitch(WW) : a.jpitch;
+    const int DPITCH = WW ? lk_dpitch(WW) : a.dpitch;
+    const int JROWS = winH + 1 + 2 * LK_MARGIN;
+    const int IRPP = 32 / (IPITCH / 4), JRPP = 32 / (JPITCH / 4);
     const float halfx = (winW - 1) * 0.5f, halfy = (winH - 1) * 0.5f;
     uint2 *win = reinterpret_cast<uint2 *>(slab);
     uint32_t *dpatch = reinterpret_cast<uint32_t *>(slab + a.off_deriv);
@@ -244,8 +268,8 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
 
         // ---- one burst of async copies: I window, its Scharr planes (group 0), J search patch (group 1) -----------
         const int ipxa = ipx & ~3;
-        stage_bytes(LI, ipxa, ipy, winH + 1, a.ipitch, a.irpp, isr, isw, ipatch, lane);
-        stage_deriv(LI, a, ipx, ipy, dpatch, lane);
+        stage_bytes(LI, ipxa, ipy, winH + 1, IPITCH, IRPP, isr, isw, ipatch, lane);
+        stage_deriv<WW, WH>(LI, a, ipx, ipy, dpatch, lane);
         cp_async_commit();
         int px0 = 0, py0 = 0;
         bool staged = false;
@@ -253,7 +277,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             const int inx = cv_floor(nx), iny = cv_floor(ny);
             if (!window_oob(inx, iny, winW, winH, rows, cols)) {
                 px0 = (inx - LK_MARGIN) & ~3; py0 = iny - LK_MARGIN;
-                stage_bytes(LJ, px0, py0, a.jrows, a.jpitch, a.jrpp, jsr, jsw, jpatch, lane);
+                stage_bytes(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
                 staged = true;
             }
         }
@@ -267,9 +291,10 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
 
         // ---- template window: T0 = 256 - (Iw << 9), (Ix, Iy); structure tensor ------------------------------------
         long long sA11 = 0, sA12 = 0, sA22 = 0;
-        for (int s = 0; s < a.nstrips; s++) {
-            const int cs = s * a.strip_cols;
-            const bool active = lane < min(a.strip_cols, winW - cs);
+#pragma unroll
+        for (int s = 0; s < nstrips; s++) {
+            const int cs = s * strip_cols;
+            const bool active = lane < min(strip_cols, winW - cs);
             const uint8_t *ip = ipatch + (ipx - ipxa) + cs + lane;
             const uint32_t *dp = dpatch + cs + lane;
             uint2 *wrow = win + (s * winH) * 32 + lane;
@@ -278,11 +303,10 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             uint32_t dc = dp[0], dcr = dp[1];
             int d00x = (int)(short)(dc & 0xffffu), d00y = (int)dc >> 16;
             int d01x = (int)(short)(dcr & 0xffffu), d01y = (int)dcr >> 16;
-#pragma unroll 4
+#pragma unroll(WH ? 8 : 4)
             for (int r = 0; r < winH; r++) {
-                ip += a.ipitch; dp += a.dpitch;
-                const uint32_t cpair = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
-                dc = dp[0]; dcr = dp[1];
+                const uint32_t cpair = (uint32_t)ip[(r + 1) * IPITCH] | ((uint32_t)ip[(r + 1) * IPITCH + 1] << 8);
+                dc = dp[(r + 1) * DPITCH]; dcr = dp[(r + 1) * DPITCH + 1];
                 const int d10x = (int)(short)(dc & 0xffffu), d10y = (int)dc >> 16;
                 const int d11x = (int)(short)(dcr & 0xffffu), d11y = (int)dcr >> 16;
                 uint32_t v = dp2a_s16u8(wtop, ipair, 256u);
@@ -296,6 +320,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
                 wrow[r * 32] = t;
                 a11 += Ix * Ix; a12 += Ix * Iy; a22 += Iy * Iy;
                 ipair = cpair; d00x = d10x; d00y = d10y; d01x = d11x; d01y = d11y;
+                __syncwarp();            // the template slab overlaps the Scharr patch rows already consumed (see launch_lk)
             }
             sA11 += warp_sum_wide(a11); sA12 += warp_sum_wide(a12); sA22 += warp_sum_wide(a22);
         }
@@ -325,7 +350,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             if (!staged || (unsigned)(inx - px0) > (unsigned)max_off || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
                 px0 = (inx - LK_MARGIN) & ~3; py0 = iny - LK_MARGIN;
                 __syncwarp();
-                stage_bytes(LJ, px0, py0, a.jrows, a.jpitch, a.jrpp, jsr, jsw, jpatch, lane);
+                stage_bytes(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
                 cp_async_commit();
                 cp_async_wait<0>();
                 __syncwarp();
@@ -333,7 +358,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wtop, wbot, iw00, iw01, iw10, iw11);
             long long sb1, sb2;
-            window_pass<0>(a, jpatch, inx - px0, iny - py0, wtop, wbot, win, lane, sb1, sb2);
+            window_pass<0, WW, WH>(a, jpatch, inx - px0, iny - py0, wtop, wbot, win, lane, sb1, sb2);
             ++iters;
             const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE);
             const float b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
@@ -355,14 +380,14 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             if (!staged || (unsigned)(iqx - px0) > (unsigned)max_off || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
                 px0 = (iqx - LK_MARGIN) & ~3; py0 = iqy - LK_MARGIN;
                 __syncwarp();
-                stage_bytes(LJ, px0, py0, a.jrows, a.jpitch, a.jrpp, jsr, jsw, jpatch, lane);
+                stage_bytes(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
                 cp_async_commit();
                 cp_async_wait<0>();
                 __syncwarp();
             }
             bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), wtop, wbot, iw00, iw01, iw10, iw11);
             long long s1, s2;
-            window_pass<1>(a, jpatch, iqx - px0, iqy - py0, wtop, wbot, win, lane, s1, s2);
+            window_pass<1, WW, WH>(a, jpatch, iqx - px0, iqy - py0, wtop, wbot, win, lane, s1, s2);
             err = __fdiv_rn(__ll2float_rn(s2), (float)(32 * winW * winH));
         }
         __syncwarp();
@@ -371,6 +396,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
     if (!status && !(a.flags & IBT_LK_GET_MIN_EIGENVALS)) err = 0.f;
 }
 
+template <int WW, int WH>
 __global__ void __launch_bounds__(256)
 lk_kernel(const __grid_constant__ LKArgs a)
 {
@@ -378,7 +404,7 @@ lk_kernel(const __grid_constant__ LKArgs a)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char *slab = lk_smem + (size_t)wib * a.warp_smem;
     // lane -> (row, word) assignment of the two byte-patch layouts
-    const int ippw = a.ipitch >> 2, jppw = a.jpitch >> 2;
+    const int ippw = (WW ? lk_ipitch(WW) : a.ipitch) >> 2, jppw = (WW ? lk_jpitch(WW) : a.jpitch) >> 2;
     const int isr = lane / ippw, isw = lane - isr * ippw;
     const int jsr = lane / jppw, jsw = lane - jsr * jppw;
 
@@ -397,7 +423,7 @@ lk_kernel(const __grid_constant__ LKArgs a)
         int status, iters = 0;
         const bool use_init = pass == 0 && (a.flags & IBT_LK_USE_INITIAL_FLOW) != 0;
         if (use_init) { ox = a.p1[2 * k]; oy = a.p1[2 * k + 1]; }
-        lk_point(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, ox, oy, status, err, iters, slab, isr, isw, jsr, jsw,
+        lk_point<WW, WH>(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, ox, oy, status, err, iters, slab, isr, isw, jsr, jsw,
                  lane);
         if (pass == 0) it_f = iters; else it_b = iters;
         if (lane == 0) {
@@ -463,19 +489,25 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     for (int l = 0; l < A->nlevels; l++)
         if (A->rows[l] != B->rows[l] || A->cols[l] != B->cols[l]) return IBT_E_INVALID;
     a.winW = winW; a.winH = winH;
-    a.nstrips = (winW + 31) / 32;
-    a.strip_cols = (winW + a.nstrips - 1) / a.nstrips;
-    // every lane of every strip reads two adjacent elements per row, active or not: pitches keep those reads in the slab
-    const int reach = (a.nstrips - 1) * a.strip_cols + 33;
+    a.nstrips = lk_nstrips(winW);
+    a.strip_cols = lk_strip_cols(winW);
     a.tmpl_elems = a.nstrips * winH * 32;
-    a.dpitch = reach;
-    a.ipitch = (3 + reach + 3) & ~3;
-    a.jpitch = (2 * LK_MARGIN + 3 + reach + 3) & ~3;
+    a.dpitch = lk_dpitch(winW);
+    a.ipitch = lk_ipitch(winW);
+    a.jpitch = lk_jpitch(winW);
     a.jrows = winH + 1 + 2 * LK_MARGIN;
     a.irpp = 32 / (a.ipitch / 4);
     a.jrpp = 32 / (a.jpitch / 4);
-    size_t off = (size_t)a.tmpl_elems * sizeof(uint2);
-    a.off_deriv = (int)off;  off += (size_t)(winH + 1) * a.dpitch * 4;
+    // The Scharr patch is consumed row by row while the template rows are produced, so it OVERLAPS the template slab of
+    // the last strip: template row r (256 B) is written only after patch row r+1 has been read, and patch row r+1 starts
+    // at or after the end of template row r  <=>  D0 >= off_last + (256 - 4*dpitch) * winH.
+    const size_t off_last = (size_t)(a.nstrips - 1) * winH * 32 * sizeof(uint2);
+    const int slack = 256 - 4 * a.dpitch;
+    const size_t d0 = off_last + (slack > 0 ? (size_t)slack * winH : 0);
+    a.off_deriv = (int)d0;
+    size_t off = d0 + (size_t)(winH + 1) * a.dpitch * 4;
+    if (off < (size_t)a.tmpl_elems * sizeof(uint2)) off = (size_t)a.tmpl_elems * sizeof(uint2);
+    off = (off + 15) & ~(size_t)15;
     a.off_ipatch = (int)off; off += (size_t)(winH + 1) * a.ipitch;
     a.off_jpatch = (int)off; off += (size_t)a.jrows * a.jpitch;
     a.warp_smem = (int)((off + 15) & ~(size_t)15);
@@ -499,8 +531,16 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     static unsigned int *counters = nullptr;           // ring of work counters: one 4-byte slot per launch in flight
     static unsigned int next_slot = 0;
     constexpr unsigned int kSlots = 256;
+    void (*kern)(const LKArgs) = lk_kernel<0, 0>;      // generic window; the sizes the configs use are specialised
+    if (winW == 21 && winH == 21) kern = lk_kernel<21, 21>;
+    else if (winW == 31 && winH == 31) kern = lk_kernel<31, 31>;
+    else if (winW == 35 && winH == 35) kern = lk_kernel<35, 35>;
     if (!attr_set) {
-        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        const int lim = 200 * 1024;
+        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<21, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<31, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<35, 35>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         IBT_CUDA_TRY(cudaMalloc(&counters, kSlots * sizeof(unsigned int)));
         attr_set = true;
     }
@@ -509,7 +549,7 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     int blocks = kNumSMs * best_ctas;                   // persistent: one wave, warps pull points until none are left
     const int need = (a.n + wpc - 1) / wpc;
     if (blocks > need) blocks = need;
-    lk_kernel<<<blocks, wpc * 32, smem, st>>>(a);
+    kern<<<blocks, wpc * 32, smem, st>>>(a);
     return check_launch("ibt_lk");
 }
 
