@@ -2,96 +2,143 @@
 // (SURVEY.md A.2, A.4).  Replaces the buildOpticalFlowPyramid / calcScharrDeriv work that
 // cv2.calcOpticalFlowPyrLK repeats on every call (s1_lucaskanade_tracking.py:323,326).
 //
-// HBM-bound: per level-l pixel 1 B is read once, 4 B (int16 dx,dy interleaved) and 1/4 B
-// (level l+1) are written.  A CTA stages a (TH+3) x (TW+8) u8 halo tile in shared memory
-// (REFLECT_101 applied while staging), then every thread slides a 4-pixel-wide column strip down
-// 16 rows: the horizontal halves of both separable filters are computed once per staged row and
-// kept in registers, the vertical halves finish them; each derivative row leaves as one 16-byte
-// store per thread (512 contiguous bytes per warp).
+// HBM-bound: per level-l pixel 1 B is read once, 4 B (int16 dx,dy interleaved) and 1/4 B (level l+1) are written.
+// Persistent CTAs walk over 128 x (16*NW) pixel tiles with a two-stage cp.async pipeline: while the warps filter
+// tile t out of one shared-memory buffer, the 16-byte cp.async copies of tile t+1 are in flight into the other
+// (tiles touching the left/right image border take a byte path that resolves REFLECT_101; rows reflect by index).
+// Each lane slides a 4-pixel-wide strip down 16 rows: per row it reads its word and the two neighbouring words and
+// evaluates the horizontal halves of both separable filters with dp4a on funnel-shifted byte windows -- (3,10,3) and
+// (-1,0,1) for Scharr, (1,4,6,4,1) for pyrDown -- so no byte is ever unpacked; the vertical halves run on the per-lane
+// register history of the previous rows.  Each derivative row leaves as one 16-byte store per lane (512 contiguous
+// bytes per warp), each level-(l+1) row as one 2-byte store.  The grid is sized so that every CTA gets the same
+// number of tiles (no tail wave).
 #include "common.cuh"
 
 namespace ibt {
 
 constexpr int TW = 128;                 // tile width  (input pixels)
-constexpr int TH = 32;                  // tile height (input pixels), 2 warps x 16 rows
 constexpr int RPW = 16;                 // rows per warp
-constexpr int HX = 4;                   // staged columns left/right of the tile (keeps words aligned)
-constexpr int SROWS = TH + 3;           // rows y0-2 .. y0+TH
-constexpr int SWORDS = (TW + 2 * HX) / 4;   // 34 words per staged row (conflict-free word reads)
+constexpr int HXB = 16;                 // staged bytes left/right of the tile (keeps 16-byte chunks aligned)
+constexpr int SPITCH = TW + 2 * HXB;    // 160 bytes per staged row
 
-__device__ __forceinline__ uint32_t pack_i16(int lo, int hi)
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) { return (int)__dp4a(a, b, (unsigned)c); }
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
 {
-    return (static_cast<uint32_t>(lo) & 0xffffu) | (static_cast<uint32_t>(hi) << 16);
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_i16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+
+struct PyrArgs {
+    const uint8_t *src; int h, w; int64_t pitch;
+    uint8_t *deriv; int64_t dpitch;
+    uint8_t *down; int64_t downpitch;
+    int src_vec_ok, deriv_vec_ok, down_vec_ok;
+    int ntx, ntiles;
+};
+
+// stage bytes [x0-16, x0+144) of rows y0-2 .. y0+TH into `tile`: every 16-byte chunk that lies inside the row goes
+// as cp.async; the columns left of 0 / right of w-1 are filled in later from shared memory itself (reflect_tile)
+template <int NW>
+__device__ __forceinline__ void stage_tile(const PyrArgs &a, int t, uint8_t *tile, int tid)
+{
+    constexpr int TH = NW * RPW, SROWS = TH + 3, NT = NW * 32;
+    const int ty = t / a.ntx, tx = t - ty * a.ntx;
+    const int x0 = tx * TW, y0 = ty * TH;
+    if (a.src_vec_ok) {
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
+        const uint8_t *g0 = a.src + (x0 - HXB);
+#pragma unroll 2
+        for (int idx = tid; idx < SROWS * (SPITCH / 16); idx += NT) {
+            const int r = idx / (SPITCH / 16), c = idx - r * (SPITCH / 16);
+            const int gx = x0 - HXB + 16 * c;
+            if (gx >= 0 && gx + 16 <= a.pitch) {
+                const uint8_t *g = g0 + (int64_t)r101(y0 - 2 + r, a.h) * a.pitch + 16 * c;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + r * SPITCH + 16 * c), "l"(g) : "memory");
+            }
+        }
+    } else {
+        // unaligned image: byte path, only the bytes the filters read (columns x0-4 .. x0+TW+3), REFLECT_101 resolved here
+        for (int idx = tid; idx < SROWS * (TW + 8); idx += NT) {
+            const int r = idx / (TW + 8), c = idx - r * (TW + 8);
+            tile[r * SPITCH + (HXB - 4) + c] = a.src[(int64_t)r101(y0 - 2 + r, a.h) * a.pitch + r101(x0 - 4 + c, a.w)];
+        }
+    }
 }
 
-template <bool DERIV, bool DOWN>
-__global__ void __launch_bounds__(64)
-pyr_level_kernel(const uint8_t *__restrict__ src, int h, int w, int64_t pitch,
-                 uint8_t *__restrict__ deriv, int64_t dpitch,
-                 uint8_t *__restrict__ down, int64_t downpitch, int src_word_ok, int deriv_vec_ok)
+// REFLECT_101 columns of a staged tile, from the tile itself: -1 -> 1, -2 -> 2, w+k -> w-2-k.  Returns whether it wrote.
+template <int NW>
+__device__ __forceinline__ bool reflect_tile(const PyrArgs &a, int t, uint8_t *tile, int tid)
 {
-    __shared__ uint32_t tile[SROWS * SWORDS];
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-
-    // ---- stage the halo tile -------------------------------------------------------------
-    for (int idx = tid; idx < SROWS * SWORDS; idx += 64) {
-        const int r = idx / SWORDS, cw = idx - r * SWORDS;
-        const int gx = x0 - HX + 4 * cw;
-        const uint8_t *rowp = src + (int64_t)r101(y0 - 2 + r, h) * pitch;
-        uint32_t v;
-        if (src_word_ok && gx >= 0 && gx + 3 < w) {
-            v = __ldg(reinterpret_cast<const uint32_t *>(rowp + gx));
-        } else {
-            v = (uint32_t)rowp[r101(gx, w)] | ((uint32_t)rowp[r101(gx + 1, w)] << 8) |
-                ((uint32_t)rowp[r101(gx + 2, w)] << 16) | ((uint32_t)rowp[r101(gx + 3, w)] << 24);
+    constexpr int TH = NW * RPW, SROWS = TH + 3, NT = NW * 32;
+    const int tx = t % a.ntx;
+    const int x0 = tx * TW;
+    const bool left = x0 == 0, right = x0 + TW + 4 > a.w;
+    if (!a.src_vec_ok || !(left || right)) return false;
+    const int org = x0 - HXB;                         // image column of tile byte 0
+    for (int r = tid; r < SROWS; r += NT) {
+        uint8_t *row = tile + r * SPITCH;
+        if (left) {
+            row[HXB - 1] = row[HXB + r101(-1, a.w)];
+            row[HXB - 2] = row[HXB + r101(-2, a.w)];
         }
-        tile[idx] = v;
-    }
-    __syncthreads();
-
-    const int tx = tid & 31, wy = tid >> 5;
-    const int x = x0 + 4 * tx;
-    const int ybase = y0 + RPW * wy;
-    if (x >= w || ybase >= h) return;
-
-    // horizontal halves kept for the previous rows
-    int hx1[4], hx2[4], hs1[4], hs2[4];     // row j-1, row j-2
-    int hp[5][2];                           // pyrDown horizontal sums of rows j-4 .. j
+        if (right) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) { hx1[i] = hx2[i] = hs1[i] = hs2[i] = 0; }
-#pragma unroll
-    for (int i = 0; i < 5; i++) { hp[i][0] = hp[i][1] = 0; }
-
-    const uint32_t *trow = tile + (RPW * wy) * SWORDS + tx;
-#pragma unroll
-    for (int j = 0; j <= RPW + 2; j++) {            // staged rows ybase-2 .. ybase+16
-        const uint32_t w0 = trow[j * SWORDS], w1 = trow[j * SWORDS + 1], w2 = trow[j * SWORDS + 2];
-        // p[k] = pixel at column x - 4 + k
-        const int p2 = (w0 >> 16) & 0xff, p3 = w0 >> 24;
-        const int p4 = w1 & 0xff, p5 = (w1 >> 8) & 0xff, p6 = (w1 >> 16) & 0xff, p7 = w1 >> 24;
-        const int p8 = w2 & 0xff;
-        const int p[7] = {p2, p3, p4, p5, p6, p7, p8};   // p[k] here = column x - 2 + k
-
-        int hx[4], hs[4];
-        if (DERIV) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {                // column x+i is p[2+i]
-                hx[i] = p[3 + i] - p[1 + i];
-                hs[i] = 3 * (p[1 + i] + p[3 + i]) + 10 * p[2 + i];
+            for (int k = 0; k < 4; k++) {
+                const int c = a.w + k;
+                if (c - org < SPITCH) {
+                    int sc = r101(c, a.w) - org;
+                    if (sc < 0) sc = HXB + r101(c, a.w);      // tiny images: fold into the staged range
+                    row[c - org] = row[sc];
+                }
             }
-            if (j >= 3) {                                // emit derivative row of staged row j-1
-                const int yo = ybase + j - 3;
-                if (yo < h) {
+        }
+    }
+    return true;
+}
+
+template <bool DERIV, bool DOWN, int NW>
+__device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8_t *tile, int tid)
+{
+    constexpr int TH = NW * RPW;
+    const int ty = t / a.ntx, tx = t - ty * a.ntx;
+    const int lane = tid & 31, wy = tid >> 5;
+    const int x = tx * TW + 4 * lane;
+    const int ybase = ty * TH + RPW * wy;
+    const int h = a.h, w = a.w;
+    if (x >= w || ybase >= h) return;
+    const int oh = (h + 1) >> 1, ow = (w + 1) >> 1;
+
+    int hx1[4], hx2[4], hs1[4], hs2[4];     // Scharr horizontal halves of the two previous rows
+    int hp[4][2];                           // pyrDown horizontal sums of the four previous rows
+#pragma unroll
+    for (int i = 0; i < 4; i++) { hx1[i] = hx2[i] = hs1[i] = hs2[i] = 0; hp[i][0] = hp[i][1] = 0; }
+
+    const uint32_t *trow = reinterpret_cast<const uint32_t *>(tile + (RPW * wy) * SPITCH + HXB - 4) + lane;
+    uint8_t *dp = DERIV ? a.deriv + (int64_t)ybase * a.dpitch + (int64_t)x * 4 : nullptr;
+    const bool vec = a.deriv_vec_ok && x + 3 < w;
+#pragma unroll
+    for (int j = 0; j <= RPW + 2; j++) {                 // staged rows ybase-2 .. ybase+16
+        const uint32_t Lw = trow[j * (SPITCH / 4)], O = trow[j * (SPITCH / 4) + 1], Rw = trow[j * (SPITCH / 4) + 2];
+        // byte windows: w0 = (x-1..x+2), O = (x..x+3), w2 = (x+1..x+4), w3 = (x+2..x+5)
+        const uint32_t w0 = __funnelshift_r(Lw, O, 24);
+        const uint32_t w2 = __funnelshift_r(O, Rw, 8);
+        const uint32_t w3 = __funnelshift_r(O, Rw, 16);
+
+        if (DERIV && j >= 1) {
+            int hx[4], hs[4];
+            hs[0] = dp4a_uu(w0, 0x00030A03u, 0); hx[0] = dp4a_us(w0, 0x000100FF, 0);
+            hs[1] = dp4a_uu(O, 0x00030A03u, 0);  hx[1] = dp4a_us(O, 0x000100FF, 0);
+            hs[2] = dp4a_uu(w2, 0x00030A03u, 0); hx[2] = dp4a_us(w2, 0x000100FF, 0);
+            hs[3] = dp4a_uu(w3, 0x00030A03u, 0); hx[3] = dp4a_us(w3, 0x000100FF, 0);
+            if (j >= 3) {                                // derivative row of staged row j-1 = image row ybase+j-3
+                if (ybase + j - 3 < h) {
                     uint32_t o[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int dx = 3 * (hx2[i] + hx[i]) + 10 * hx1[i];
-                        const int dy = hs[i] - hs2[i];
-                        o[i] = pack_i16(dx, dy);
-                    }
-                    uint8_t *dp = deriv + (int64_t)yo * dpitch + (int64_t)x * 4;
-                    if (deriv_vec_ok && x + 3 < w) {
+                    for (int i = 0; i < 4; i++)
+                        o[i] = pack_i16(3 * (hx2[i] + hx[i]) + 10 * hx1[i], hs[i] - hs2[i]);
+                    if (vec) {
                         *reinterpret_cast<uint4 *>(dp) = make_uint4(o[0], o[1], o[2], o[3]);
                     } else {
 #pragma unroll
@@ -99,31 +146,73 @@ pyr_level_kernel(const uint8_t *__restrict__ src, int h, int w, int64_t pitch,
                             if (x + i < w) reinterpret_cast<uint32_t *>(dp)[i] = o[i];
                     }
                 }
+                dp += a.dpitch;
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) { hx2[i] = hx1[i]; hx1[i] = hx[i]; hs2[i] = hs1[i]; hs1[i] = hs[i]; }
         }
         if (DOWN) {
-#pragma unroll
-            for (int o = 0; o < 2; o++) {                // output column x/2+o is centred on p[2+2o]
-                hp[4][o] = p[2 * o] + p[4 + 2 * o] + 4 * (p[1 + 2 * o] + p[3 + 2 * o]) + 6 * p[2 + 2 * o];
-            }
+            // output column x/2 is centred on x, x/2+1 on x+2: taps (1,4,6,4,1)
+            const uint32_t v0 = __funnelshift_r(Lw, O, 16);               // (x-2 .. x+1)
+            const int h0 = dp4a_uu(O, 0x00010000u, dp4a_uu(v0, 0x04060401u, 0));
+            const int h1 = dp4a_uu(w3, 0x00010000u, dp4a_uu(O, 0x04060401u, 0));
             if (j >= 4 && (j & 1) == 0) {                // centre row = staged row j-2 = image row ybase+j-4
                 const int Y = (ybase + j - 4) >> 1;
-                const int oh = (h + 1) >> 1, ow = (w + 1) >> 1;
                 if (Y < oh) {
-#pragma unroll
-                    for (int o = 0; o < 2; o++) {
-                        const int X = (x >> 1) + o;
-                        const int v = (hp[0][o] + hp[4][o] + 4 * (hp[1][o] + hp[3][o]) + 6 * hp[2][o] + 128) >> 8;
-                        if (X < ow) down[(int64_t)Y * downpitch + X] = (uint8_t)v;
+                    const int X = x >> 1;
+                    const int o0 = (hp[0][0] + h0 + 4 * (hp[1][0] + hp[3][0]) + 6 * hp[2][0] + 128) >> 8;
+                    const int o1 = (hp[0][1] + h1 + 4 * (hp[1][1] + hp[3][1]) + 6 * hp[2][1] + 128) >> 8;
+                    uint8_t *op = a.down + (int64_t)Y * a.downpitch + X;
+                    if (a.down_vec_ok && X + 1 < ow) {
+                        *reinterpret_cast<uint16_t *>(op) = (uint16_t)(o0 | (o1 << 8));
+                    } else {
+                        op[0] = (uint8_t)o0;
+                        if (X + 1 < ow) op[1] = (uint8_t)o1;
                     }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) { hp[i][0] = hp[i + 1][0]; hp[i][1] = hp[i + 1][1]; }
+            for (int i = 0; i < 3; i++) { hp[i][0] = hp[i + 1][0]; hp[i][1] = hp[i + 1][1]; }
+            hp[3][0] = h0; hp[3][1] = h1;
         }
     }
+}
+
+template <bool DERIV, bool DOWN, int NW>
+__global__ void __launch_bounds__(NW * 32)
+pyr_level_kernel(const __grid_constant__ PyrArgs a)
+{
+    constexpr int SROWS = NW * RPW + 3;
+    __shared__ __align__(16) uint8_t tiles[2][SROWS * SPITCH];
+    const int tid = threadIdx.x;
+    int t = blockIdx.x, buf = 0;
+    if (t < a.ntiles) stage_tile<NW>(a, t, tiles[0], tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (; t < a.ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        if (tn < a.ntiles) stage_tile<NW>(a, tn, tiles[buf ^ 1], tid);       // prefetch the next tile of this CTA
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");                  // tile t has landed
+        __syncthreads();
+        if (reflect_tile<NW>(a, t, tiles[buf], tid)) __syncthreads();
+        filter_tile<DERIV, DOWN, NW>(a, t, tiles[buf], tid);
+        __syncthreads();                                                      // buffer may be refilled next round
+        buf ^= 1;
+    }
+}
+
+template <bool DERIV, bool DOWN, int NW>
+static void launch_variant(const PyrArgs &a0, cudaStream_t st)
+{
+    PyrArgs a = a0;
+    constexpr int TH = NW * RPW;
+    a.ntx = (a.w + TW - 1) / TW;
+    a.ntiles = a.ntx * ((a.h + TH - 1) / TH);
+    // persistent CTAs, every CTA the same number of tiles: no partial last wave
+    const int resident = kNumSMs * (NW == 4 ? 7 : 16);
+    const int per_cta = (a.ntiles + resident - 1) / resident;
+    const int blocks = (a.ntiles + per_cta - 1) / per_cta;
+    pyr_level_kernel<DERIV, DOWN, NW><<<blocks, NW * 32, 0, st>>>(a);
 }
 
 static int launch_level(const uint8_t *src, int h, int w, int64_t pitch, int16_t *deriv, int64_t dpitch,
@@ -134,16 +223,19 @@ static int launch_level(const uint8_t *src, int h, int w, int64_t pitch, int16_t
     if (deriv && (dpitch < (int64_t)w * 4 || dpitch % 4 != 0 || reinterpret_cast<uintptr_t>(deriv) % 4 != 0))
         return IBT_E_INVALID;
     if (down && downpitch < (w + 1) / 2) return IBT_E_INVALID;
-    const int src_word_ok = (reinterpret_cast<uintptr_t>(src) % 4 == 0) && (pitch % 4 == 0);
-    const int deriv_vec_ok = deriv && (reinterpret_cast<uintptr_t>(deriv) % 16 == 0) && (dpitch % 16 == 0);
-    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH);
-    uint8_t *d8 = reinterpret_cast<uint8_t *>(deriv);
-    if (deriv && down)
-        pyr_level_kernel<true, true><<<grid, 64, 0, st>>>(src, h, w, pitch, d8, dpitch, down, downpitch, src_word_ok, deriv_vec_ok);
-    else if (deriv)
-        pyr_level_kernel<true, false><<<grid, 64, 0, st>>>(src, h, w, pitch, d8, dpitch, nullptr, 0, src_word_ok, deriv_vec_ok);
-    else
-        pyr_level_kernel<false, true><<<grid, 64, 0, st>>>(src, h, w, pitch, nullptr, 0, down, downpitch, src_word_ok, 0);
+    PyrArgs a;
+    a.src = src; a.h = h; a.w = w; a.pitch = pitch;
+    a.deriv = reinterpret_cast<uint8_t *>(deriv); a.dpitch = dpitch;
+    a.down = down; a.downpitch = downpitch;
+    a.src_vec_ok = (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (pitch % 16 == 0);
+    a.deriv_vec_ok = deriv && (reinterpret_cast<uintptr_t>(deriv) % 16 == 0) && (dpitch % 16 == 0);
+    a.down_vec_ok = down && (reinterpret_cast<uintptr_t>(down) % 2 == 0) && (downpitch % 2 == 0);
+    a.ntx = a.ntiles = 0;
+    // big levels: 128 x 64 tiles (4 warps); small levels: 128 x 16 tiles (1 warp) so that they still spread over the SMs
+    const bool big = (int64_t)((w + TW - 1) / TW) * ((h + 63) / 64) >= 2 * kNumSMs;
+    if (deriv && down) { if (big) launch_variant<true, true, 4>(a, st); else launch_variant<true, true, 1>(a, st); }
+    else if (deriv)    { if (big) launch_variant<true, false, 4>(a, st); else launch_variant<true, false, 1>(a, st); }
+    else               { if (big) launch_variant<false, true, 4>(a, st); else launch_variant<false, true, 1>(a, st); }
     return check_launch("ibt_pyr_level_u8");
 }
 
