@@ -47,15 +47,17 @@ __device__ __forceinline__ void stage_tile(const PyrArgs &a, int t, uint8_t *til
     const int ty = t / a.ntx, tx = t - ty * a.ntx;
     const int x0 = tx * TW, y0 = ty * TH;
     if (a.src_vec_ok) {
-        const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
-        const uint8_t *g0 = a.src + (x0 - HXB);
+        // thread -> (row r0 + k*RSTEP, chunk c): no division in the loop, one REFLECT_101 row lookup per copy
+        constexpr int CH = SPITCH / 16, RSTEP = NT / CH;
+        const int r0 = tid / CH, c = tid - r0 * CH;
+        const int gx = x0 - HXB + 16 * c;
+        if (r0 < RSTEP && gx >= 0 && gx + 16 <= a.pitch) {
+            const unsigned sdst = (unsigned)__cvta_generic_to_shared(tile) + 16 * c;
+            const uint8_t *g0 = a.src + gx;
 #pragma unroll 2
-        for (int idx = tid; idx < SROWS * (SPITCH / 16); idx += NT) {
-            const int r = idx / (SPITCH / 16), c = idx - r * (SPITCH / 16);
-            const int gx = x0 - HXB + 16 * c;
-            if (gx >= 0 && gx + 16 <= a.pitch) {
-                const uint8_t *g = g0 + (int64_t)r101(y0 - 2 + r, a.h) * a.pitch + 16 * c;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + r * SPITCH + 16 * c), "l"(g) : "memory");
+            for (int r = r0; r < SROWS; r += RSTEP) {
+                const uint8_t *g = g0 + (int64_t)r101(y0 - 2 + r, a.h) * a.pitch;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + r * SPITCH), "l"(g) : "memory");
             }
         }
     } else {
@@ -98,7 +100,8 @@ __device__ __forceinline__ bool reflect_tile(const PyrArgs &a, int t, uint8_t *t
     return true;
 }
 
-template <bool DERIV, bool DOWN, int NW>
+// FULL: the tile lies completely inside the image (no per-row / per-column bounds checks)
+template <bool DERIV, bool DOWN, int NW, bool FULL>
 __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8_t *tile, int tid)
 {
     constexpr int TH = NW * RPW;
@@ -107,7 +110,7 @@ __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8
     const int x = tx * TW + 4 * lane;
     const int ybase = ty * TH + RPW * wy;
     const int h = a.h, w = a.w;
-    if (x >= w || ybase >= h) return;
+    if (!FULL && (x >= w || ybase >= h)) return;
     const int oh = (h + 1) >> 1, ow = (w + 1) >> 1;
 
     int hx1[4], hx2[4], hs1[4], hs2[4];     // Scharr horizontal halves of the two previous rows
@@ -117,7 +120,9 @@ __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8
 
     const uint32_t *trow = reinterpret_cast<const uint32_t *>(tile + (RPW * wy) * SPITCH + HXB - 4) + lane;
     uint8_t *dp = DERIV ? a.deriv + (int64_t)ybase * a.dpitch + (int64_t)x * 4 : nullptr;
-    const bool vec = a.deriv_vec_ok && x + 3 < w;
+    const bool vec = a.deriv_vec_ok && (FULL || x + 3 < w);
+    uint8_t *op = DOWN ? a.down + (int64_t)(ybase >> 1) * a.downpitch + (x >> 1) : nullptr;
+    const bool dvec = a.down_vec_ok && (FULL || (x >> 1) + 1 < ow);
 #pragma unroll
     for (int j = 0; j <= RPW + 2; j++) {                 // staged rows ybase-2 .. ybase+16
         const uint32_t Lw = trow[j * (SPITCH / 4)], O = trow[j * (SPITCH / 4) + 1], Rw = trow[j * (SPITCH / 4) + 2];
@@ -133,7 +138,7 @@ __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8
             hs[2] = dp4a_uu(w2, 0x00030A03u, 0); hx[2] = dp4a_us(w2, 0x000100FF, 0);
             hs[3] = dp4a_uu(w3, 0x00030A03u, 0); hx[3] = dp4a_us(w3, 0x000100FF, 0);
             if (j >= 3) {                                // derivative row of staged row j-1 = image row ybase+j-3
-                if (ybase + j - 3 < h) {
+                if (FULL || ybase + j - 3 < h) {
                     uint32_t o[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++)
@@ -157,19 +162,17 @@ __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8
             const int h0 = dp4a_uu(O, 0x00010000u, dp4a_uu(v0, 0x04060401u, 0));
             const int h1 = dp4a_uu(w3, 0x00010000u, dp4a_uu(O, 0x04060401u, 0));
             if (j >= 4 && (j & 1) == 0) {                // centre row = staged row j-2 = image row ybase+j-4
-                const int Y = (ybase + j - 4) >> 1;
-                if (Y < oh) {
-                    const int X = x >> 1;
+                if (FULL || ((ybase + j - 4) >> 1) < oh) {
                     const int o0 = (hp[0][0] + h0 + 4 * (hp[1][0] + hp[3][0]) + 6 * hp[2][0] + 128) >> 8;
                     const int o1 = (hp[0][1] + h1 + 4 * (hp[1][1] + hp[3][1]) + 6 * hp[2][1] + 128) >> 8;
-                    uint8_t *op = a.down + (int64_t)Y * a.downpitch + X;
-                    if (a.down_vec_ok && X + 1 < ow) {
+                    if (dvec) {
                         *reinterpret_cast<uint16_t *>(op) = (uint16_t)(o0 | (o1 << 8));
                     } else {
                         op[0] = (uint8_t)o0;
-                        if (X + 1 < ow) op[1] = (uint8_t)o1;
+                        if ((x >> 1) + 1 < ow) op[1] = (uint8_t)o1;
                     }
                 }
+                op += a.downpitch;
             }
 #pragma unroll
             for (int i = 0; i < 3; i++) { hp[i][0] = hp[i + 1][0]; hp[i][1] = hp[i + 1][1]; }
@@ -179,7 +182,7 @@ __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8
 }
 
 template <bool DERIV, bool DOWN, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 7 : 16)
 pyr_level_kernel(const __grid_constant__ PyrArgs a)
 {
     constexpr int SROWS = NW * RPW + 3;
@@ -195,7 +198,13 @@ pyr_level_kernel(const __grid_constant__ PyrArgs a)
         asm volatile("cp.async.wait_group 1;" ::: "memory");                  // tile t has landed
         __syncthreads();
         if (reflect_tile<NW>(a, t, tiles[buf], tid)) __syncthreads();
-        filter_tile<DERIV, DOWN, NW>(a, t, tiles[buf], tid);
+        {
+            constexpr int TH = NW * RPW;
+            const int ty = t / a.ntx, tx = t - ty * a.ntx;
+            const bool full = (tx + 1) * TW <= a.w && (ty + 1) * TH <= a.h;
+            if (full) filter_tile<DERIV, DOWN, NW, true>(a, t, tiles[buf], tid);
+            else filter_tile<DERIV, DOWN, NW, false>(a, t, tiles[buf], tid);
+        }
         __syncthreads();                                                      // buffer may be refilled next round
         buf ^= 1;
     }
