@@ -219,48 +219,71 @@ rs_count_kernel(const unsigned long long *__restrict__ keys, uint32_t n, int shi
     blockhist[threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
 }
 
-// exclusive scan of `len` uint32 in place, single block of 1024 threads, 8 elements per thread per round
+// exclusive scan of uint32 in place.  Block b scans its SCAN_TILE elements; with `block_sums` the block total goes there
+// (phase 1 of the hierarchical scan), with `block_offs` the scanned totals are added back (phase 3).
+constexpr int SCAN_EPT = 8, SCAN_TILE = 1024 * SCAN_EPT;
+
 __global__ void __launch_bounds__(1024)
-scan_kernel(uint32_t *__restrict__ data, uint32_t len, uint32_t *__restrict__ total_out)
+scan_tile_kernel(uint32_t *__restrict__ data, uint32_t len, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ total_out)
 {
     __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int EPT = 8;
-    for (uint32_t base = 0; base < len; base += 1024 * EPT) {
-        const uint32_t i0 = base + threadIdx.x * EPT;
-        uint32_t v[EPT], sum = 0;
+    const uint32_t i0 = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_EPT;
+    uint32_t v[SCAN_EPT], sum = 0;
 #pragma unroll
-        for (int e = 0; e < EPT; e++) { v[e] = (i0 + e < len) ? data[i0 + e] : 0; sum += v[e]; }
-        uint32_t inc = sum;
+    for (int e = 0; e < SCAN_EPT; e++) { v[e] = (i0 + e < len) ? data[i0 + e] : 0; sum += v[e]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t tmp = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += tmp;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = warp_tot[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t tmp = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += tmp;
+            const uint32_t tmp = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += tmp;
         }
-        if (lane == 31) warp_tot[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = warp_tot[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t tmp = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += tmp;
-            }
-            warp_tot[lane] = w;              // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t c = carry;
-        uint32_t run = c + (wid ? warp_tot[wid - 1] : 0) + inc - sum;
-#pragma unroll
-        for (int e = 0; e < EPT; e++) { if (i0 + e < len) data[i0 + e] = run; run += v[e]; }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = run;
-        __syncthreads();
+        warp_tot[lane] = w;              // inclusive over warps
     }
-    if (total_out && threadIdx.x == 0) *total_out = carry;
+    __syncthreads();
+    uint32_t run = (wid ? warp_tot[wid - 1] : 0) + inc - sum;
+#pragma unroll
+    for (int e = 0; e < SCAN_EPT; e++) { if (i0 + e < len) data[i0 + e] = run; run += v[e]; }
+    if (threadIdx.x == 1023) {
+        if (block_sums) block_sums[blockIdx.x] = run;
+        if (total_out) *total_out = run;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+scan_add_kernel(uint32_t *__restrict__ data, uint32_t len, const uint32_t *__restrict__ block_offs, uint32_t nblocks,
+                uint32_t *__restrict__ total_out)
+{
+    const uint32_t off = block_offs[blockIdx.x];
+    const uint32_t i0 = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_EPT;
+#pragma unroll
+    for (int e = 0; e < SCAN_EPT; e++) if (i0 + e < len) data[i0 + e] += off;
+    // grand total = offset of the last block + its own sum, which phase 1 left in block_offs[nblocks] (see scan_u32)
+    if (total_out && blockIdx.x == 0 && threadIdx.x == 0) *total_out = block_offs[nblocks];
+}
+
+// exclusive scan of data[0..len) in place; *total_out (device, optional) receives the grand total.
+// scratch: (len / SCAN_TILE + 2) uint32.  len up to SCAN_TILE^2 (67 M).
+static void scan_u32(uint32_t *data, uint32_t len, uint32_t *total_out, uint32_t *scratch, cudaStream_t st)
+{
+    const uint32_t nb = (len + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb <= 1) {
+        scan_tile_kernel<<<1, 1024, 0, st>>>(data, len, nullptr, total_out);
+        return;
+    }
+    scan_tile_kernel<<<nb, 1024, 0, st>>>(data, len, scratch, nullptr);
+    // scan the nb block sums; the total lands in scratch[nb]
+    scan_tile_kernel<<<1, 1024, 0, st>>>(scratch, nb, nullptr, scratch + nb);
+    scan_add_kernel<<<nb, 1024, 0, st>>>(data, len, scratch, nb, total_out);
 }
 
 __global__ void __launch_bounds__(256)
@@ -409,7 +432,7 @@ write_corners_kernel(const uint32_t *__restrict__ pos, const uint8_t *__restrict
 // workspace layout
 struct GfttLayout {
     size_t off_cnt, off_eig, off_keys0, off_keys1, off_blockhist, off_pos, off_state, off_cells, off_fill, off_items,
-        off_blockcnt, total;
+        off_blockcnt, off_scan, total;
     uint32_t cap, max_sort_blocks, max_cells;
 };
 static GfttLayout gftt_layout(int H, int W)
@@ -432,6 +455,7 @@ static GfttLayout gftt_layout(int H, int W)
     L.off_fill = o; o = up(o + (size_t)L.max_cells * 4);
     L.off_items = o; o = up(o + (size_t)L.cap * 4);
     L.off_blockcnt = o; o = up(o + ((size_t)L.cap / 256 + 2) * 4);
+    L.off_scan = o; o = up(o + ((size_t)L.max_cells / SCAN_TILE + 4) * 4);
     L.total = o;
     return L;
 }
@@ -473,6 +497,7 @@ IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, in
     uint32_t *cell_fill = reinterpret_cast<uint32_t *>(ws + L.off_fill);
     uint32_t *items = reinterpret_cast<uint32_t *>(ws + L.off_items);
     uint32_t *blockcnt = reinterpret_cast<uint32_t *>(ws + L.off_blockcnt);
+    uint32_t *scan_scratch = reinterpret_cast<uint32_t *>(ws + L.off_scan);
     *out_count = 0;
 
     IBT_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(GfttCounters), st));
@@ -498,7 +523,7 @@ IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, in
         for (int p = 0; p < 8; p++) {
             if (p > hi_addr_byte && p < 4) continue;
             rs_count_kernel<<<nblocks, 256, 0, st>>>(src, n, 8 * p, nblocks, blockhist);
-            scan_kernel<<<1, 1024, 0, st>>>(blockhist, 256u * nblocks, nullptr);
+            scan_u32(blockhist, 256u * nblocks, nullptr, scan_scratch, st);
             rs_scatter_kernel<<<nblocks, 256, 0, st>>>(src, dst, n, 8 * p, nblocks, blockhist);
             unsigned long long *t = src; src = dst; dst = t;
         }
@@ -519,7 +544,7 @@ IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, in
     uint32_t nout = n;
     if (cull) {
         IBT_CUDA_TRY(cudaMemsetAsync(cell_fill, 0, (size_t)ncells * 4, st));
-        scan_kernel<<<1, 1024, 0, st>>>(cell_start, ncells + 1, nullptr);
+        scan_u32(cell_start, ncells + 1, nullptr, scan_scratch, st);
         cell_fill_kernel<<<nb, 256, 0, st>>>(pos, n, cell, gw, cell_start, cell_fill, items);
         const float md2 = (float)(minDistance * minDistance);
         int round = 0;
@@ -536,7 +561,7 @@ IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, in
             if (round > (1 << 20)) return IBT_E_CUDA;
         }
         accepted_count_kernel<<<nb, 256, 0, st>>>(state, n, blockcnt);
-        scan_kernel<<<1, 1024, 0, st>>>(blockcnt, nb, &cnt->nacc);
+        scan_u32(blockcnt, nb, &cnt->nacc, scan_scratch, st);
         write_corners_kernel<<<nb, 256, 0, st>>>(pos, state, n, blockcnt, limit, out_xy);
         if ((rc = check_launch("write_corners_kernel"))) return rc;
         IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
