@@ -23,16 +23,24 @@ inline int check_launch(const char *where)
         if (e__ != cudaSuccess) { ::ibt::set_last_error(e__, #expr); return IBT_E_CUDA; } \
     } while (0)
 
-// REFLECT_101 index for any i (period 2(n-1)); the common cases cost two compares.
+// REFLECT_101 index for any i (period 2(n-1)).  The common cases (inside, or one reflection) cost a few compares;
+// indices further out (tiny images under big windows) take the out-of-line modulo path.
+__host__ __device__ __noinline__ inline int r101_far(int i, int n)
+{
+    if (n == 1) return 0;
+    const int p = 2 * (n - 1);
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - i;
+}
 __host__ __device__ __forceinline__ int r101(int i, int n)
 {
     if (i >= 0 && i < n) return i;
-    if (n == 1) return 0;
     if (i < 0) i = -i;                   // -1 -> 1
     if (i < n) return i;
-    int p = 2 * (n - 1);
-    i %= p;
-    return i < n ? i : p - i;
+    const int j = 2 * (n - 1) - i;       // n -> n-2
+    if (j >= 0) return j;
+    return r101_far(i, n);
 }
 
 constexpr int kNumSMs = 148;             // B200: 2 dies x 74 SMs

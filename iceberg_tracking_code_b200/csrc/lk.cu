@@ -121,6 +121,25 @@ __device__ __forceinline__ bool window_oob(int ix, int iy, int winW, int winH, i
 }
 
 // ---- staging ---------------------------------------------------------------------------------------------
+// Border variant of stage_bytes: REFLECT_101 gather (column indices resolved once per lane, rows batched four at a time).
+// Kept out of line: it is rare and would otherwise bloat the hot instruction stream.
+__device__ __noinline__ void stage_bytes_border(const LKLevel &L, int x0a, int y0, int nrows, int pitch, uint8_t *dst, int lane)
+{
+    for (int c = lane; c < pitch; c += 32) {
+        const uint8_t *s = L.img + r101(x0a + c, L.cols);
+        uint8_t *d = dst + c;
+        int r = 0;
+        for (; r + 4 <= nrows; r += 4) {
+            const uint8_t v0 = __ldg(s + (int64_t)r101(y0 + r, L.rows) * L.img_pitch);
+            const uint8_t v1 = __ldg(s + (int64_t)r101(y0 + r + 1, L.rows) * L.img_pitch);
+            const uint8_t v2 = __ldg(s + (int64_t)r101(y0 + r + 2, L.rows) * L.img_pitch);
+            const uint8_t v3 = __ldg(s + (int64_t)r101(y0 + r + 3, L.rows) * L.img_pitch);
+            d[r * pitch] = v0; d[(r + 1) * pitch] = v1; d[(r + 2) * pitch] = v2; d[(r + 3) * pitch] = v3;
+        }
+        for (; r < nrows; r++) d[r * pitch] = __ldg(s + (int64_t)r101(y0 + r, L.rows) * L.img_pitch);
+    }
+}
+
 // Stage image rows [y0, y0+nrows) x bytes [x0a, x0a+pitch) (x0a a multiple of 4) into dst (row pitch `pitch`).
 // Interior patches go as 4-byte cp.async (lane -> (row sr + k*rpp, word sw)); patches that touch the border are
 // gathered through REFLECT_101 (column indices resolved once per lane, rows batched four at a time).
@@ -142,20 +161,19 @@ __device__ __forceinline__ void stage_bytes(const LKLevel &L, int x0a, int y0, i
             }
         }
     } else {
-        for (int c = lane; c < pitch; c += 32) {
-            const uint8_t *s = L.img + r101(x0a + c, L.cols);
-            uint8_t *d = dst + c;
-            int r = 0;
-            for (; r + 4 <= nrows; r += 4) {
-                const uint8_t v0 = __ldg(s + (int64_t)r101(y0 + r, L.rows) * L.img_pitch);
-                const uint8_t v1 = __ldg(s + (int64_t)r101(y0 + r + 1, L.rows) * L.img_pitch);
-                const uint8_t v2 = __ldg(s + (int64_t)r101(y0 + r + 2, L.rows) * L.img_pitch);
-                const uint8_t v3 = __ldg(s + (int64_t)r101(y0 + r + 3, L.rows) * L.img_pitch);
-                d[r * pitch] = v0; d[(r + 1) * pitch] = v1; d[(r + 2) * pitch] = v2; d[(r + 3) * pitch] = v3;
-            }
-            for (; r < nrows; r++) d[r * pitch] = __ldg(s + (int64_t)r101(y0 + r, L.rows) * L.img_pitch);
-        }
+        stage_bytes_border(L, x0a, y0, nrows, pitch, dst, lane);
     }
+}
+
+// Re-stage the J patch synchronously (the window drifted out of the prefetched patch): rare, kept out of line.
+__device__ __noinline__ void restage_sync(const LKLevel &L, int x0a, int y0, int nrows, int pitch, int rpp, int sr, int sw,
+                                          uint8_t *dst, int lane)
+{
+    __syncwarp();
+    stage_bytes(L, x0a, y0, nrows, pitch, rpp, sr, sw, dst, lane);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
 }
 
 // Stage the Scharr planes of the template window: rows [y0, y0+winH], columns [x0, x0+winW]; zero outside the image.
@@ -204,7 +222,7 @@ __device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__re
         const bool active = lane < min(strip_cols, winW - cs);
         int b1 = 0, b2 = 0;
         uint32_t prev = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
-#pragma unroll(WH ? 8 : 4)
+#pragma unroll(MODE == 0 ? (WH ? 8 : 4) : 1)
         for (int r = 0; r < winH; r++) {
             const uint32_t cur = (uint32_t)p[(r + 1) * PP] | ((uint32_t)p[(r + 1) * PP + 1] << 8);
             const uint2 t = wrow[r * 32];
@@ -303,7 +321,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             uint32_t dc = dp[0], dcr = dp[1];
             int d00x = (int)(short)(dc & 0xffffu), d00y = (int)dc >> 16;
             int d01x = (int)(short)(dcr & 0xffffu), d01y = (int)dcr >> 16;
-#pragma unroll(WH ? 8 : 4)
+#pragma unroll 4
             for (int r = 0; r < winH; r++) {
                 const uint32_t cpair = (uint32_t)ip[(r + 1) * IPITCH] | ((uint32_t)ip[(r + 1) * IPITCH + 1] << 8);
                 dc = dp[(r + 1) * DPITCH]; dcr = dp[(r + 1) * DPITCH + 1];
@@ -349,11 +367,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             }
             if (!staged || (unsigned)(inx - px0) > (unsigned)max_off || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
                 px0 = (inx - LK_MARGIN) & ~3; py0 = iny - LK_MARGIN;
-                __syncwarp();
-                stage_bytes(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
-                cp_async_commit();
-                cp_async_wait<0>();
-                __syncwarp();
+                restage_sync(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
                 staged = true;
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wtop, wbot, iw00, iw01, iw10, iw11);
@@ -379,11 +393,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             if (window_oob(iqx, iqy, winW, winH, rows, cols)) { status = 0; err = 0.f; continue; }
             if (!staged || (unsigned)(iqx - px0) > (unsigned)max_off || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
                 px0 = (iqx - LK_MARGIN) & ~3; py0 = iqy - LK_MARGIN;
-                __syncwarp();
-                stage_bytes(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
-                cp_async_commit();
-                cp_async_wait<0>();
-                __syncwarp();
+                restage_sync(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
             }
             bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), wtop, wbot, iw00, iw01, iw10, iw11);
             long long s1, s2;
