@@ -14,7 +14,7 @@ is timed separately ("gftt_ms").  metric = tracked points / s (= 20 000 x frame 
 
   value : inputs (RGB frames, points) resident in HBM; CUDA events on the launch stream; max over ranks.
   e2e   : the public host API (SequenceTracker.upload/prepare/track) with PINNED HOST frames: every step copies its
-          72 MB RGB frame host->device and reads p1 / FB distance / alive back to the host, inside the timed region.
+          72 MB RGB frame host->device and reads p1 / FB distance back to the host, inside the timed region.
   --impl reference : the reference's own CPU implementation of the same step -- the cv2 calls of s1:311,323,326 +
           the numpy FB arithmetic of s1:329-333 -- on the host cores (falls back to the C oracle port when cv2 is absent).
 """
@@ -48,7 +48,7 @@ def pingpong(i):
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons during the timed region (NVML; nvidia-smi as fallback)."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -156,7 +156,7 @@ def run_cpu(frames_np, grays_np, pts_np, steps, warmup, budget_s=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
