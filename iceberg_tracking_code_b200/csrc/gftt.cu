@@ -18,6 +18,7 @@
 //                        final and monotone, so rounds may read each other's fresh or stale states.
 //        compaction      accepted candidates in rank order -> (x, y) float32, first maxCorners
 #include "common.cuh"
+#include <stddef.h>
 #include <string.h>
 
 namespace ibt {
@@ -59,15 +60,25 @@ eig_kernel(const uint8_t *__restrict__ img, int H, int W, int64_t pitch, int bs,
     uint32_t lmax = 0;
     const int nrows = min(ERS, H - Y0) + bs - 1;
     int slot = 0;
-    for (int k = 0; k < nrows; k++) {
-        const int py = r101(Y0 + a0 + k, H);
-        const uint8_t *r0 = img + (int64_t)r101(py - 1, H) * pitch;
-        const uint8_t *r1 = img + (int64_t)py * pitch;
+    // the 3x3 bytes of support row k+1 are fetched before the barrier of row k: the loads fly during the window sums
+    int b00, b01, b02, b10, b12, b20, b21, b22;
+    {
+        const int py = r101(Y0 + a0, H);
+        const uint8_t *r0 = img + (int64_t)r101(py - 1, H) * pitch, *r1 = img + (int64_t)py * pitch;
         const uint8_t *r2 = img + (int64_t)r101(py + 1, H) * pitch;
-        const int sx = (r0[xp] + 2 * r1[xp] + r2[xp]) - (r0[xm] + 2 * r1[xm] + r2[xm]);
-        const int sy = (r2[xm] + 2 * r2[px] + r2[xp]) - (r0[xm] + 2 * r0[px] + r0[xp]);
+        b00 = r0[xm]; b01 = r0[px]; b02 = r0[xp]; b10 = r1[xm]; b12 = r1[xp]; b20 = r2[xm]; b21 = r2[px]; b22 = r2[xp];
+    }
+    for (int k = 0; k < nrows; k++) {
+        const int sx = (b02 + 2 * b12 + b22) - (b00 + 2 * b10 + b20);
+        const int sy = (b20 + 2 * b21 + b22) - (b00 + 2 * b01 + b02);
         int *pb = prod + (k & 1) * 3 * EW;
         pb[t] = sx * sx; pb[EW + t] = sx * sy; pb[2 * EW + t] = sy * sy;
+        if (k + 1 < nrows) {
+            const int py = r101(Y0 + a0 + k + 1, H);
+            const uint8_t *r0 = img + (int64_t)r101(py - 1, H) * pitch, *r1 = img + (int64_t)py * pitch;
+            const uint8_t *r2 = img + (int64_t)r101(py + 1, H) * pitch;
+            b00 = r0[xm]; b01 = r0[px]; b02 = r0[xp]; b10 = r1[xm]; b12 = r1[xp]; b20 = r2[xm]; b21 = r2[px]; b22 = r2[xp];
+        }
         __syncthreads();
         if (t < nout) {
             int h0 = 0, h1 = 0, h2 = 0;
@@ -126,6 +137,7 @@ struct GfttCounters {
     uint32_t nacc;           // accepted after culling
     uint32_t pad;
     uint32_t remaining[64];  // undecided candidates left after round k (mod 64)
+    uint32_t hist[4096];     // candidates per top-12-bit bin of the ordered response (top-k prefilter)
 };
 
 __device__ __forceinline__ float tozero(float v, float thr) { return v > thr ? v : 0.f; }
@@ -137,6 +149,9 @@ nms_kernel(const float *__restrict__ eig, int H, int W, const uint8_t *__restric
 {
     const uint32_t mb = cnt->maxbits;
     if (!mb) return;
+    __shared__ uint32_t shist[4096];                              // per-CTA response histogram (top-k prefilter)
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) shist[i] = 0;
+    __syncthreads();
     const float thr = (float)((double)dec_f32(mb) * quality);
     const int wq = (W + 3) >> 2;                                  // 4-pixel groups per row
     const int64_t total = (int64_t)(H - 2) * wq;
@@ -185,11 +200,16 @@ nms_kernel(const float *__restrict__ eig, int H, int W, const uint8_t *__restric
 #pragma unroll
             for (int i = 0; i < 4; i++)
                 if (flags & (1u << i)) {
-                    if (pos < cap) keys[pos] = ((unsigned long long)enc_f32(vals[i]) << 32) | (uint32_t)(y * W + x0 + i);
+                    const uint32_t e = enc_f32(vals[i]);
+                    if (pos < cap) keys[pos] = ((unsigned long long)e << 32) | (uint32_t)(y * W + x0 + i);
+                    atomicAdd(&shist[e >> 20], 1u);
                     pos++;
                 }
         }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x)
+        if (shist[i]) atomicAdd(&cnt->hist[i], shist[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,6 +221,25 @@ complement_kernel(unsigned long long *__restrict__ keys, uint32_t n)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = ~keys[i];                   // ascending sort of ~key = descending (response, address)
+}
+
+// keep the candidates whose response bin is >= min_bin (the strongest ones), complemented for the ascending sort
+__global__ void __launch_bounds__(256)
+select_kernel(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t min_bin, unsigned long long *__restrict__ out,
+              uint32_t *__restrict__ out_count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long k = 0;
+    bool keep = false;
+    if (i < n) { k = keys[i]; keep = (uint32_t)(k >> 52) >= min_bin; }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+    if (ballot) {
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(out_count, (uint32_t)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) out[base + __popc(ballot & ((1u << lane) - 1))] = ~k;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -330,6 +369,26 @@ rs_scatter_kernel(const unsigned long long *__restrict__ src, unsigned long long
             const uint32_t d = (uint32_t)((k[s] >> shift) & 0xff);
             dst[wcount[wid][d] + rank[s]] = k[s];
         }
+    }
+}
+
+// After the stable sort on the response bytes, equal responses keep their arrival order: order each run of equal
+// responses by address (complemented keys ascending = address descending, OpenCV's tie-break).  Runs are rare and short;
+// the first element of a run sorts it.
+__global__ void __launch_bounds__(256)
+tie_fix_kernel(unsigned long long *__restrict__ keys, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = (uint32_t)(keys[i] >> 32);
+    if (i > 0 && (uint32_t)(keys[i - 1] >> 32) == v) return;       // not the first of its run
+    uint32_t e = i + 1;
+    while (e < n && (uint32_t)(keys[e] >> 32) == v) e++;
+    for (uint32_t a = i + 1; a < e; a++) {                          // insertion sort of keys[i..e)
+        const unsigned long long k = keys[a];
+        uint32_t b = a;
+        while (b > i && keys[b - 1] > k) { keys[b] = keys[b - 1]; b--; }
+        keys[b] = k;
     }
 }
 
@@ -504,72 +563,99 @@ IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, in
     int rc = launch_eig(gray, H, W, pitch, blockSize, eig, (int64_t)W * 4, mask, mask_pitch, &cnt->maxbits, st);
     if (rc) return rc;
     const int nblk = kNumSMs * 8;
-    nms_kernel<<<nblk, 256, 0, st>>>(eig, H, W, mask, mask_pitch, qualityLevel, cnt, keys0, L.cap);
-    if ((rc = check_launch("nms_kernel"))) return rc;
-
-    GfttCounters hc;
-    IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
-    IBT_CUDA_TRY(cudaStreamSynchronize(st));
-    if (hc.ncand > L.cap) return IBT_E_CAPACITY;
-    const uint32_t n = hc.ncand;
-    if (n == 0) return IBT_OK;
-
-    // ---- order all candidates by (response desc, address desc): rank --------------------------------------
-    unsigned long long *src = keys0, *dst = keys1;
-    complement_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, n);
-    if (n > 1) {
-        const uint32_t nblocks = (n + RS_TILE - 1) / RS_TILE;
-        const int hi_addr_byte = ((uint64_t)H * W > (1u << 24)) ? 3 : 2;          // address bytes above are constant
-        for (int p = 0; p < 8; p++) {
-            if (p > hi_addr_byte && p < 4) continue;
-            rs_count_kernel<<<nblocks, 256, 0, st>>>(src, n, 8 * p, nblocks, blockhist);
-            scan_u32(blockhist, 256u * nblocks, nullptr, scan_scratch, st);
-            rs_scatter_kernel<<<nblocks, 256, 0, st>>>(src, dst, n, 8 * p, nblocks, blockhist);
-            unsigned long long *t = src; src = dst; dst = t;
-        }
-        if ((rc = check_launch("radix sort"))) return rc;
-    }
-    const uint32_t nb = (n + 255) / 256;
     const bool cull = minDistance >= 1.0;
     const int cell = cull ? (int)lrint(minDistance) : 65536;        // no culling: one cell, only positions are needed
     const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
     const uint32_t ncells = (uint32_t)gw * gh;
     uint32_t limit = (maxCorners > 0) ? (uint32_t)maxCorners : 0xffffffffu;
     if (limit > (uint32_t)cap) limit = (uint32_t)cap;
+    static GfttCounters hc;                                        // 17 KB: keep it off the stack
+    uint32_t nout = 0;
 
-    // positions of all ranks (+ cell histogram when culling)
-    IBT_CUDA_TRY(cudaMemsetAsync(cell_start, 0, ((size_t)ncells + 1) * 4, st));
-    cell_count_kernel<<<nb, 256, 0, st>>>(src, n, W, cell, gw, pos, cell_start, state);
-    if ((rc = check_launch("cell_count_kernel"))) return rc;
-    uint32_t nout = n;
-    if (cull) {
-        IBT_CUDA_TRY(cudaMemsetAsync(cell_fill, 0, (size_t)ncells * 4, st));
-        scan_u32(cell_start, ncells + 1, nullptr, scan_scratch, st);
-        cell_fill_kernel<<<nb, 256, 0, st>>>(pos, n, cell, gw, cell_start, cell_fill, items);
-        const float md2 = (float)(minDistance * minDistance);
-        int round = 0;
-        for (;;) {
-            const int batch = round == 0 ? 12 : 4;
-            for (int b = 0; b < batch; b++, round++) {
-                if (round >= 64) IBT_CUDA_TRY(cudaMemsetAsync(&cnt->remaining[round & 63], 0, 4, st));
-                cull_round_kernel<<<nb, 256, 0, st>>>(pos, n, cell_start, items, state, cnt, cell, gw, gh, md2, round);
-            }
-            if ((rc = check_launch("cull_round_kernel"))) return rc;
-            IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
-            IBT_CUDA_TRY(cudaStreamSynchronize(st));
-            if (hc.remaining[(round - 1) & 63] == 0) break;
-            if (round > (1 << 20)) return IBT_E_CUDA;
+    // attempt 0 may work on the strongest candidates only (top-k prefilter); if culling leaves fewer than maxCorners of
+    // them, attempt 1 repeats with every candidate.  The greedy order makes the prefix exact either way: whether a
+    // candidate is accepted depends on stronger candidates only.
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (attempt == 1) {
+            IBT_CUDA_TRY(cudaMemsetAsync(&cnt->ncand, 0, sizeof(GfttCounters) - offsetof(GfttCounters, ncand), st));
         }
-        accepted_count_kernel<<<nb, 256, 0, st>>>(state, n, blockcnt);
-        scan_u32(blockcnt, nb, &cnt->nacc, scan_scratch, st);
-        write_corners_kernel<<<nb, 256, 0, st>>>(pos, state, n, blockcnt, limit, out_xy);
-        if ((rc = check_launch("write_corners_kernel"))) return rc;
+        nms_kernel<<<nblk, 256, 0, st>>>(eig, H, W, mask, mask_pitch, qualityLevel, cnt, keys0, L.cap);
+        if ((rc = check_launch("nms_kernel"))) return rc;
         IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
         IBT_CUDA_TRY(cudaStreamSynchronize(st));
-        nout = hc.nacc;
-    } else {
-        write_corners_kernel<<<nb, 256, 0, st>>>(pos, nullptr, n, nullptr, limit, out_xy);
-        if ((rc = check_launch("write_corners_kernel"))) return rc;
+        if (hc.ncand > L.cap) return IBT_E_CAPACITY;
+        uint32_t n = hc.ncand;
+        if (n == 0) return IBT_OK;
+
+        // ---- order the candidates by (response desc, address desc): rank ------------------------------------
+        unsigned long long *src = keys0, *dst = keys1;
+        bool subset = false;
+        const uint64_t want = maxCorners > 0 ? (uint64_t)maxCorners * 4 + 1024 : 0;
+        if (attempt == 0 && maxCorners > 0 && cull && n > 2 * want) {
+            uint32_t cum = 0;
+            int b = 4095;
+            for (; b >= 0; b--) { cum += hc.hist[b]; if (cum >= want) break; }
+            if (b > 0 && cum < n) {
+                IBT_CUDA_TRY(cudaMemsetAsync(&cnt->nacc, 0, 4, st));            // reused as the selection counter
+                select_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys0, n, (uint32_t)b, keys1, &cnt->nacc);
+                src = keys1; dst = keys0;
+                n = cum;
+                subset = true;
+            }
+        }
+        if (!subset) complement_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, n);
+        if (n > 1) {
+            const uint32_t nblocks = (n + RS_TILE - 1) / RS_TILE;
+            // the top response byte (sign + 7 exponent bits) is usually the same for every candidate: the histogram tells
+            int lo_bin = 4096, hi_bin = -1;
+            for (int b = 0; b < 4096; b++) if (hc.hist[b]) { if (b < lo_bin) lo_bin = b; hi_bin = b; }
+            const int last_pass = (lo_bin >> 4) == (hi_bin >> 4) ? 6 : 7;
+            for (int p = 4; p <= last_pass; p++) {                      // response bytes only; ties are fixed below
+                rs_count_kernel<<<nblocks, 256, 0, st>>>(src, n, 8 * p, nblocks, blockhist);
+                scan_u32(blockhist, 256u * nblocks, nullptr, scan_scratch, st);
+                rs_scatter_kernel<<<nblocks, 256, 0, st>>>(src, dst, n, 8 * p, nblocks, blockhist);
+                unsigned long long *t = src; src = dst; dst = t;
+            }
+            tie_fix_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, n);
+            if ((rc = check_launch("radix sort"))) return rc;
+        }
+        const uint32_t nb = (n + 255) / 256;
+
+        // positions of all ranks (+ cell histogram when culling)
+        IBT_CUDA_TRY(cudaMemsetAsync(cell_start, 0, ((size_t)ncells + 1) * 4, st));
+        cell_count_kernel<<<nb, 256, 0, st>>>(src, n, W, cell, gw, pos, cell_start, state);
+        if ((rc = check_launch("cell_count_kernel"))) return rc;
+        nout = n;
+        if (cull) {
+            IBT_CUDA_TRY(cudaMemsetAsync(cell_fill, 0, (size_t)ncells * 4, st));
+            scan_u32(cell_start, ncells + 1, nullptr, scan_scratch, st);
+            cell_fill_kernel<<<nb, 256, 0, st>>>(pos, n, cell, gw, cell_start, cell_fill, items);
+            const float md2 = (float)(minDistance * minDistance);
+            int round = 0;
+            for (;;) {
+                const int batch = round == 0 ? 12 : 4;
+                for (int b = 0; b < batch; b++, round++) {
+                    if (round >= 64) IBT_CUDA_TRY(cudaMemsetAsync(&cnt->remaining[round & 63], 0, 4, st));
+                    cull_round_kernel<<<nb, 256, 0, st>>>(pos, n, cell_start, items, state, cnt, cell, gw, gh, md2, round);
+                }
+                if ((rc = check_launch("cull_round_kernel"))) return rc;
+                IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, offsetof(GfttCounters, hist), cudaMemcpyDeviceToHost, st));
+                IBT_CUDA_TRY(cudaStreamSynchronize(st));
+                if (hc.remaining[(round - 1) & 63] == 0) break;
+                if (round > (1 << 20)) return IBT_E_CUDA;
+            }
+            accepted_count_kernel<<<nb, 256, 0, st>>>(state, n, blockcnt);
+            scan_u32(blockcnt, nb, &cnt->nacc, scan_scratch, st);
+            write_corners_kernel<<<nb, 256, 0, st>>>(pos, state, n, blockcnt, limit, out_xy);
+            if ((rc = check_launch("write_corners_kernel"))) return rc;
+            IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, offsetof(GfttCounters, hist), cudaMemcpyDeviceToHost, st));
+            IBT_CUDA_TRY(cudaStreamSynchronize(st));
+            nout = hc.nacc;
+        } else {
+            write_corners_kernel<<<nb, 256, 0, st>>>(pos, nullptr, n, nullptr, limit, out_xy);
+            if ((rc = check_launch("write_corners_kernel"))) return rc;
+        }
+        if (!subset || nout >= (uint32_t)maxCorners) break;          // done (the subset produced a full prefix)
     }
     if (maxCorners > 0 && nout > (uint32_t)maxCorners) nout = (uint32_t)maxCorners;
     *out_count = (int)nout;
