@@ -165,13 +165,21 @@ nms_kernel(const float *__restrict__ eig, int H, int W, const uint8_t *__restric
             y = (int)(g / wq) + 1;
             x0 = (int)(g - (int64_t)(y - 1) * wq) * 4;
             float r[3][6];                                        // rows y-1..y+1, columns x0-1 .. x0+4, thresholded
+            const bool vec = (W & 3) == 0;                        // rows are 16-byte aligned: one float4 + two scalars per row
 #pragma unroll
             for (int dy = 0; dy < 3; dy++) {
                 const float *row = eig + (int64_t)(y - 1 + dy) * W;
+                if (vec) {
+                    const float4 m = __ldg(reinterpret_cast<const float4 *>(row + x0));
+                    r[dy][0] = x0 > 0 ? tozero(__ldg(row + x0 - 1), thr) : 0.f;
+                    r[dy][1] = tozero(m.x, thr); r[dy][2] = tozero(m.y, thr); r[dy][3] = tozero(m.z, thr); r[dy][4] = tozero(m.w, thr);
+                    r[dy][5] = x0 + 4 < W ? tozero(__ldg(row + x0 + 4), thr) : 0.f;
+                } else {
 #pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    const int xx = x0 - 1 + c;
-                    r[dy][c] = (xx >= 0 && xx < W) ? tozero(__ldg(row + xx), thr) : 0.f;
+                    for (int c = 0; c < 6; c++) {
+                        const int xx = x0 - 1 + c;
+                        r[dy][c] = (xx >= 0 && xx < W) ? tozero(__ldg(row + xx), thr) : 0.f;
+                    }
                 }
             }
 #pragma unroll
