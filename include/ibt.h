@@ -144,6 +144,15 @@ int ibt_tracks_compact(const float *tracks_tm, const float *quality_tm, const ui
  *   easting, northing, reserved }.  EN (n,2) f64.  All arithmetic in fp64. */
 int ibt_photo_to_utm(const float *xy, int64_t n, const double *cam, double *EN, void *stream);
 
+/* ---- s2 consumer: the per-track body of cam_to_utm, s2_cam_to_utm.py:243-343, for all tracks of one .npz file:
+ *      project every vertex (as ibt_photo_to_utm), u = dE/dt, v = dN/dt, speed = hypot(u, v) per segment (s2:279-290),
+ *      then the plausibility criteria (s2:309-343): mean speed < min_speed or max speed > max_speed; and, only when
+ *      max speed > speed_threshold, consecutive speed ratio > max_speedfactor or direction change > max_angle_deg.
+ *      tracks (M, T+1, 2) f32; cam HOST 12 doubles; EN (M, T+1, 2) f64; uv (M, T, 2) f64; speed (M, T) f64; keep (M) u8. */
+int ibt_track_velocities(const float *tracks, int M, int T, const double *cam, double interval_s, double min_speed,
+                         double max_speed, double max_speedfactor, double max_angle_deg, double speed_threshold,
+                         double *EN, double *uv, double *speed, uint8_t *keep, void *stream);
+
 /* ---- mask: Camera.mask_meshgrid (imports/camtools.py:184-211) as used at s1:285-294: rasterise the (already
  *      crop-shifted) water polygon over the H x W pixel centres.  poly_xy: DEVICE (E,2) f64, 3 <= E <= 2048,
  *      implicitly closed; crossing-number rule of matplotlib.path.Path.contains_points (radius 0).

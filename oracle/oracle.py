@@ -204,3 +204,35 @@ def fb_check(p0, p0r, threshold=1.0):
     diff = np.abs(np.asarray(p0, np.float32) - np.asarray(p0r, np.float32)).reshape(-1, 2)
     dist = np.hypot(diff[:, 0], diff[:, 1])
     return dist, dist < threshold
+
+
+def track_velocities(tracks, cam, tracking_interval, min_speed, max_speed, max_speedfactor, max_angle, speed_threshold):
+    """Per-track body of cam_to_utm, s2_cam_to_utm.py:243-343, restated with the reference's own Python loops and list
+    max()/min() calls (small inputs only).  Returns EN (M,T+1,2), uv (M,T,2), speed (M,T) float64 and keep (M,) bool."""
+    import warnings
+    tracks = np.asarray(tracks, np.float32)
+    M, T = tracks.shape[0], tracks.shape[1] - 1
+    EN = photo_to_utm(tracks.reshape(-1, 2).astype(np.float64), cam).reshape(M, T + 1, 2)
+    uv = np.zeros((M, T, 2)); sp = np.zeros((M, T)); keep = np.ones(M, bool)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for m in range(M):
+            usub, vsub, ssub = [], [], []
+            for i in range(1, T + 1):
+                xm = (EN[m, i, 0] - EN[m, i - 1, 0]) / float(tracking_interval)
+                ym = (EN[m, i, 1] - EN[m, i - 1, 1]) / float(tracking_interval)
+                usub.append(xm); vsub.append(ym); ssub.append(np.hypot(xm, ym))
+            uv[m, :, 0], uv[m, :, 1], sp[m] = usub, vsub, ssub
+            if (np.mean(ssub) < min_speed) or (max(ssub) > max_speed):
+                keep[m] = False
+                continue
+            if max(ssub) > speed_threshold and T >= 2:
+                ang, rat = [], []
+                for c1, c2 in zip(range(0, T - 1), range(1, T)):
+                    dot = usub[c1] * usub[c2] + vsub[c1] * vsub[c2]
+                    mag1, mag2 = np.hypot(usub[c1], vsub[c1]), np.hypot(usub[c2], vsub[c2])
+                    ang.append(abs(np.degrees(np.arccos(dot / (mag1 * mag2)))))
+                    rat.append(max([ssub[c1], ssub[c2]]) / min([ssub[c1], ssub[c2]]))
+                if max(rat) > max_speedfactor or max(ang) > max_angle:
+                    keep[m] = False
+    return EN, uv, sp, keep

@@ -7,6 +7,9 @@
                    -- five synthetic JPEG frames and what the UNMODIFIED reference class
                       /root/reference/s0_1_test_lucaskanade_tracking.py:LucasKanade.run() produced on them (matplotlib
                       replaced by MagicMock; cv2 calls recorded), i.e. outputs of the reference itself run here.
+  * s2_expected.npz  -- the UNMODIFIED reference worker s2_cam_to_utm.cam_to_utm run on synthetic track files crossing an
+                      hour boundary (tide pickle as the reference reads it; pd.read_excel patched to return the parameter
+                      table because openpyxl is absent): inputs and the hourly x, y, u, v, speed, time arrays it wrote.
   * utm_expected.npz -- Camera.photo_to_utm / photocords_cropped_to_uncropped of /root/reference/imports/camtools.py
                       evaluated on a Camera object whose Excel parsing is bypassed (object.__new__ + the dict fields
                       __init__ would fill, camtools.py:126-147).
@@ -216,11 +219,74 @@ def make_utm():
     print("utm_expected.npz", EN[:2])
 
 
+def make_s2():
+    """Run the UNMODIFIED reference s2_cam_to_utm.cam_to_utm on synthetic track files (pd.read_excel is patched to
+    return the parameter table because openpyxl is not installed; everything else is the reference's own code)."""
+    import datetime as dt
+    import tempfile
+    import pandas as pd
+    for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.collections", "matplotlib.path", "shapefile"):
+        sys.modules.setdefault(m, MagicMock())
+    sys.path.insert(0, "/root/reference")
+    import s2_cam_to_utm as s2
+    W, H = 6000, 4000
+    row = dict(camera="cam1", start_day=20190701, end_day=20190801, image_width=W, image_height=H, sensor_width=22.3,
+               easting=377280.39, northing=6525846.97, elevation=261.3, antenna_height=1.6, theta=300.0, phi=5.0,
+               psi=-1.0, sigma=18.0, crop_left=250, crop_right=0, crop_top=400, crop_bottom=0, tracking_interval=60,
+               mask="mask.shp")
+    params = pd.DataFrame([row])
+    real_read_excel = pd.read_excel
+    pd.read_excel = lambda *a, **k: params
+    rng = np.random.default_rng(21)
+    tmp = tempfile.mkdtemp()
+    src = os.path.join(tmp, "output", "cam1", "oblique", "20190724")
+    tgt = os.path.join(tmp, "output", "cam1", "utm")
+    os.makedirs(src); os.makedirs(tgt); os.makedirs(os.path.join(tmp, "data"))
+    minutes = pd.date_range("2019-07-24 12:00", "2019-07-24 14:00", freq="min")
+    tides = pd.DataFrame({"date": minutes, "depth_tide_ellipsoid": 0.3 + 0.01 * np.arange(len(minutes))})
+    tide_path = os.path.join(tmp, "data", "tide_2019.pickle")
+    tides.to_pickle(tide_path)
+    out = {}
+    stamps = ["20190724-125700", "20190724-125900", "20190724-130100", "20190724-130300"]
+    for si, stamp in enumerate(stamps):
+        M = 120
+        p0 = (rng.random((M, 2)) * [5200, 1700] + [100, 1500]).astype(np.float32)       # water, below the horizon
+        step = rng.normal(0, 1.0, (M, 1, 2)) + rng.normal(0, 0.25, (M, 2, 2))            # ~0.2 m/px * px/60 s
+        step[::7] *= 12.0                                                                 # too fast (criterion 1 / 2)
+        step[3::11, 1] *= -1.0                                                            # direction flips (criterion 3)
+        step[5::13] = 0.0                                                                 # no motion at all
+        tr = np.concatenate([p0[:, None, :], p0[:, None, :] + np.cumsum(step, 1)], 1).astype(np.float32)
+        q = np.abs(rng.normal(0, 0.2, (M, 2))).astype(np.float32)
+        np.savez(os.path.join(src, "%s_120sec_at_60sec_tracks.npz" % stamp), tracks=tr, trackquality=q)
+        out["in%d_tracks" % si] = tr
+    np.savez(os.path.join(src, "20190724-130500_120sec_at_60sec_tracks.npz"), tracks=[], trackquality=[])   # empty group
+    stamps.append("20190724-130500")
+    s2.cam_to_utm((src, tgt, "cam1", 1.7, 0.0, 2.5, 60, 0.1, os.path.join(tmp, "parameter_file.xlsx"), tide_path))
+    pd.read_excel = real_read_excel
+    files = sorted(os.listdir(tgt))
+    out["stamps"] = np.array(stamps)
+    out["out_files"] = np.array(files)
+    for fi, f in enumerate(files):
+        z = np.load(os.path.join(tgt, f))
+        for k in ("x", "y", "u", "v", "speed", "time"):
+            out["out%d_%s" % (fi, k)] = z[k]
+    out["params_keys"] = np.array(list(row.keys()))
+    out["params_vals"] = np.array([str(v) for v in row.values()])
+    out["tide_minutes"] = np.array([str(m) for m in minutes])
+    out["tide_values"] = tides["depth_tide_ellipsoid"].to_numpy()
+    np.savez_compressed(os.path.join(HERE, "s2_expected.npz"), **out)
+    print("s2_expected.npz", files, {k: v.shape for k, v in out.items() if k.startswith("out") and k.endswith("_x")})
+
+
 if __name__ == "__main__":
-    torch.manual_seed(0)
-    cv2.setNumThreads(1)
-    make_kat("kat_texture.npz", 240, 320, 3, "texture")
-    make_kat("kat_iceberg.npz", 201, 333, 4, "iceberg")
-    make_edge()
-    make_sequence()
-    make_utm()
+    if "--only-s2" in sys.argv:
+        make_s2()
+    else:
+        torch.manual_seed(0)
+        cv2.setNumThreads(1)
+        make_kat("kat_texture.npz", 240, 320, 3, "texture")
+        make_kat("kat_iceberg.npz", 201, 333, 4, "iceberg")
+        make_edge()
+        make_sequence()
+        make_utm()
+        make_s2()
