@@ -246,8 +246,9 @@ __device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__re
 // On exit (ox, oy) = nextPts[k], status/err as cv2 (err = 0 where status == 0).
 template <int WW, int WH>
 __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, float ptx, float pty,
-                                         bool use_init, float &ox, float &oy, int &status, float &err, int &iters,
-                                         unsigned char *slab, int isr, int isw, int jsr, int jsw, int lane)
+                                         bool use_init, bool want_status, bool want_err, float &ox, float &oy, int &status,
+                                         float &err, int &iters, unsigned char *slab, int isr, int isw, int jsr, int jsw,
+                                         int lane)
 {
     const float FLT_SCALE = 1.f / (1 << 20);
     const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
@@ -387,10 +388,13 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             }
             pdx = dx; pdy = dy;
         }
-        if (status && level == 0 && !(a.flags & IBT_LK_GET_MIN_EIGENVALS)) {
+        // OpenCV's final stage at level 0 (A.5 step 9): bounds test of the final window (-> status) and the residual err.
+        // The reference never reads status or err (s1:323-333): callers that pass no status / err buffers skip the stage.
+        if (status && level == 0 && !(a.flags & IBT_LK_GET_MIN_EIGENVALS) && (want_status || want_err)) {
             const float qx = __fsub_rn(ox, halfx), qy = __fsub_rn(oy, halfy);
             const int iqx = cv_floor(qx), iqy = cv_floor(qy);
             if (window_oob(iqx, iqy, winW, winH, rows, cols)) { status = 0; err = 0.f; continue; }
+            if (!want_err) continue;
             if (!staged || (unsigned)(iqx - px0) > (unsigned)max_off || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
                 px0 = (iqx - LK_MARGIN) & ~3; py0 = iqy - LK_MARGIN;
                 restage_sync(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
@@ -433,8 +437,10 @@ lk_kernel(const __grid_constant__ LKArgs a)
         int status, iters = 0;
         const bool use_init = pass == 0 && (a.flags & IBT_LK_USE_INITIAL_FLOW) != 0;
         if (use_init) { ox = a.p1[2 * k]; oy = a.p1[2 * k + 1]; }
-        lk_point<WW, WH>(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, ox, oy, status, err, iters, slab, isr, isw, jsr, jsw,
-                 lane);
+        const bool want_status = pass == 0 ? a.st1 != nullptr : a.st0 != nullptr;
+        const bool want_err = pass == 0 ? a.err1 != nullptr : a.err0 != nullptr;
+        lk_point<WW, WH>(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, want_status, want_err, ox, oy, status, err, iters,
+                         slab, isr, isw, jsr, jsw, lane);
         if (pass == 0) it_f = iters; else it_b = iters;
         if (lane == 0) {
             if (pass == 0) {
