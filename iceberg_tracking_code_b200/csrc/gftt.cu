@@ -577,7 +577,7 @@ IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, in
     const uint32_t ncells = (uint32_t)gw * gh;
     uint32_t limit = (maxCorners > 0) ? (uint32_t)maxCorners : 0xffffffffu;
     if (limit > (uint32_t)cap) limit = (uint32_t)cap;
-    static GfttCounters hc;                                        // 17 KB: keep it off the stack
+    static thread_local GfttCounters hc;                           // 17 KB: keep it off the stack
     uint32_t nout = 0;
 
     // attempt 0 may work on the strongest candidates only (top-k prefilter); if culling leaves fewer than maxCorners of
