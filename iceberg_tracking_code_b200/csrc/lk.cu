@@ -20,6 +20,7 @@
 // and rounded to float once; OpenCV accumulates in float SIMD lanes, which differs in the last bits only.
 // All float arithmetic that OpenCV does unfused is compiled with -fmad=false.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace ibt {
@@ -541,6 +542,14 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
         if (ctas > 32) ctas = 32;
         const int warps = ctas * w;
         if (warps >= best) { best = warps; wpc = w; best_ctas = ctas; }
+    }
+    if (const char *e = getenv("IBT_LK_WPC")) {             // tuning knob (warps per CTA); the default is the choice above
+        const int w = atoi(e);
+        if (w >= 1 && w <= 8 && (size_t)a.warp_smem * w + 1024 <= 200 * 1024) {
+            wpc = w;
+            best_ctas = (int)((227 * 1024) / ((size_t)a.warp_smem * w + 1024));
+            if (best_ctas > 32) best_ctas = 32;
+        }
     }
     const size_t smem = (size_t)a.warp_smem * wpc;
     static bool attr_set = false;

@@ -7,6 +7,8 @@
                    -- five synthetic JPEG frames and what the UNMODIFIED reference class
                       /root/reference/s0_1_test_lucaskanade_tracking.py:LucasKanade.run() produced on them (matplotlib
                       replaced by MagicMock; cv2 calls recorded), i.e. outputs of the reference itself run here.
+  * kat_extreme.npz  -- cv2 outputs at parameter extremes (window 3..63, maxLevel 0..7, criteria clamps, blockSize 1..31,
+                      fractional / huge minDistance, single-pixel mask) and awkward shapes (odd widths, 9-pixel-thin images).
   * s2_expected.npz  -- the UNMODIFIED reference worker s2_cam_to_utm.cam_to_utm run on synthetic track files crossing an
                       hour boundary (tide pickle as the reference reads it; pd.read_excel patched to return the parameter
                       table because openpyxl is absent): inputs and the hourly x, y, u, v, speed, time arrays it wrote.
@@ -219,6 +221,69 @@ def make_utm():
     print("utm_expected.npz", EN[:2])
 
 
+LK_EXTREME = [
+    dict(winSize=(3, 3), maxLevel=0, criteria=(3, 30, 0.01)),
+    dict(winSize=(63, 63), maxLevel=7, criteria=(3, 30, 0.01)),
+    dict(winSize=(5, 61), maxLevel=2, criteria=(3, 200, 0.0)),        # maxCount clamps to 100, eps 0
+    dict(winSize=(33, 32), maxLevel=3, criteria=(3, 0, 20.0)),        # maxCount 0: no iteration; eps clamps to 10
+    dict(winSize=(21, 21), maxLevel=3, criteria=(0, 5, 0.5)),         # neither bit set: defaults 30 / 0.01
+    dict(winSize=(45, 47), maxLevel=1, criteria=(3, 30, 0.01), minEigThreshold=0.01),
+]
+GFTT_EXTREME = [
+    dict(maxCorners=0, qualityLevel=0.01, minDistance=1, blockSize=4),
+    dict(maxCorners=0, qualityLevel=0.01, minDistance=0.5, blockSize=2),
+    dict(maxCorners=1, qualityLevel=0.5, minDistance=3, blockSize=3),
+    dict(maxCorners=0, qualityLevel=0.001, minDistance=33.3, blockSize=31),
+    dict(maxCorners=40, qualityLevel=0.05, minDistance=2.5, blockSize=17),
+    dict(maxCorners=0, qualityLevel=0.9, minDistance=4, blockSize=7),
+]
+
+
+def make_extreme():
+    """Parameter extremes and awkward shapes (width not a multiple of 4 / 16, tiny images)."""
+    rng = np.random.default_rng(77)
+    out = {}
+    h, w = 150, 211
+    base = syn.base_texture(h, w, 8, scene="texture")
+    f0 = syn.frame_gray(base, 0, noise_sigma=1.0, seed=8).numpy()
+    f1 = syn.frame_gray(base, 1, vx=1.5, vy=0.75, noise_sigma=1.0, seed=8).numpy()
+    out["f0"], out["f1"] = f0, f1
+    pts = lk_points(h, w, f0, rng)
+    out["lk_pts"] = pts
+    for li, lp in enumerate(LK_EXTREME):
+        p1, st, err = cv2.calcOpticalFlowPyrLK(f0, f1, pts, None, **lp)
+        out["lk%d_p1" % li], out["lk%d_st" % li] = p1, st
+        out["lk%d_err" % li] = np.where(st == 1, err, 0).astype(np.float32)
+    mask = np.zeros((h, w), np.uint8)
+    mask[h // 2, w // 2] = 255
+    mask[10:40, 15:90] = 1                                  # any non-zero value allows
+    out["mask"] = mask
+    for gi, gp in enumerate(GFTT_EXTREME):
+        for mi, m in enumerate([None, mask]):
+            p = cv2.goodFeaturesToTrack(f0, mask=m, **gp)
+            out["gftt%d_m%d" % (gi, mi)] = np.zeros((0, 1, 2), np.float32) if p is None else p
+    for (hh, ww) in [(24, 24), (9, 130), (130, 9), (40, 37)]:
+        a = rng.integers(0, 256, (hh, ww), dtype=np.uint8)
+        b = np.roll(a, 1, axis=1)
+        out["tiny_%dx%d_a" % (hh, ww)], out["tiny_%dx%d_b" % (hh, ww)] = a, b
+        tp = (rng.random((25, 1, 2)) * [ww - 1, hh - 1]).astype(np.float32)
+        out["tiny_%dx%d_pts" % (hh, ww)] = tp
+        p1, st, err = cv2.calcOpticalFlowPyrLK(a, b, tp, None, winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+        out["tiny_%dx%d_p1" % (hh, ww)], out["tiny_%dx%d_st" % (hh, ww)] = p1, st
+        p = cv2.goodFeaturesToTrack(a, 0, 0.05, 3, blockSize=3)
+        out["tiny_%dx%d_gftt" % (hh, ww)] = np.zeros((0, 1, 2), np.float32) if p is None else p
+        rgb = rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8)
+        out["tiny_%dx%d_rgb" % (hh, ww)] = rgb
+        out["tiny_%dx%d_gray" % (hh, ww)] = cv2.cvtColor(rgb, cv2.COLOR_BGR2GRAY)
+        ml, pyr = cv2.buildOpticalFlowPyramid(a, (5, 5), 3, withDerivatives=True)
+        out["tiny_%dx%d_ml" % (hh, ww)] = np.int32(ml)
+        for l in range(ml + 1):
+            out["tiny_%dx%d_L%d" % (hh, ww, l)] = np.ascontiguousarray(pyr[2 * l])
+            out["tiny_%dx%d_D%d" % (hh, ww, l)] = np.ascontiguousarray(pyr[2 * l + 1])
+    np.savez_compressed(os.path.join(HERE, "kat_extreme.npz"), **out)
+    print("kat_extreme.npz", len(out))
+
+
 def make_s2():
     """Run the UNMODIFIED reference s2_cam_to_utm.cam_to_utm on synthetic track files (pd.read_excel is patched to
     return the parameter table because openpyxl is not installed; everything else is the reference's own code)."""
@@ -281,6 +346,8 @@ def make_s2():
 if __name__ == "__main__":
     if "--only-s2" in sys.argv:
         make_s2()
+    elif "--only-extreme" in sys.argv:
+        make_extreme()
     else:
         torch.manual_seed(0)
         cv2.setNumThreads(1)
@@ -289,4 +356,5 @@ if __name__ == "__main__":
         make_edge()
         make_sequence()
         make_utm()
+        make_extreme()
         make_s2()
