@@ -196,12 +196,15 @@ def group_time_ok(paths, track_len_sec):
 
 def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), feature_params=None, lk_params=None,
                    save=True, loader=load_image, tracker=None, check_time=True, on_group=None, first_group=0,
-                   n_groups=None):
+                   n_groups=None, decode_workers=4):
     """The loop of s1:296-450 over `imagelist` (paths, or in-memory frames when loader is None).
     Returns the list of (seed_index, npz_path_or_None, tracks, trackquality) of every completed group.
 
     first_group / n_groups select a contiguous block of groups (time-block sharding): group g of start s
-    covers frames s+g*T .. s+(g+1)*T; a block needs one halo frame shared with the next block."""
+    covers frames s+g*T .. s+(g+1)*T; a block needs one halo frame shared with the next block.
+
+    decode_workers: the loader (PIL JPEG decode, ~0.25 s per 24 MP frame, far slower than the GPU step) runs in a thread
+    pool that keeps `decode_workers` frames decoded ahead of the tracker; the order of processing is unchanged."""
     T = int(track_len)
     trk = tracker or SequenceTracker(feature_params, lk_params)
     if mask is not None:
@@ -216,9 +219,23 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
             continue
         prev = None
         seed_idx = None
-        for counter in range(g0 * T, g1 * T + 1):
+        counters = range(g0 * T, g1 * T + 1)
+        pool, pending = None, {}
+        if loader is not None and decode_workers and decode_workers > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(max_workers=int(decode_workers))
+            for c in counters[:decode_workers]:
+                pending[c] = pool.submit(loader, frames[c])
+        for counter in counters:
             item = frames[counter]
-            cur = trk.prepare(loader(item) if loader is not None else item)
+            if pool is not None:
+                nxt = counter + decode_workers
+                if nxt <= counters[-1]:
+                    pending[nxt] = pool.submit(loader, frames[nxt])
+                decoded = pending.pop(counter).result()
+            else:
+                decoded = loader(item) if loader is not None else item
+            cur = trk.prepare(decoded)
             if prev is not None and trk.n > 0:
                 trk.track(prev, cur)
             if (counter - g0 * T) % T == 0:
@@ -239,6 +256,8 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
                     trk.seed(cur, mask, T)
                     seed_idx = counter
             prev = cur
+        if pool is not None:
+            pool.shutdown(wait=False)
     return results
 
 
