@@ -13,6 +13,8 @@
 // bytes per warp), each level-(l+1) row as one 2-byte store.  The grid is sized so that every CTA gets the same
 // number of tiles (no tail wave).
 #include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>              // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace ibt {
 
@@ -210,6 +212,140 @@ pyr_level_kernel(const __grid_constant__ PyrArgs a)
     }
 }
 
+
+// ---- TMA variant ----------------------------------------------------------------------------------------------
+// Same tiles, same filters; the halo tile arrives by ONE cp.async.bulk.tensor.2d per tile (issued by one thread, signalled
+// on an mbarrier) instead of per-thread 16-byte cp.async copies: no staging instructions, no per-row index math.  The
+// tensor map covers the w x h image; coordinates left / above / right / below it come back as zeros and the
+// REFLECT_101 rows and columns are then patched from the tile itself.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    for (int spin = 0; spin < (1 << 26); spin++) {
+        unsigned ok;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();                                   // a lost TMA must fail loudly, not hang the GPU
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1),
+                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// REFLECT_101 rows of a TMA-staged tile (zeros outside the image): rows -2, -1 and h, h+1, copied inside the tile.
+template <int NW>
+__device__ __forceinline__ bool reflect_rows(const PyrArgs &a, int t, uint8_t *tile, int tid)
+{
+    constexpr int TH = NW * RPW, SROWS = TH + 3, NT = NW * 32;
+    const int ty = t / a.ntx;
+    const int org = ty * TH - 2;                          // image row of tile row 0
+    const bool top = ty == 0, bottom = org + SROWS > a.h;
+    if (!(top || bottom)) return false;
+    // up to four rows to patch: (dst tile row, src tile row)
+    int dst[4], src[4], n = 0;
+    if (top) { dst[n] = 0; src[n++] = 4; dst[n] = 1; src[n++] = 3; }
+    if (bottom) {
+        for (int k = 0; k < 2; k++) {
+            const int r = a.h + k - org;
+            if (r >= 0 && r < SROWS) { dst[n] = r; src[n++] = a.h - 2 - k - org; }
+        }
+    }
+    for (int i = tid; i < n * (SPITCH / 4); i += NT) {
+        const int j = i / (SPITCH / 4), c = i - j * (SPITCH / 4);
+        reinterpret_cast<uint32_t *>(tile + dst[j] * SPITCH)[c] = reinterpret_cast<const uint32_t *>(tile + src[j] * SPITCH)[c];
+    }
+    return true;
+}
+
+template <bool DERIV, bool DOWN, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 7 : 16)
+pyr_level_tma_kernel(const __grid_constant__ PyrArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+    constexpr int TH = NW * RPW, SROWS = TH + 3;
+    constexpr unsigned TILE_BYTES = SROWS * SPITCH;
+    constexpr unsigned TILE_ALLOC = (TILE_BYTES + 127) & ~127u;
+    __shared__ __align__(128) uint8_t tiles[2][TILE_ALLOC];
+    __shared__ __align__(8) uint64_t full[2];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t, int b) {                      // one thread: arm the barrier, launch the bulk tensor copy
+        if (tid == 0) {
+            const int ty = t / a.ntx, tx = t - ty * a.ntx;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // our generic-proxy patches precede the async write
+            mbar_expect_tx(&full[b], TILE_BYTES);
+            tma_load_2d(tiles[b], &tmap, tx * TW - HXB, ty * TH - 2, &full[b]);
+        }
+    };
+    unsigned phases = 0u;                                 // bit b = parity to wait for on full[b]
+    int t = blockIdx.x, buf = 0;
+    if (t < a.ntiles) issue(t, 0);
+    for (; t < a.ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        if (tn < a.ntiles) issue(tn, buf ^ 1);                                // prefetch the next tile of this CTA
+        mbar_wait(&full[buf], (phases >> buf) & 1u);                          // tile t has landed
+        phases ^= 1u << buf;
+        if (reflect_rows<NW>(a, t, tiles[buf], tid)) __syncthreads();
+        if (reflect_tile<NW>(a, t, tiles[buf], tid)) __syncthreads();
+        {
+            const int ty = t / a.ntx, tx = t - ty * a.ntx;
+            const bool fullt = (tx + 1) * TW <= a.w && (ty + 1) * TH <= a.h;
+            if (fullt) filter_tile<DERIV, DOWN, NW, true>(a, t, tiles[buf], tid);
+            else filter_tile<DERIV, DOWN, NW, false>(a, t, tiles[buf], tid);
+        }
+        __syncthreads();                                                      // buffer may be refilled next round
+        buf ^= 1;
+    }
+}
+
+// host: tensor map of a (h, w) u8 image with row pitch `pitch`, box = SPITCH x SROWS, zero fill outside
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+static bool make_tile_map(CUtensorMap *m, const uint8_t *src, int h, int w, int64_t pitch, int srows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)SPITCH, (cuuint32_t)srows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(src), gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <bool DERIV, bool DOWN, int NW>
 static void launch_variant(const PyrArgs &a0, cudaStream_t st)
 {
@@ -221,6 +357,13 @@ static void launch_variant(const PyrArgs &a0, cudaStream_t st)
     const int resident = kNumSMs * (NW == 4 ? 7 : 16);
     const int per_cta = (a.ntiles + resident - 1) / resident;
     const int blocks = (a.ntiles + per_cta - 1) / per_cta;
+    // TMA staging needs a 16-byte aligned image and enough rows / columns for the in-tile reflections
+    static const bool no_tma = getenv("IBT_NO_TMA") != nullptr;
+    CUtensorMap tmap;
+    if (!no_tma && a.src_vec_ok && a.h >= 8 && a.w >= 16 && make_tile_map(&tmap, a.src, a.h, a.w, a.pitch, TH + 3)) {
+        pyr_level_tma_kernel<DERIV, DOWN, NW><<<blocks, NW * 32, 0, st>>>(a, tmap);
+        return;
+    }
     pyr_level_kernel<DERIV, DOWN, NW><<<blocks, NW * 32, 0, st>>>(a);
 }
 
