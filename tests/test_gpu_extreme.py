@@ -37,3 +37,24 @@ def test_cuda_vs_oracle_random_shapes(ibt, oracle):
         bs = int(rng.integers(2, 12))          # blockSize 1 is degenerate: lambda_min of a rank-1 tensor is rounding noise
         e, eo = ibt.cornerMinEigenVal(a, bs), oracle.cornerMinEigenVal(a, bs)
         assert np.abs(e - eo).max() <= 2e-4 * np.abs(eo).max(), (h, w, bs)
+
+
+def test_pyramid_cp_async_path_without_tma(tmp_path):
+    """The 16-byte cp.async staging path (used when no tensor map can be made) stays bit-exact: run in a subprocess
+    with IBT_NO_TMA=1 against the oracle."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from iceberg_tracking_code_b200 import cv\n"
+        "from oracle import oracle as orc\n"
+        "rng = np.random.default_rng(3)\n"
+        "for hw in [(1080, 1920), (333, 640), (64, 48), (37, 1024)]:\n"
+        "    a = rng.integers(0, 256, hw, dtype=np.uint8)\n"
+        "    ml, p = cv.buildOpticalFlowPyramid(a, (21, 21), 4, True)\n"
+        "    mlo, po = orc.buildOpticalFlowPyramid(a, (21, 21), 4, True)\n"
+        "    assert ml == mlo and all(np.array_equal(x, y) for x, y in zip(p, po)), hw\n"
+        "print('cp.async path ok')\n" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, IBT_NO_TMA="1"))
+    assert r.returncode == 0 and "cp.async path ok" in r.stdout, r.stdout + r.stderr
