@@ -32,9 +32,10 @@ __host__ __device__ constexpr int lk_nstrips(int w) { return (w + 31) / 32; }
 __host__ __device__ constexpr int lk_strip_cols(int w) { return (w + lk_nstrips(w) - 1) / lk_nstrips(w); }
 // every lane of every strip reads two adjacent elements per row, active or not: pitches keep those reads in the slab
 __host__ __device__ constexpr int lk_reach(int w) { return (lk_nstrips(w) - 1) * lk_strip_cols(w) + 33; }
-__host__ __device__ constexpr int lk_dpitch(int w) { return lk_reach(w); }
-__host__ __device__ constexpr int lk_ipitch(int w) { return (3 + lk_reach(w) + 3) & ~3; }
-__host__ __device__ constexpr int lk_jpitch(int w) { return (2 * LK_MARGIN + 3 + lk_reach(w) + 3) & ~3; }
+__host__ __device__ constexpr int lk_dpitch(int w) { return (lk_reach(w) + 3) & ~3; }                 // words; rows are 16-byte multiples (TMA box)
+// TMA boxes start on 16-byte boundaries of the image row: up to 15 extra columns on the left
+__host__ __device__ constexpr int lk_ipitch(int w) { return (15 + lk_reach(w) + 15) & ~15; }
+__host__ __device__ constexpr int lk_jpitch(int w) { return (15 + 2 * LK_MARGIN + lk_reach(w) + 15) & ~15; }
 
 struct LKLevel {
     const uint8_t *img;
@@ -43,11 +44,17 @@ struct LKLevel {
     int deriv_pitch;            // 4-byte elements
     int rows, cols;
     int word_ok;                // img and img_pitch are 4-byte aligned: patch staging may use 4-byte cp.async
+    int tma_img, tma_der;       // tensor maps exist for this level (16-byte aligned base and pitch)
 };
 struct LKPyr {
     LKLevel lv[IBT_MAX_LEVELS];
     int nlevels;
 };
+// tensor maps of both pyramids: [pyramid][level]; boxes = I window, J search patch, Scharr window
+struct LKMaps {
+    CUtensorMap imgI[2][IBT_MAX_LEVELS], imgJ[2][IBT_MAX_LEVELS], der[2][IBT_MAX_LEVELS];
+};
+
 struct LKArgs {
     LKPyr pyr[2];               // [0] = prev, [1] = next
     const float *p0;
@@ -249,7 +256,8 @@ template <int WW, int WH>
 __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, float ptx, float pty,
                                          bool use_init, bool want_status, bool want_err, float &ox, float &oy, int &status,
                                          float &err, int &iters, unsigned char *slab, int isr, int isw, int jsr, int jsw,
-                                         int lane)
+                                         int lane, const CUtensorMap *mapI, const CUtensorMap *mapJ, const CUtensorMap *mapD,
+                                         uint64_t *bars, unsigned &phases)
 {
     const float FLT_SCALE = 1.f / (1 << 20);
     const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
@@ -286,23 +294,42 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
         }
         nx = __fsub_rn(nx, halfx); ny = __fsub_rn(ny, halfy);
 
-        // ---- one burst of async copies: I window, its Scharr planes (group 0), J search patch (group 1) -----------
-        const int ipxa = ipx & ~3;
-        stage_bytes(LI, ipxa, ipy, winH + 1, IPITCH, IRPP, isr, isw, ipatch, lane);
-        stage_deriv<WW, WH>(LI, a, ipx, ipy, dpatch, lane);
-        cp_async_commit();
+        // ---- one burst of async copies: I window + its Scharr planes (barrier / group 0), J search patch (1) -------------
+        // TMA where the level has tensor maps and the patch needs no reflection (bulk tensor copies zero-fill outside the
+        // image: right for the Scharr planes, wrong for intensities); else 4-byte cp.async; else the REFLECT_101 gather.
+        const bool i_in = ipx >= 0 && ipy >= 0 && ipx + winW < cols && ipy + winH < rows;
+        const bool i_tma = LI.tma_img && i_in, d_tma = LI.tma_der != 0;
+        const int ipxa = i_tma ? (ipx & ~15) : (ipx & ~3);     // bulk tensor copies start on 16-byte boundaries
+        const int doff = d_tma ? (ipx & 3) : 0;
         int px0 = 0, py0 = 0;
-        bool staged = false;
-        {
-            const int inx = cv_floor(nx), iny = cv_floor(ny);
-            if (!window_oob(inx, iny, winW, winH, rows, cols)) {
-                px0 = (inx - LK_MARGIN) & ~3; py0 = iny - LK_MARGIN;
-                stage_bytes(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
-                staged = true;
+        bool staged = false, j_tma = false;
+        const int jnx = cv_floor(nx), jny = cv_floor(ny);
+        const bool j_ok = !window_oob(jnx, jny, winW, winH, rows, cols);
+        if (j_ok) {
+            const int bx = jnx - LK_MARGIN, by = jny - LK_MARGIN, bxa = bx & ~15;
+            j_tma = LJ.tma_img && bxa >= 0 && by >= 0 && bxa + JPITCH <= cols && by + JROWS <= rows;
+            px0 = j_tma ? bxa : (bx & ~3); py0 = by;
+            staged = true;
+        }
+        if (lane == 0 && (i_tma || d_tma || j_tma)) {
+            fence_proxy_async();                              // this warp's earlier generic-proxy slab accesses come first
+            if (i_tma || d_tma) {
+                mbar_expect_tx(&bars[0], (i_tma ? (unsigned)(IPITCH * (winH + 1)) : 0u) + (d_tma ? (unsigned)(DPITCH * 4 * (winH + 1)) : 0u));
+                if (i_tma) tma_load_2d(ipatch, &mapI[level], ipxa, ipy, &bars[0]);
+                if (d_tma) tma_load_2d(dpatch, &mapD[level], ipx - doff, ipy, &bars[0]);
+            }
+            if (j_tma) {
+                mbar_expect_tx(&bars[1], (unsigned)(JPITCH * JROWS));
+                tma_load_2d(jpatch, &mapJ[level], px0, py0, &bars[1]);
             }
         }
+        if (!i_tma) stage_bytes(LI, ipxa, ipy, winH + 1, IPITCH, IRPP, isr, isw, ipatch, lane);
+        if (!d_tma) stage_deriv<WW, WH>(LI, a, ipx, ipy, dpatch, lane);
+        cp_async_commit();
+        if (j_ok && !j_tma) stage_bytes(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
         cp_async_commit();
         cp_async_wait<1>();
+        if (i_tma || d_tma) { mbar_wait(&bars[0], phases & 1u); phases ^= 1u; }
         __syncwarp();
 
         uint32_t wtop, wbot;
@@ -316,7 +343,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             const int cs = s * strip_cols;
             const bool active = lane < min(strip_cols, winW - cs);
             const uint8_t *ip = ipatch + (ipx - ipxa) + cs + lane;
-            const uint32_t *dp = dpatch + cs + lane;
+            const uint32_t *dp = dpatch + doff + cs + lane;
             uint2 *wrow = win + (s * winH) * 32 + lane;
             int a11 = 0, a12 = 0, a22 = 0;
             uint32_t ipair = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
@@ -345,6 +372,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             sA11 += warp_sum_wide(a11); sA12 += warp_sum_wide(a12); sA22 += warp_sum_wide(a22);
         }
         cp_async_wait<0>();
+        if (j_tma) { mbar_wait(&bars[1], (phases >> 1) & 1u); phases ^= 2u; }
         __syncwarp();
         const float A11 = __fmul_rn(__ll2float_rn(sA11), FLT_SCALE);
         const float A12 = __fmul_rn(__ll2float_rn(sA12), FLT_SCALE);
@@ -359,7 +387,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             continue;
         }
         D = __fdiv_rn(1.f, D);
-        const int max_off = 2 * LK_MARGIN + 3;
+        const int max_off = JPITCH - (WW ? lk_reach(WW) : (nstrips - 1) * strip_cols + 33);   // window + neighbour column stay inside the patch row
         float pdx = 0.f, pdy = 0.f;
         for (int j = 0; j < a.maxCount; j++) {
             const int inx = cv_floor(nx), iny = cv_floor(ny);
@@ -413,10 +441,17 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
 
 template <int WW, int WH>
 __global__ void __launch_bounds__(256)
-lk_kernel(const __grid_constant__ LKArgs a)
+lk_kernel(const __grid_constant__ LKArgs a, const LKMaps *__restrict__ maps)
 {
-    extern __shared__ __align__(16) unsigned char lk_smem[];
+    extern __shared__ __align__(128) unsigned char lk_smem[];
+    __shared__ __align__(8) uint64_t lk_bars[8][2];        // per warp: [0] I window + Scharr planes, [1] J patch
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (lane == 0) {
+        mbar_init(&lk_bars[wib][0], 1); mbar_init(&lk_bars[wib][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phases = 0u;                                  // bit b = parity to wait for on lk_bars[wib][b]
     unsigned char *slab = lk_smem + (size_t)wib * a.warp_smem;
     // lane -> (row, word) assignment of the two byte-patch layouts
     const int ippw = (WW ? lk_ipitch(WW) : a.ipitch) >> 2, jppw = (WW ? lk_jpitch(WW) : a.jpitch) >> 2;
@@ -441,7 +476,8 @@ lk_kernel(const __grid_constant__ LKArgs a)
         const bool want_status = pass == 0 ? a.st1 != nullptr : a.st0 != nullptr;
         const bool want_err = pass == 0 ? a.err1 != nullptr : a.err0 != nullptr;
         lk_point<WW, WH>(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, want_status, want_err, ox, oy, status, err, iters,
-                         slab, isr, isw, jsr, jsw, lane);
+                         slab, isr, isw, jsr, jsw, lane, maps->imgI[pass], maps->imgJ[pass ^ 1], maps->der[pass], lk_bars[wib],
+                         phases);
         if (pass == 0) it_f = iters; else it_b = iters;
         if (lane == 0) {
             if (pass == 0) {
@@ -488,6 +524,7 @@ static int fill_pyr(const ibt_pyramid_t *p, LKPyr &o, bool need_deriv)
         o.lv[l].rows = p->rows[l];
         o.lv[l].cols = p->cols[l];
         o.lv[l].word_ok = (reinterpret_cast<uintptr_t>(p->img[l]) % 4 == 0) && (p->img_pitch[l] % 4 == 0);
+        o.lv[l].tma_img = o.lv[l].tma_der = 0;
     }
     return IBT_OK;
 }
@@ -520,14 +557,32 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     // at or after the end of template row r  <=>  D0 >= off_last + (256 - 4*dpitch) * winH.
     const size_t off_last = (size_t)(a.nstrips - 1) * winH * 32 * sizeof(uint2);
     const int slack = 256 - 4 * a.dpitch;
-    const size_t d0 = off_last + (slack > 0 ? (size_t)slack * winH : 0);
+    size_t d0 = off_last + (slack > 0 ? (size_t)slack * winH : 0);
+    d0 = (d0 + 127) & ~(size_t)127;                     // TMA destinations are 128-byte aligned
     a.off_deriv = (int)d0;
     size_t off = d0 + (size_t)(winH + 1) * a.dpitch * 4;
     if (off < (size_t)a.tmpl_elems * sizeof(uint2)) off = (size_t)a.tmpl_elems * sizeof(uint2);
-    off = (off + 15) & ~(size_t)15;
-    a.off_ipatch = (int)off; off += (size_t)(winH + 1) * a.ipitch;
+    off = (off + 127) & ~(size_t)127;
+    a.off_ipatch = (int)off; off += (size_t)(winH + 1) * a.ipitch; off = (off + 127) & ~(size_t)127;
     a.off_jpatch = (int)off; off += (size_t)a.jrows * a.jpitch;
-    a.warp_smem = (int)((off + 15) & ~(size_t)15);
+    a.warp_smem = (int)((off + 127) & ~(size_t)127);
+    // tensor maps (boxes: I window ipitch x (winH+1), J patch jpitch x jrows, Scharr window dpitch words x (winH+1))
+    static thread_local LKMaps maps;
+    static const bool no_tma = getenv("IBT_NO_TMA") != nullptr;
+    static const int tma_mask = getenv("IBT_LK_TMA") ? atoi(getenv("IBT_LK_TMA")) : 3;      // 1: intensity patches, 2: Scharr
+    for (int pi = 0; pi < 2 && !no_tma; pi++) {
+        const ibt_pyramid_t *P = pi ? B : A;
+        for (int l = 0; l < P->nlevels; l++) {
+            LKLevel &lv = a.pyr[pi].lv[l];
+            lv.tma_img = (tma_mask & 1) && make_map_2d(&maps.imgI[pi][l], CU_TENSOR_MAP_DATA_TYPE_UINT8, P->img[l], P->cols[l], P->rows[l],
+                                     P->img_pitch[l], a.ipitch, winH + 1) &&
+                         make_map_2d(&maps.imgJ[pi][l], CU_TENSOR_MAP_DATA_TYPE_UINT8, P->img[l], P->cols[l], P->rows[l],
+                                     P->img_pitch[l], a.jpitch, a.jrows);
+            lv.tma_der = (tma_mask & 2) && P->deriv[l] != nullptr &&
+                         make_map_2d(&maps.der[pi][l], CU_TENSOR_MAP_DATA_TYPE_UINT32, P->deriv[l], P->cols[l], P->rows[l],
+                                     P->deriv_pitch[l], a.dpitch, winH + 1);
+        }
+    }
     a.maxCount = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
     if (epsilon < 0) epsilon = 0;
     if (epsilon > 10) epsilon = 10;
@@ -555,8 +610,10 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     static bool attr_set = false;
     static unsigned int *counters = nullptr;           // ring of work counters: one 4-byte slot per launch in flight
     static unsigned int next_slot = 0;
+    static LKMaps *dmaps = nullptr;                    // ring of tensor-map sets in global memory (one per launch in flight)
+    constexpr unsigned int kMapSlots = 32;
     constexpr unsigned int kSlots = 256;
-    void (*kern)(const LKArgs) = lk_kernel<0, 0>;      // generic window; the sizes the configs use are specialised
+    void (*kern)(const LKArgs, const LKMaps *) = lk_kernel<0, 0>;      // generic window; the sizes the configs use are specialised
     if (winW == 21 && winH == 21) kern = lk_kernel<21, 21>;
     else if (winW == 31 && winH == 31) kern = lk_kernel<31, 31>;
     else if (winW == 35 && winH == 35) kern = lk_kernel<35, 35>;
@@ -567,6 +624,7 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
         IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<31, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<35, 35>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         IBT_CUDA_TRY(cudaMalloc(&counters, kSlots * sizeof(unsigned int)));
+        IBT_CUDA_TRY(cudaMalloc(&dmaps, kMapSlots * sizeof(LKMaps)));
         attr_set = true;
     }
     a.work_counter = counters + (next_slot++ % kSlots);
@@ -574,7 +632,9 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     int blocks = kNumSMs * best_ctas;                   // persistent: one wave, warps pull points until none are left
     const int need = (a.n + wpc - 1) / wpc;
     if (blocks > need) blocks = need;
-    kern<<<blocks, wpc * 32, smem, st>>>(a);
+    LKMaps *dm = dmaps + (next_slot % kMapSlots);
+    IBT_CUDA_TRY(cudaMemcpyAsync(dm, &maps, sizeof(LKMaps), cudaMemcpyHostToDevice, st));
+    kern<<<blocks, wpc * 32, smem, st>>>(a, dm);
     return check_launch("ibt_lk");
 }
 

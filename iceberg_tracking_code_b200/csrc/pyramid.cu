@@ -218,33 +218,6 @@ pyr_level_kernel(const __grid_constant__ PyrArgs a)
 // on an mbarrier) instead of per-thread 16-byte cp.async copies: no staging instructions, no per-row index math.  The
 // tensor map covers the w x h image; coordinates left / above / right / below it come back as zeros and the
 // REFLECT_101 rows and columns are then patched from the tile itself.
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    for (int spin = 0; spin < (1 << 26); spin++) {
-        unsigned ok;
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    __trap();                                   // a lost TMA must fail loudly, not hang the GPU
-}
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1),
-                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-
 // REFLECT_101 rows of a TMA-staged tile (zeros outside the image): rows -2, -1 and h, h+1, copied inside the tile.
 template <int NW>
 __device__ __forceinline__ bool reflect_rows(const PyrArgs &a, int t, uint8_t *tile, int tid)
@@ -288,7 +261,7 @@ pyr_level_tma_kernel(const __grid_constant__ PyrArgs a, const __grid_constant__ 
     auto issue = [&](int t, int b) {                      // one thread: arm the barrier, launch the bulk tensor copy
         if (tid == 0) {
             const int ty = t / a.ntx, tx = t - ty * a.ntx;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // our generic-proxy patches precede the async write
+            fence_proxy_async();                                              // our generic-proxy patches precede the async write
             mbar_expect_tx(&full[b], TILE_BYTES);
             tma_load_2d(tiles[b], &tmap, tx * TW - HXB, ty * TH - 2, &full[b]);
         }
@@ -314,36 +287,9 @@ pyr_level_tma_kernel(const __grid_constant__ PyrArgs a, const __grid_constant__ 
     }
 }
 
-// host: tensor map of a (h, w) u8 image with row pitch `pitch`, box = SPITCH x SROWS, zero fill outside
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        (void)cudaGetLastError();
-    }
-    return fn;
-}
 static bool make_tile_map(CUtensorMap *m, const uint8_t *src, int h, int w, int64_t pitch, int srows)
 {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) return false;
-    const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
-    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
-    const cuuint32_t box[2] = {(cuuint32_t)SPITCH, (cuuint32_t)srows};
-    const cuuint32_t estr[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(src), gdim, gstride, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, src, w, h, pitch, SPITCH, srows);
 }
 
 template <bool DERIV, bool DOWN, int NW>
