@@ -441,7 +441,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
 
 template <int WW, int WH>
 __global__ void __launch_bounds__(256)
-lk_kernel(const __grid_constant__ LKArgs a, const LKMaps *__restrict__ maps)
+lk_kernel(const __grid_constant__ LKArgs a, const __grid_constant__ LKMaps maps)
 {
     extern __shared__ __align__(128) unsigned char lk_smem[];
     __shared__ __align__(8) uint64_t lk_bars[8][2];        // per warp: [0] I window + Scharr planes, [1] J patch
@@ -476,7 +476,7 @@ lk_kernel(const __grid_constant__ LKArgs a, const LKMaps *__restrict__ maps)
         const bool want_status = pass == 0 ? a.st1 != nullptr : a.st0 != nullptr;
         const bool want_err = pass == 0 ? a.err1 != nullptr : a.err0 != nullptr;
         lk_point<WW, WH>(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, want_status, want_err, ox, oy, status, err, iters,
-                         slab, isr, isw, jsr, jsw, lane, maps->imgI[pass], maps->imgJ[pass ^ 1], maps->der[pass], lk_bars[wib],
+                         slab, isr, isw, jsr, jsw, lane, maps.imgI[pass], maps.imgJ[pass ^ 1], maps.der[pass], lk_bars[wib],
                          phases);
         if (pass == 0) it_f = iters; else it_b = iters;
         if (lane == 0) {
@@ -610,10 +610,8 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     static bool attr_set = false;
     static unsigned int *counters = nullptr;           // ring of work counters: one 4-byte slot per launch in flight
     static unsigned int next_slot = 0;
-    static LKMaps *dmaps = nullptr;                    // ring of tensor-map sets in global memory (one per launch in flight)
-    constexpr unsigned int kMapSlots = 32;
     constexpr unsigned int kSlots = 256;
-    void (*kern)(const LKArgs, const LKMaps *) = lk_kernel<0, 0>;      // generic window; the sizes the configs use are specialised
+    void (*kern)(const LKArgs, const LKMaps) = lk_kernel<0, 0>;      // generic window; the sizes the configs use are specialised
     if (winW == 21 && winH == 21) kern = lk_kernel<21, 21>;
     else if (winW == 31 && winH == 31) kern = lk_kernel<31, 31>;
     else if (winW == 35 && winH == 35) kern = lk_kernel<35, 35>;
@@ -624,7 +622,6 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
         IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<31, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<35, 35>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         IBT_CUDA_TRY(cudaMalloc(&counters, kSlots * sizeof(unsigned int)));
-        IBT_CUDA_TRY(cudaMalloc(&dmaps, kMapSlots * sizeof(LKMaps)));
         attr_set = true;
     }
     a.work_counter = counters + (next_slot++ % kSlots);
@@ -632,9 +629,7 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     int blocks = kNumSMs * best_ctas;                   // persistent: one wave, warps pull points until none are left
     const int need = (a.n + wpc - 1) / wpc;
     if (blocks > need) blocks = need;
-    LKMaps *dm = dmaps + (next_slot % kMapSlots);
-    IBT_CUDA_TRY(cudaMemcpyAsync(dm, &maps, sizeof(LKMaps), cudaMemcpyHostToDevice, st));
-    kern<<<blocks, wpc * 32, smem, st>>>(a, dm);
+    kern<<<blocks, wpc * 32, smem, st>>>(a, maps);          // the tensor maps travel as a __grid_constant__ parameter
     return check_launch("ibt_lk");
 }
 
