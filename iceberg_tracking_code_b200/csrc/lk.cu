@@ -301,14 +301,15 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
         const bool i_tma = LI.tma_img && i_in, d_tma = LI.tma_der != 0;
         const int ipxa = i_tma ? (ipx & ~15) : (ipx & ~3);     // bulk tensor copies start on 16-byte boundaries
         const int doff = d_tma ? (ipx & 3) : 0;
-        int px0 = 0, py0 = 0;
+        int px0 = 0, py0 = 0, vx0 = 0;                        // staged origin (aligned) and logical patch origin
         bool staged = false, j_tma = false;
         const int jnx = cv_floor(nx), jny = cv_floor(ny);
         const bool j_ok = !window_oob(jnx, jny, winW, winH, rows, cols);
         if (j_ok) {
-            const int bx = jnx - LK_MARGIN, by = jny - LK_MARGIN, bxa = bx & ~15;
-            j_tma = LJ.tma_img && bxa >= 0 && by >= 0 && bxa + JPITCH <= cols && by + JROWS <= rows;
-            px0 = j_tma ? bxa : (bx & ~3); py0 = by;
+            const int bx = jnx - LK_MARGIN, by = jny - LK_MARGIN;
+            // the logical patch (window + margin) must lie inside the image; the box may stick out (zero fill, never read)
+            j_tma = LJ.tma_img && bx >= 0 && by >= 0 && bx + winW + 2 * LK_MARGIN < cols && by + JROWS <= rows;
+            px0 = j_tma ? (bx & ~15) : (bx & ~3); py0 = by; vx0 = bx;
             staged = true;
         }
         if (lane == 0 && (i_tma || d_tma || j_tma)) {
@@ -387,7 +388,6 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             continue;
         }
         D = __fdiv_rn(1.f, D);
-        const int max_off = JPITCH - (WW ? lk_reach(WW) : (nstrips - 1) * strip_cols + 33);   // window + neighbour column stay inside the patch row
         float pdx = 0.f, pdy = 0.f;
         for (int j = 0; j < a.maxCount; j++) {
             const int inx = cv_floor(nx), iny = cv_floor(ny);
@@ -395,8 +395,8 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
                 if (level == 0) status = 0;
                 break;
             }
-            if (!staged || (unsigned)(inx - px0) > (unsigned)max_off || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
-                px0 = (inx - LK_MARGIN) & ~3; py0 = iny - LK_MARGIN;
+            if (!staged || (unsigned)(inx - vx0) > 2u * LK_MARGIN || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
+                vx0 = inx - LK_MARGIN; px0 = vx0 & ~3; py0 = iny - LK_MARGIN;
                 restage_sync(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
                 staged = true;
             }
@@ -424,8 +424,8 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             const int iqx = cv_floor(qx), iqy = cv_floor(qy);
             if (window_oob(iqx, iqy, winW, winH, rows, cols)) { status = 0; err = 0.f; continue; }
             if (!want_err) continue;
-            if (!staged || (unsigned)(iqx - px0) > (unsigned)max_off || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
-                px0 = (iqx - LK_MARGIN) & ~3; py0 = iqy - LK_MARGIN;
+            if (!staged || (unsigned)(iqx - vx0) > 2u * LK_MARGIN || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
+                vx0 = iqx - LK_MARGIN; px0 = vx0 & ~3; py0 = iqy - LK_MARGIN;
                 restage_sync(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
             }
             bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), wtop, wbot, iw00, iw01, iw10, iw11);
