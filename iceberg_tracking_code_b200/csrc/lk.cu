@@ -173,6 +173,37 @@ __device__ __forceinline__ void stage_bytes(const LKLevel &L, int x0a, int y0, i
     }
 }
 
+// REFLECT_101 of a TMA-staged intensity patch inside shared memory.  The bulk tensor copy zero-fills what lies outside
+// the image; when every mirror source of the needed region [nx0, nx1] x [y0, y0 + nrows) lies inside that region (and
+// inside the image) the out-of-image rows, then columns, are copied from the patch itself.  patch_reflectable() is the
+// warp-uniform test; windows further out take the gather path.
+__device__ __forceinline__ bool patch_reflectable(int nx0, int nx1, int y0, int nrows, int rows, int cols)
+{
+    const int y1 = y0 + nrows - 1;
+    return -nx0 <= nx1 && -nx0 < cols && 2 * (cols - 1) - nx1 >= nx0 && 2 * (cols - 1) - nx1 >= 0 &&
+           -y0 <= y1 && -y0 < rows && 2 * (rows - 1) - y1 >= y0 && 2 * (rows - 1) - y1 >= 0;
+}
+__device__ __noinline__ void patch_reflect(uint8_t *patch, int pitch, int x0a, int nx0, int nx1, int y0, int nrows, int rows,
+                                           int cols, int lane)
+{
+    __syncwarp();
+    const int pw = pitch >> 2;
+    for (int r = 0; r < nrows; r++) {                           // rows first (whole staged width)
+        const int y = y0 + r;
+        if (y >= 0 && y < rows) continue;
+        const int rs = (y < 0 ? -y : 2 * (rows - 1) - y) - y0;
+        for (int c = lane; c < pw; c += 32)
+            reinterpret_cast<uint32_t *>(patch + r * pitch)[c] = reinterpret_cast<const uint32_t *>(patch + rs * pitch)[c];
+    }
+    __syncwarp();
+    for (int x = nx0; x <= nx1; x++) {                          // then the needed columns outside the image
+        if (x >= 0 && x < cols) { if (x >= 0 && nx1 < cols) break; continue; }
+        const int xs = (x < 0 ? -x : 2 * (cols - 1) - x) - x0a, xd = x - x0a;
+        for (int r = lane; r < nrows; r += 32) patch[r * pitch + xd] = patch[r * pitch + xs];
+    }
+    __syncwarp();
+}
+
 // Re-stage the J patch synchronously (the window drifted out of the prefetched patch): rare, kept out of line.
 __device__ __noinline__ void restage_sync(const LKLevel &L, int x0a, int y0, int nrows, int pitch, int rpp, int sr, int sw,
                                           uint8_t *dst, int lane)
@@ -298,17 +329,21 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
         // TMA where the level has tensor maps and the patch needs no reflection (bulk tensor copies zero-fill outside the
         // image: right for the Scharr planes, wrong for intensities); else 4-byte cp.async; else the REFLECT_101 gather.
         const bool i_in = ipx >= 0 && ipy >= 0 && ipx + winW < cols && ipy + winH < rows;
-        const bool i_tma = LI.tma_img && i_in, d_tma = LI.tma_der != 0;
+        const bool i_fix = !i_in && patch_reflectable(ipx, ipx + winW, ipy, winH + 1, rows, cols);
+        const bool i_tma = LI.tma_img && (i_in || i_fix), d_tma = LI.tma_der != 0;
         const int ipxa = i_tma ? (ipx & ~15) : (ipx & ~3);     // bulk tensor copies start on 16-byte boundaries
         const int doff = d_tma ? (ipx & 3) : 0;
         int px0 = 0, py0 = 0, vx0 = 0;                        // staged origin (aligned) and logical patch origin
-        bool staged = false, j_tma = false;
+        bool staged = false, j_tma = false, j_fix = false;
         const int jnx = cv_floor(nx), jny = cv_floor(ny);
         const bool j_ok = !window_oob(jnx, jny, winW, winH, rows, cols);
         if (j_ok) {
             const int bx = jnx - LK_MARGIN, by = jny - LK_MARGIN;
-            // the logical patch (window + margin) must lie inside the image; the box may stick out (zero fill, never read)
-            j_tma = LJ.tma_img && bx >= 0 && by >= 0 && bx + winW + 2 * LK_MARGIN < cols && by + JROWS <= rows;
+            // the logical patch (window + margin) must lie inside the image (or be mirrorable inside shared memory);
+            // the box may stick out further (zero fill, never read)
+            const bool j_in = bx >= 0 && by >= 0 && bx + winW + 2 * LK_MARGIN < cols && by + JROWS <= rows;
+            j_fix = !j_in && patch_reflectable(bx, bx + winW + 2 * LK_MARGIN, by, JROWS, rows, cols);
+            j_tma = LJ.tma_img && (j_in || j_fix);
             px0 = j_tma ? (bx & ~15) : (bx & ~3); py0 = by; vx0 = bx;
             staged = true;
         }
@@ -332,6 +367,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
         cp_async_wait<1>();
         if (i_tma || d_tma) { mbar_wait(&bars[0], phases & 1u); phases ^= 1u; }
         __syncwarp();
+        if (i_tma && i_fix) patch_reflect(ipatch, IPITCH, ipxa, ipx, ipx + winW, ipy, winH + 1, rows, cols, lane);
 
         uint32_t wtop, wbot;
         int iw00, iw01, iw10, iw11;
@@ -375,6 +411,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
         cp_async_wait<0>();
         if (j_tma) { mbar_wait(&bars[1], (phases >> 1) & 1u); phases ^= 2u; }
         __syncwarp();
+        if (j_tma && j_fix) patch_reflect(jpatch, JPITCH, px0, vx0, vx0 + winW + 2 * LK_MARGIN, py0, JROWS, rows, cols, lane);
         const float A11 = __fmul_rn(__ll2float_rn(sA11), FLT_SCALE);
         const float A12 = __fmul_rn(__ll2float_rn(sA12), FLT_SCALE);
         const float A22 = __fmul_rn(__ll2float_rn(sA22), FLT_SCALE);
