@@ -125,6 +125,7 @@ class FramePyramid:
         self.maxLevel = ml
         self.sizes = [(sizes[2 * l], sizes[2 * l + 1]) for l in range(ml + 1)]
         dev = g.device
+        g = self._level0(g)
         self._img_buf = [g]
         self._deriv_buf = []
         self.levels = [g]
@@ -138,7 +139,7 @@ class FramePyramid:
                 self._img_buf.append(buf)
                 self.levels.append(buf[:, :w])
             else:
-                pitch = W
+                pitch = g.stride(0)
             st.rows[l], st.cols[l] = h, w
             st.img[l] = self._img_buf[l].data_ptr()
             st.img_pitch[l] = pitch
@@ -151,6 +152,20 @@ class FramePyramid:
                 st.deriv_pitch[l] = dpitch
         self.c = st
         self._build(None)
+
+    def _level0(self, g):
+        """Level 0 is the caller's gray image itself when its rows are 16-byte aligned (the TMA staging paths need that);
+        otherwise it is copied once into a row-padded buffer (view [:, :W]) so that odd widths also take the fast paths."""
+        H, W = g.shape
+        if W % 16 == 0 and g.data_ptr() % 16 == 0:
+            return g
+        pad = getattr(self, "_l0_pad", None)
+        if pad is None or pad.shape[0] != H:
+            pad = torch.empty((H, _round_up(W, 128)), dtype=torch.uint8, device=g.device)
+            self._l0_pad = pad
+        view = pad[:, :W]
+        view.copy_(g)
+        return view
 
     def _build(self, probe):
         if probe is None:
@@ -174,9 +189,11 @@ class FramePyramid:
         g = _to_dev(gray, np.uint8, "FramePyramid gray")
         if tuple(g.shape) != tuple(self.sizes[0]):
             raise error("FramePyramid.rebuild: frame size changed")
+        g = self._level0(g)
         self._img_buf[0] = g
         self.levels[0] = g
         self.c.img[0] = g.data_ptr()
+        self.c.img_pitch[0] = g.stride(0)
         self._build(probe)
         return self
 

@@ -40,7 +40,7 @@ def test_cuda_vs_oracle_random_shapes(ibt, oracle):
 
 
 def test_pyramid_cp_async_path_without_tma(tmp_path):
-    """The 16-byte cp.async staging path (used when no tensor map can be made) stays bit-exact: run in a subprocess
+    """The cp.async staging paths of K1 and K3 (used when no tensor map can be made) stay exact: run in a subprocess
     with IBT_NO_TMA=1 against the oracle."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -54,7 +54,12 @@ def test_pyramid_cp_async_path_without_tma(tmp_path):
         "    ml, p = cv.buildOpticalFlowPyramid(a, (21, 21), 4, True)\n"
         "    mlo, po = orc.buildOpticalFlowPyramid(a, (21, 21), 4, True)\n"
         "    assert ml == mlo and all(np.array_equal(x, y) for x, y in zip(p, po)), hw\n"
-        "print('cp.async path ok')\n" % root)
+        "g = dict(np.load(%r))\n"
+        "for lp in (dict(winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01)), dict(winSize=(35, 35), maxLevel=4, criteria=(3, 25, 0.03))):\n"
+        "    p1, st, err = cv.calcOpticalFlowPyrLK(g['f0'], g['f1'], g['lk_pts'], None, **lp)\n"
+        "    po, so, eo = orc.calcOpticalFlowPyrLK(g['f0'], g['f1'], g['lk_pts'], None, **lp)\n"
+        "    assert np.mean(st == so) >= 0.995 and np.abs(p1 - po).reshape(-1, 2).max(1)[(st == 1).ravel() & (so == 1).ravel()].max() <= 0.01\n"
+        "print('cp.async path ok')\n" % (root, os.path.join(root, "tests", "golden", "kat_texture.npz")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
                        env=dict(os.environ, IBT_NO_TMA="1"))
     assert r.returncode == 0 and "cp.async path ok" in r.stdout, r.stdout + r.stderr
