@@ -269,13 +269,14 @@ __device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__re
             v = dp2a_s16u8(wbot, cur, v);
             const int diff = (int)v >> 9;
             if (MODE == 0) {
-                b1 += diff * ((int)t.y >> 16);                 // Ix, Iy are zero on inactive lanes
+                b1 += diff * ((int)t.y >> 16);
                 b2 += diff * (int)(short)(t.y & 0xffffu);
             } else {
-                b2 += active ? abs(diff) : 0;
+                b2 += abs(diff);
             }
             prev = cur;
         }
+        if (!active) { b1 = 0; b2 = 0; }                        // lanes beyond the window: masked once per pass
         if (MODE == 0) S1 += warp_sum_wide(b1);
         S2 += warp_sum_wide(b2);
     }
@@ -395,9 +396,8 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
                 const int d11x = (int)(short)(dcr & 0xffffu), d11y = (int)dcr >> 16;
                 uint32_t v = dp2a_s16u8(wtop, ipair, 256u);
                 v = dp2a_s16u8(wbot, cpair, v);                        // v = taps + 256; Iw = v >> 9
-                int Ix = (d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
-                int Iy = (d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
-                if (!active) { Ix = 0; Iy = 0; }
+                const int Ix = (d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
+                const int Iy = (d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
                 uint2 t;
                 t.x = 256u - (v & 0xfffffe00u);
                 t.y = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
@@ -406,6 +406,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
                 ipair = cpair; d00x = d10x; d00y = d10y; d01x = d11x; d01y = d11y;
                 __syncwarp();            // the template slab overlaps the Scharr patch rows already consumed (see launch_lk)
             }
+            if (!active) { a11 = 0; a12 = 0; a22 = 0; }       // lanes beyond the window hold garbage columns: masked here
             sA11 += warp_sum_wide(a11); sA12 += warp_sum_wide(a12); sA22 += warp_sum_wide(a22);
         }
         cp_async_wait<0>();
