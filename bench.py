@@ -62,32 +62,40 @@ class ClockSampler(threading.Thread):
             phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            nv = pynvml
+            self.names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
             self.ok = True
         except Exception as e:                      # noqa: BLE001
             self.err = repr(e)
+
+    def sample_now(self):
+        """One synchronous sample (called while the timed kernels are still in flight, so short runs get one too)."""
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:                       # noqa: BLE001
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:                           # noqa: BLE001
+            pass
 
     def run(self):
         if not self.ok:
             return
         nv = self.nv
-        names = {
-            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-        }
         while not self._halt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:                   # noqa: BLE001
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:                       # noqa: BLE001
-                pass
+            self.sample_now()
             self._halt.wait(self.period)
 
     def stop(self):
@@ -231,6 +239,7 @@ def main():
         i = warmup + k
         device_step(i, (i + 1) & 1, probe=probes[k])
     ev1.record()
+    sampler.sample_now()                       # the GPU is still working through the queued steps
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
