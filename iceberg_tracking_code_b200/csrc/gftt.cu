@@ -142,7 +142,9 @@ struct GfttCounters {
 
 __device__ __forceinline__ float tozero(float v, float thr) { return v > thr ? v : 0.f; }
 
-// one thread per 4 pixels of a row: three float4 row loads + the two neighbouring columns
+// one thread per 4 x 4 pixel block: six row loads (float4 + the two neighbouring columns) issued up front
+constexpr int NMS_RY = 4;
+
 __global__ void __launch_bounds__(256)
 nms_kernel(const float *__restrict__ eig, int H, int W, const uint8_t *__restrict__ mask, int64_t mask_pitch,
            double quality, GfttCounters *__restrict__ cnt, unsigned long long *__restrict__ keys, uint32_t cap)
@@ -154,43 +156,55 @@ nms_kernel(const float *__restrict__ eig, int H, int W, const uint8_t *__restric
     __syncthreads();
     const float thr = (float)((double)dec_f32(mb) * quality);
     const int wq = (W + 3) >> 2;                                  // 4-pixel groups per row
-    const int64_t total = (int64_t)(H - 2) * wq;
+    const int hq = (H - 2 + NMS_RY - 1) / NMS_RY;                 // row groups over rows 1 .. H-2
+    const int64_t total = (int64_t)hq * wq;
     const int lane = threadIdx.x & 31;
+    const bool vec = (W & 3) == 0;                                // rows are 16-byte aligned: one float4 + two scalars per row
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
         const int64_t g = base + threadIdx.x;
-        uint32_t flags = 0;
-        float vals[4] = {0.f, 0.f, 0.f, 0.f};
-        int y = 0, x0 = 0;
+        uint32_t flags = 0;                                       // bit (4 * row + col)
+        float r[NMS_RY + 2][6];                                   // rows y0-1 .. y0+RY, columns x0-1 .. x0+4, thresholded
+        int y0 = 0, x0 = 0;
         if (g < total) {
-            y = (int)(g / wq) + 1;
-            x0 = (int)(g - (int64_t)(y - 1) * wq) * 4;
-            float r[3][6];                                        // rows y-1..y+1, columns x0-1 .. x0+4, thresholded
-            const bool vec = (W & 3) == 0;                        // rows are 16-byte aligned: one float4 + two scalars per row
+            const int gy = (int)(g / wq);
+            y0 = gy * NMS_RY + 1;
+            x0 = (int)(g - (int64_t)gy * wq) * 4;
 #pragma unroll
-            for (int dy = 0; dy < 3; dy++) {
-                const float *row = eig + (int64_t)(y - 1 + dy) * W;
+            for (int dy = 0; dy < NMS_RY + 2; dy++) {
+                const int yy = min(y0 - 1 + dy, H - 1);
+                const float *row = eig + (int64_t)yy * W;
                 if (vec) {
                     const float4 m = __ldg(reinterpret_cast<const float4 *>(row + x0));
-                    r[dy][0] = x0 > 0 ? tozero(__ldg(row + x0 - 1), thr) : 0.f;
-                    r[dy][1] = tozero(m.x, thr); r[dy][2] = tozero(m.y, thr); r[dy][3] = tozero(m.z, thr); r[dy][4] = tozero(m.w, thr);
-                    r[dy][5] = x0 + 4 < W ? tozero(__ldg(row + x0 + 4), thr) : 0.f;
+                    r[dy][0] = x0 > 0 ? __ldg(row + x0 - 1) : 0.f;
+                    r[dy][1] = m.x; r[dy][2] = m.y; r[dy][3] = m.z; r[dy][4] = m.w;
+                    r[dy][5] = x0 + 4 < W ? __ldg(row + x0 + 4) : 0.f;
                 } else {
 #pragma unroll
                     for (int c = 0; c < 6; c++) {
                         const int xx = x0 - 1 + c;
-                        r[dy][c] = (xx >= 0 && xx < W) ? tozero(__ldg(row + xx), thr) : 0.f;
+                        r[dy][c] = (xx >= 0 && xx < W) ? __ldg(row + xx) : 0.f;
                     }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int xx = x0 + i;
-                const float v = r[1][i + 1];
-                if (xx >= 1 && xx <= W - 2 && v != 0.f) {
-                    float m = v;
+            for (int dy = 0; dy < NMS_RY + 2; dy++)
 #pragma unroll
-                    for (int dy = 0; dy < 3; dy++) m = fmaxf(m, fmaxf(r[dy][i], fmaxf(r[dy][i + 1], r[dy][i + 2])));
-                    if (v == m && (!mask || mask[(int64_t)y * mask_pitch + xx])) { flags |= 1u << i; vals[i] = v; }
+                for (int c = 0; c < 6; c++) r[dy][c] = tozero(r[dy][c], thr);
+#pragma unroll
+            for (int ry = 0; ry < NMS_RY; ry++) {
+                const int y = y0 + ry;
+                if (y > H - 2) break;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int xx = x0 + i;
+                    const float v = r[ry + 1][i + 1];
+                    if (xx >= 1 && xx <= W - 2 && v != 0.f) {
+                        float m = v;
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++)
+                            m = fmaxf(m, fmaxf(r[ry + dy][i], fmaxf(r[ry + dy][i + 1], r[ry + dy][i + 2])));
+                        if (v == m && (!mask || mask[(int64_t)y * mask_pitch + xx])) flags |= 1u << (4 * ry + i);
+                    }
                 }
             }
         }
@@ -206,13 +220,15 @@ nms_kernel(const float *__restrict__ eig, int H, int W, const uint8_t *__restric
             basepos = __shfl_sync(0xffffffffu, basepos, 31);
             uint32_t pos = basepos + pre - n;
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (flags & (1u << i)) {
-                    const uint32_t e = enc_f32(vals[i]);
-                    if (pos < cap) keys[pos] = ((unsigned long long)e << 32) | (uint32_t)(y * W + x0 + i);
-                    atomicAdd(&shist[e >> 20], 1u);
-                    pos++;
-                }
+            for (int ry = 0; ry < NMS_RY; ry++)
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (flags & (1u << (4 * ry + i))) {
+                        const uint32_t e = enc_f32(r[ry + 1][i + 1]);
+                        if (pos < cap) keys[pos] = ((unsigned long long)e << 32) | (uint32_t)((y0 + ry) * W + x0 + i);
+                        atomicAdd(&shist[e >> 20], 1u);
+                        pos++;
+                    }
         }
     }
     __syncthreads();
