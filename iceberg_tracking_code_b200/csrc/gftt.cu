@@ -114,11 +114,8 @@ static int launch_eig(const uint8_t *gray, int H, int W, int64_t pitch, int bs, 
     if (!gray || !eig || H <= 0 || W <= 0 || bs < 1 || bs > MAX_BLOCK || pitch < W || eig_pitch_bytes % 4 != 0 ||
         eig_pitch_bytes < (int64_t)W * 4)
         return IBT_E_INVALID;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (eig_smem_bytes(bs) > 48 * 1024)                 // large blockSize: opt in to > 48 KB dynamic shared memory (per device)
         IBT_CUDA_TRY(cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem_bytes(MAX_BLOCK)));
-        attr_done = true;
-    }
     const float scale = (float)(1.0 / (4.0 * bs * 255.0));       // OpenCV's Sobel scale for ksize 3
     const double s2 = (double)scale * (double)scale;
     const int nout = EW - bs + 1;

@@ -645,8 +645,15 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
         }
     }
     const size_t smem = (size_t)a.warp_smem * wpc;
-    static bool attr_set = false;
-    static unsigned int *counters = nullptr;           // ring of work counters: one 4-byte slot per launch in flight
+    // per-device state (function attributes and the ring of work counters: one 4-byte slot per launch in flight)
+    constexpr int kMaxDev = 64;
+    static bool attr_set_dev[kMaxDev] = {false};
+    static unsigned int *counters_dev[kMaxDev] = {nullptr};
+    int dev_id = 0;
+    IBT_CUDA_TRY(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= kMaxDev) return IBT_E_INVALID;
+    bool &attr_set = attr_set_dev[dev_id];
+    unsigned int *&counters = counters_dev[dev_id];
     static unsigned int next_slot = 0;
     constexpr unsigned int kSlots = 256;
     void (*kern)(const LKArgs, const LKMaps) = lk_kernel<0, 0>;      // generic window; the sizes the configs use are specialised
