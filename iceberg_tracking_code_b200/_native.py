@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libibt.so")
 
 IBT_MAX_LEVELS = 8
 IBT_MAX_WIN = 63
-IBT_OK, IBT_E_INVALID, IBT_E_CUDA, IBT_E_WORKSPACE, IBT_E_CAPACITY = 0, -1, -2, -3, -4
+IBT_OK, IBT_E_INVALID, IBT_E_CUDA, IBT_E_WORKSPACE, IBT_E_CAPACITY, IBT_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 
 class IbtError(RuntimeError):
@@ -31,9 +31,24 @@ class ibt_pyramid_t(C.Structure):
     ]
 
 
+class ibt_jpeg_info_t(C.Structure):
+    """HOST mirror of `struct ibt_jpeg_info` in include/ibt.h."""
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32),
+        ("hsamp", C.c_int32 * 3), ("vsamp", C.c_int32 * 3),
+        ("qsel", C.c_int32 * 3), ("dcsel", C.c_int32 * 3), ("acsel", C.c_int32 * 3),
+        ("restart_interval", C.c_int32), ("reserved", C.c_int32),
+        ("scan_offset", C.c_int64), ("scan_bytes", C.c_int64),
+        ("quant", (C.c_uint16 * 64) * 4),
+        ("dc_bits", (C.c_uint8 * 16) * 4), ("dc_vals", (C.c_uint8 * 16) * 4),
+        ("ac_bits", (C.c_uint8 * 16) * 4), ("ac_vals", (C.c_uint8 * 256) * 4),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/ibt.h declares
 _vp, _i, _i64, _d, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_size_t
 _PYR = C.POINTER(ibt_pyramid_t)
+_JPG = C.POINTER(ibt_jpeg_info_t)
 SIGNATURES = {
     "ibt_version": (_i, []),
     "ibt_error_string": (C.c_char_p, [_i]),
@@ -52,6 +67,9 @@ SIGNATURES = {
     "ibt_photo_to_utm": (_i, [_vp, _i64, C.POINTER(C.c_double), _vp, _vp]),
     "ibt_track_velocities": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "ibt_polygon_mask": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp]),
+    "ibt_jpeg_parse": (_i, [_vp, _i64, _JPG]),
+    "ibt_jpeg_workspace_bytes": (_i64, [_JPG]),
+    "ibt_jpeg_decode": (_i, [_vp, _JPG, _vp, _i64, _vp, _i64, _vp, _i64, _i, C.POINTER(C.c_int), _vp]),
 }
 
 _lib = None

@@ -24,6 +24,7 @@ IBT_API const char *ibt_error_string(int code)
     case IBT_E_CUDA: return "CUDA error (see ibt_last_cuda_error)";
     case IBT_E_WORKSPACE: return "workspace too small";
     case IBT_E_CAPACITY: return "output capacity too small";
+    case IBT_E_UNSUPPORTED: return "unsupported input";
     default: return "unknown error code";
     }
 }

@@ -1,0 +1,789 @@
+// K5: baseline JPEG -> RGB / gray on the GPU.
+// Replaces `np.array(Image.open(image))` (+ the cv2.cvtColor that follows it) at s1_lucaskanade_tracking.py:310-311,
+// s0_1_test_lucaskanade_tracking.py:79-80: Pillow's bundled libjpeg-turbo with default settings (islow IDCT, fancy
+// upsampling, 16-bit fixed-point YCbCr->RGB), reproduced bit for bit.  The file travels to the GPU compressed
+// (a few MB instead of 72 MB of RGB per 24 MP frame) and the tracker consumes the gray plane in place.
+//
+//   destuff       remove the 0x00 after every 0xFF of the entropy-coded segment (count / scan / write); bytes are stored
+//                 so that a 32-bit load returns them in bit-stream (big-endian) order
+//   Huffman       the segment has no restart markers, so it is decoded speculatively: thread i owns bits
+//                 [i*S, (i+1)*S) and starts from a guessed decoder state (block 0 of an MCU, DC expected).  Huffman
+//                 streams self-synchronise: after a few symbols a decoder that started in the wrong state is in the
+//                 right one.  Rounds: every thread whose entry state changed decodes its subsequence again and hands its
+//                 exit state (bit position, block in MCU, zig-zag index) to its successor, until nothing changes
+//                 (thread 0's entry state is exact, so the fixed point is the sequential decode: correctness never
+//                 depends on self-synchronisation, only the number of rounds does).  Then an exclusive scan of the
+//                 blocks completed per subsequence gives every thread its output block, and one more pass writes the
+//                 coefficients (natural order, int16; DC still differential).
+//   DC            per-component prefix sum of the DC differences over MCUs (scan) + within the MCU (IDCT kernel)
+//   IDCT          one thread per 8x8 block in PLANE order (a warp stores 256 contiguous bytes per row): dequantise,
+//                 libjpeg "islow" integer IDCT in registers, saturate to u8
+//   colour        4 pixels per thread: fancy h2v2 / h2v1 chroma upsampling, YCbCr->RGB, optional fused cvtColor gray
+#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+namespace ibt {
+
+constexpr int JPG_S = 1024;              // subsequence length, bits
+constexpr int JPG_LUT_BITS = 9;
+constexpr int JPG_CHUNK = 4096;          // destuff: bytes per CTA (256 threads x 16)
+constexpr int JPG_MAX_BLK = 10;          // blocks per MCU (T.81 B.2.3)
+
+struct JpgTables {                       // kernel parameter (~9 KB): one (DC, AC) table pair per component
+    uint16_t lut[6][1 << JPG_LUT_BITS];  // [comp*2 + ac]: len << 8 | symbol; 0 = code longer than JPG_LUT_BITS
+    uint32_t limit[6][17];               // left-justified 16-bit value of the first code longer than l
+    int32_t valoff[6][17];               // vals index = valoff[l] + (w16 >> (16 - l))
+    uint8_t vals[6][256];
+    uint8_t blk_comp[12];
+    int nblk_mcu;
+};
+
+struct JpgGeom {
+    int ncomp, W, H;
+    int hs[3], vs[3], blkoff[3];
+    int mcux, mcuy, nblk_mcu;
+    int bw[3], bh[3];                    // blocks per plane row / column
+    int pw[3], ph[3];                    // plane size (samples, whole blocks)
+    int dw[3], dh[3];                    // real downsampled size
+    int hmax, vmax;
+    uint8_t *plane[3];
+    uint16_t quant[3][64];               // per component, natural order
+};
+
+__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// ---- CTA-wide exclusive scan of one value per thread (blockDim.x <= 1024, multiple of 32) -------------------------------
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t *total)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();                                       // warp_sums may still be read by a previous call
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    uint32_t ws = lane < nw ? warp_sums[lane] : 0u;
+    uint32_t wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+    }
+    const uint32_t wbase = __shfl_sync(0xffffffffu, wi - ws, w);
+    if (total) *total = __shfl_sync(0xffffffffu, wi, nw - 1);
+    return wbase + inc - v;
+}
+
+// ---- generic exclusive scan of `n` u32 values per row (gridDim.y rows, `stride` elements apart), tiles of 1024 --------------
+__global__ void __launch_bounds__(256) jpg_scan_reduce(const uint32_t *__restrict__ in, uint32_t *__restrict__ partial, int n,
+                                                       int64_t stride, int ptiles)
+{
+    const uint32_t *row = in + blockIdx.y * stride;
+    const int base = blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (base + j < n) s += row[base + j];
+    uint32_t tot;
+    cta_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) partial[blockIdx.y * ptiles + blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) jpg_scan_partials(uint32_t *__restrict__ partial, int ntiles, int ptiles)
+{
+    uint32_t *row = partial + blockIdx.x * ptiles;
+    uint32_t carry = 0;
+    for (int b = 0; b < ntiles; b += 1024) {
+        const int i = b + threadIdx.x;
+        const uint32_t v = i < ntiles ? row[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = cta_exclusive_scan(v, &tot);
+        if (i < ntiles) row[i] = carry + ex;
+        carry += tot;
+    }
+}
+__global__ void __launch_bounds__(256) jpg_scan_apply(const uint32_t *__restrict__ in, const uint32_t *__restrict__ partial,
+                                                      uint32_t *__restrict__ out, int n, int64_t stride, int ptiles)
+{
+    const uint32_t *row = in + blockIdx.y * stride;
+    uint32_t *orow = out + blockIdx.y * stride;
+    const int base = blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v[j] = base + j < n ? row[base + j] : 0u; s += v[j]; }
+    uint32_t ex = cta_exclusive_scan(s, nullptr) + partial[blockIdx.y * ptiles + blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (base + j < n) orow[base + j] = ex;
+        ex += v[j];
+    }
+}
+static int launch_scan(const uint32_t *in, uint32_t *out, uint32_t *partial, int n, int rows, int64_t stride, cudaStream_t st)
+{
+    if (n <= 0) return IBT_OK;
+    const int ntiles = (n + 1023) / 1024;
+    jpg_scan_reduce<<<dim3(ntiles, rows), 256, 0, st>>>(in, partial, n, stride, ntiles);
+    jpg_scan_partials<<<rows, 1024, 0, st>>>(partial, ntiles, ntiles);
+    jpg_scan_apply<<<dim3(ntiles, rows), 256, 0, st>>>(in, partial, out, n, stride, ntiles);
+    return check_launch("jpeg scan");
+}
+
+// ---- destuff ------------------------------------------------------------------------------------------------
+// byte j of the segment is dropped iff it is the 0x00 that follows a 0xFF
+__device__ __forceinline__ uint32_t destuff_keepmask(const uint8_t *__restrict__ src, int64_t n, int64_t j0, uint8_t *b)
+{
+    uint32_t keep = 0;
+    uint8_t prev = j0 > 0 && j0 <= n ? src[j0 - 1] : 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int64_t g = j0 + j;
+        const uint8_t c = g < n ? src[g] : 0;
+        b[j] = c;
+        if (g < n && !(c == 0x00 && prev == 0xFF)) keep |= 1u << j;
+        prev = c;
+    }
+    return keep;
+}
+__global__ void __launch_bounds__(256) jpg_destuff_count(const uint8_t *__restrict__ src, int64_t n, uint32_t *__restrict__ counts)
+{
+    uint8_t b[16];
+    const int64_t j0 = (int64_t)blockIdx.x * JPG_CHUNK + threadIdx.x * 16;
+    const uint32_t keep = destuff_keepmask(src, n, j0, b);
+    uint32_t tot;
+    cta_exclusive_scan(__popc(keep), &tot);
+    if (threadIdx.x == 0) counts[blockIdx.x] = tot;
+}
+// dst byte k lives at address k ^ 3: a 32-bit load then holds four stream bytes most-significant first
+__global__ void __launch_bounds__(256) jpg_destuff_write(const uint8_t *__restrict__ src, int64_t n, const uint32_t *__restrict__ offsets,
+                                                         uint8_t *__restrict__ dst, uint32_t *__restrict__ meta)
+{
+    uint8_t b[16];
+    const int64_t j0 = (int64_t)blockIdx.x * JPG_CHUNK + threadIdx.x * 16;
+    const uint32_t keep = destuff_keepmask(src, n, j0, b);
+    uint32_t tot;
+    uint32_t o = cta_exclusive_scan(__popc(keep), &tot) + offsets[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        if (keep >> j & 1u) { dst[o ^ 3u] = b[j]; o++; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) meta[0] = offsets[blockIdx.x] + tot;      // destuffed bytes
+}
+
+// ---- Huffman ---------------------------------------------------------------------------------------------------
+struct JpgSmemTables {
+    uint16_t lut[6][1 << JPG_LUT_BITS];
+    uint32_t limit[6][17];
+    int32_t valoff[6][17];
+    uint8_t vals[6][256];
+    uint8_t blk_comp[12];
+    uint8_t zigzag[64];
+};
+__device__ __forceinline__ void load_tables(JpgSmemTables &S, const JpgTables &T)
+{
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&T);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&S);
+    constexpr int nw = (int)(offsetof(JpgTables, nblk_mcu) / 4);
+    static_assert(offsetof(JpgTables, nblk_mcu) % 4 == 0, "layout");
+    static_assert(offsetof(JpgSmemTables, zigzag) == offsetof(JpgTables, nblk_mcu), "layout");
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 64) S.zigzag[threadIdx.x] = c_zigzag[threadIdx.x];
+    __syncthreads();
+}
+
+// Decode symbols from bit `pos` while pos < end.  State (pos, blk = block inside the MCU, k = next zig-zag index,
+// 0 = DC expected).  done counts completed blocks.  WRITE: coefficients go to coef[(base + done) * 64 + natural index].
+template <bool WRITE>
+__device__ __forceinline__ void huff_run(const uint32_t *__restrict__ words, const JpgSmemTables &S, int nblk_mcu, uint32_t &pos,
+                                         int &blk, int &k, uint32_t end, uint32_t &done, int16_t *__restrict__ coef, uint32_t base,
+                                         uint32_t nblocks)
+{
+    while (pos < end) {
+        const int tbl = S.blk_comp[blk] * 2 + (k > 0);
+        const uint32_t wi = pos >> 5;
+        const uint32_t win = __funnelshift_l(words[wi + 1], words[wi], pos & 31u);
+        const uint32_t e = S.lut[tbl][win >> (32 - JPG_LUT_BITS)];
+        int len, sym;
+        if (e) { len = (int)(e >> 8); sym = (int)(e & 255u); }
+        else {
+            const uint32_t w16 = win >> 16;
+            int l = JPG_LUT_BITS + 1;
+            while (l <= 16 && w16 >= S.limit[tbl][l]) l++;
+            if (l > 16) { len = 16; sym = 0; }                       // not a code (only a mis-synchronised decoder gets here)
+            else { len = l; sym = S.vals[tbl][(S.valoff[tbl][l] + (int)(w16 >> (16 - l))) & 255]; }
+        }
+        const int s = sym & 15;
+        int val = 0;
+        if (WRITE && s) {
+            const uint32_t r = (win << len) >> (32 - s);
+            val = r < (1u << (s - 1)) ? (int)r - (1 << s) + 1 : (int)r;
+        }
+        pos += (uint32_t)(len + s);
+        bool fin = false;
+        int widx = -1;
+        if (k == 0) { widx = 0; k = 1; }
+        else {
+            const int r = sym >> 4;
+            if (s) { k += r; if (k <= 63) widx = S.zigzag[k]; k++; fin = k > 63; }
+            else if (r == 15) { k += 16; fin = k > 63; }
+            else fin = true;
+        }
+        if (WRITE && widx >= 0) {
+            const uint32_t b = base + done;
+            if (b < nblocks) coef[(size_t)b * 64 + widx] = (int16_t)val;
+        }
+        if (fin) { k = 0; blk = blk + 1 == nblk_mcu ? 0 : blk + 1; done++; }
+    }
+}
+
+// entry state of subsequence i: pos | (blk * 64 + k) << 32
+__global__ void __launch_bounds__(256) jpg_sync_init(unsigned long long *__restrict__ start, uint8_t *__restrict__ dirty, int nsub)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsub) return;
+    start[i] = (unsigned long long)i * JPG_S;
+    dirty[i] = 1;
+    dirty[nsub + i] = 0;
+}
+// One round: threads whose entry state changed decode their subsequence and publish the exit state to their successor.
+__global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
+                                                      const __grid_constant__ JpgTables T, unsigned long long *__restrict__ start,
+                                                      uint8_t *__restrict__ dirty, uint32_t *__restrict__ nblk, int nsub, int round,
+                                                      uint32_t *__restrict__ changed_slot)
+{
+    __shared__ JpgSmemTables S;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t *din = dirty + (round & 1) * nsub, *dout = dirty + ((round + 1) & 1) * nsub;
+    // nothing to do in this CTA?  (the common case after the second round)
+    const bool mine = i < nsub && din[i];
+    if (!__syncthreads_or(mine)) return;
+    load_tables(S, T);
+    if (!mine) return;
+    din[i] = 0;
+    const unsigned long long total_bits = (unsigned long long)meta[0] * 8ull;
+    const unsigned long long lo = (unsigned long long)i * JPG_S;
+    if (lo >= total_bits) { nblk[i] = 0; return; }
+    const unsigned long long hi = lo + JPG_S < total_bits ? lo + JPG_S : total_bits;
+    const unsigned long long st = start[i];
+    uint32_t pos = (uint32_t)st;
+    int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
+    uint32_t done = 0;
+    huff_run<false>(words, S, T.nblk_mcu, pos, blk, k, (uint32_t)hi, done, nullptr, 0, 0);
+    nblk[i] = done;
+    if (i + 1 < nsub && hi < total_bits) {
+        const unsigned long long out = (unsigned long long)pos | ((unsigned long long)(blk * 64 + k) << 32);
+        if (start[i + 1] != out) {
+            start[i + 1] = out;
+            dout[i + 1] = 1;
+            atomicAdd(changed_slot, 1u);
+        }
+    }
+}
+__global__ void __launch_bounds__(128) jpg_huff_write(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
+                                                      const __grid_constant__ JpgTables T, const unsigned long long *__restrict__ start,
+                                                      const uint32_t *__restrict__ base, int16_t *__restrict__ coef, int nsub,
+                                                      uint32_t nblocks)
+{
+    __shared__ JpgSmemTables S;
+    load_tables(S, T);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsub) return;
+    const unsigned long long total_bits = (unsigned long long)meta[0] * 8ull;
+    const unsigned long long lo = (unsigned long long)i * JPG_S;
+    if (lo >= total_bits) return;
+    const unsigned long long hi = lo + JPG_S < total_bits ? lo + JPG_S : total_bits;
+    const unsigned long long st = start[i];
+    uint32_t pos = (uint32_t)st;
+    int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
+    uint32_t done = 0;
+    huff_run<true>(words, S, T.nblk_mcu, pos, blk, k, (uint32_t)hi, done, coef, base[i], nblocks);
+}
+
+// ---- DC differences -> per-MCU sums per component (rows of dcs: [comp][nmcu]) ------------------------------------------------
+__global__ void __launch_bounds__(256) jpg_dc_sums(const int16_t *__restrict__ coef, const __grid_constant__ JpgGeom G,
+                                                   uint32_t *__restrict__ dcs, int nmcu)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmcu) return;
+    for (int c = 0; c < G.ncomp; c++) {
+        int s = 0;
+        const int nb = G.hs[c] * G.vs[c];
+        for (int j = 0; j < nb; j++) s += coef[((size_t)m * G.nblk_mcu + G.blkoff[c] + j) * 64];
+        dcs[(size_t)c * nmcu + m] = (uint32_t)s;
+    }
+}
+
+// ---- libjpeg "islow" inverse DCT (jidctint.c): 13-bit constants, PASS1_BITS = 2 ------------------------------------------------
+template <int SHIFT>
+__device__ __forceinline__ void idct8(int i0, int i1, int i2, int i3, int i4, int i5, int i6, int i7, int *o)
+{
+    int z2 = i2, z3 = i6;
+    int z1 = (z2 + z3) * 4433;
+    int tmp2 = z1 + z3 * (-15137);
+    int tmp3 = z1 + z2 * 6270;
+    int tmp0 = (i0 + i4) * 8192;
+    int tmp1 = (i0 - i4) * 8192;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = i7; tmp1 = i5; tmp2 = i3; tmp3 = i1;
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * 9633;
+    tmp0 *= 2446; tmp1 *= 16819; tmp2 *= 25172; tmp3 *= 12299;
+    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    constexpr int R = 1 << (SHIFT - 1);
+    o[0] = (tmp10 + tmp3 + R) >> SHIFT; o[7] = (tmp10 - tmp3 + R) >> SHIFT;
+    o[1] = (tmp11 + tmp2 + R) >> SHIFT; o[6] = (tmp11 - tmp2 + R) >> SHIFT;
+    o[2] = (tmp12 + tmp1 + R) >> SHIFT; o[5] = (tmp12 - tmp1 + R) >> SHIFT;
+    o[3] = (tmp13 + tmp0 + R) >> SHIFT; o[4] = (tmp13 - tmp0 + R) >> SHIFT;
+}
+__device__ __forceinline__ uint32_t sat_u8(int v) { return (uint32_t)min(max(v, 0), 255); }
+
+// one thread per block, blocks numbered in plane order per component (component 0 first)
+__global__ void __launch_bounds__(128) jpg_idct(const int16_t *__restrict__ coef, const uint32_t *__restrict__ dcpre,
+                                                const __grid_constant__ JpgGeom G, int nmcu, int total_blocks)
+{
+    __shared__ int sq[3][64];
+    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) sq[i / 64][i % 64] = G.quant[i / 64][i % 64];
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_blocks) return;
+    int c = 0;
+    while (c < G.ncomp - 1 && t >= G.bw[c] * G.bh[c]) { t -= G.bw[c] * G.bh[c]; c++; }
+    const int by = t / G.bw[c], bx = t - by * G.bw[c];
+    const int h = G.hs[c], v = G.vs[c];
+    const int m = (by / v) * G.mcux + bx / h;
+    const int jl = (by % v) * h + (bx % h);
+    const size_t b0 = (size_t)m * G.nblk_mcu + G.blkoff[c];
+    int dc = (int)dcpre[(size_t)c * nmcu + m];
+    for (int j = 0; j <= jl; j++) dc += coef[(b0 + j) * 64];
+    const uint4 *src = reinterpret_cast<const uint4 *>(coef + (b0 + jl) * 64);
+    int ws[64];
+    {
+        int in[64];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint4 q = __ldg(src + r);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                in[r * 8 + 2 * j] = (int)(short)(w[j] & 0xffffu) * sq[c][r * 8 + 2 * j];
+                in[r * 8 + 2 * j + 1] = ((int)w[j] >> 16) * sq[c][r * 8 + 2 * j + 1];
+            }
+        }
+        in[0] = dc * sq[c][0];
+#pragma unroll
+        for (int col = 0; col < 8; col++) {
+            int o[8];
+            idct8<11>(in[col], in[8 + col], in[16 + col], in[24 + col], in[32 + col], in[40 + col], in[48 + col], in[56 + col], o);
+#pragma unroll
+            for (int r = 0; r < 8; r++) ws[r * 8 + col] = o[r];
+        }
+    }
+    uint8_t *dst = G.plane[c] + (size_t)by * 8 * G.pw[c] + bx * 8;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int o[8];
+        idct8<18>(ws[r * 8], ws[r * 8 + 1], ws[r * 8 + 2], ws[r * 8 + 3], ws[r * 8 + 4], ws[r * 8 + 5], ws[r * 8 + 6], ws[r * 8 + 7], o);
+        uint2 px;
+        px.x = sat_u8(o[0] + 128) | sat_u8(o[1] + 128) << 8 | sat_u8(o[2] + 128) << 16 | sat_u8(o[3] + 128) << 24;
+        px.y = sat_u8(o[4] + 128) | sat_u8(o[5] + 128) << 8 | sat_u8(o[6] + 128) << 16 | sat_u8(o[7] + 128) << 24;
+        *reinterpret_cast<uint2 *>(dst + (size_t)r * G.pw[c]) = px;
+    }
+}
+
+// ---- chroma upsampling (jdsample.c "fancy") + YCbCr -> RGB (jdcolor.c) + optional cvtColor gray ---------------------------------
+// 4 chroma samples for pixels x0..x0+3 of row y
+__device__ __forceinline__ void chroma4(const JpgGeom &G, int c, int x0, int y, int *out)
+{
+    const uint8_t *P = G.plane[c];
+    const int pw = G.pw[c], dw = G.dw[c], dh = G.dh[c];
+    const int hsub = G.hmax / G.hs[c], vsub = G.vmax / G.vs[c];
+    if (hsub == 1) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(P + (size_t)y * pw + x0);
+        out[0] = w & 255; out[1] = (w >> 8) & 255; out[2] = (w >> 16) & 255; out[3] = w >> 24;
+        return;
+    }
+    const int cx = x0 >> 1;                               // x0 is a multiple of 4: columns cx-1 .. cx+2
+    const int xa = max(cx - 1, 0), xb = min(cx, dw - 1), xc = min(cx + 1, dw - 1), xd = min(cx + 2, dw - 1);
+    if (vsub == 1) {
+        const uint8_t *r = P + (size_t)y * pw;
+        const int a = r[xa], b = r[xb], cc = r[xc], d = r[xd];
+        if (dw <= 2) { out[0] = out[1] = b; out[2] = out[3] = cc; return; }
+        out[0] = (3 * b + a + 1) >> 2; out[1] = (3 * b + cc + 2) >> 2;
+        out[2] = (3 * cc + b + 1) >> 2; out[3] = (3 * cc + d + 2) >> 2;
+        return;
+    }
+    const int cy = y >> 1;
+    const uint8_t *r0 = P + (size_t)cy * pw;
+    if (dw <= 2) { out[0] = out[1] = r0[xb]; out[2] = out[3] = r0[xc]; return; }
+    const int fy = min(max((y & 1) ? cy + 1 : cy - 1, 0), dh - 1);
+    const uint8_t *r1 = P + (size_t)fy * pw;
+    const int a = 3 * r0[xa] + r1[xa], b = 3 * r0[xb] + r1[xb], cc = 3 * r0[xc] + r1[xc], d = 3 * r0[xd] + r1[xd];
+    out[0] = (3 * b + a + 8) >> 4; out[1] = (3 * b + cc + 7) >> 4;
+    out[2] = (3 * cc + b + 8) >> 4; out[3] = (3 * cc + d + 7) >> 4;
+}
+
+template <int SH>
+__global__ void __launch_bounds__(256) jpg_color(const __grid_constant__ JpgGeom G, uint8_t *__restrict__ rgb, int64_t rgb_pitch,
+                                                 uint8_t *__restrict__ gray, int64_t gray_pitch, int k0, int k1, int k2)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= G.W) return;
+    const uint32_t yw = *reinterpret_cast<const uint32_t *>(G.plane[0] + (size_t)y * G.pw[0] + x0);
+    uint32_t R[4], Gc[4], B[4], g[4];
+    if (G.ncomp == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) g[j] = (yw >> (8 * j)) & 255u;
+    } else {
+        int cb[4], cr[4];
+        chroma4(G, 1, x0, y, cb);
+        chroma4(G, 2, x0, y, cr);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int Y = (int)((yw >> (8 * j)) & 255u), b = cb[j] - 128, r = cr[j] - 128;
+            R[j] = sat_u8(Y + ((91881 * r + 32768) >> 16));
+            Gc[j] = sat_u8(Y + ((-22554 * b + 32768 - 46802 * r) >> 16));
+            B[j] = sat_u8(Y + ((116130 * b + 32768) >> 16));
+            g[j] = (R[j] * k0 + Gc[j] * k1 + B[j] * k2 + (1u << (SH - 1))) >> SH;      // channel 0 takes the "B" weight (s1:311)
+        }
+    }
+    const bool full = x0 + 4 <= G.W;
+    if (gray) {
+        uint8_t *d = gray + (size_t)y * gray_pitch + x0;
+        if (full && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) *reinterpret_cast<uint32_t *>(d) = g[0] | g[1] << 8 | g[2] << 16 | g[3] << 24;
+        else for (int j = 0; j < 4 && x0 + j < G.W; j++) d[j] = (uint8_t)g[j];
+    }
+    if (rgb && G.ncomp == 3) {
+        uint8_t *d = rgb + (size_t)y * rgb_pitch + (size_t)x0 * 3;
+        if (full && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+            uint32_t *w = reinterpret_cast<uint32_t *>(d);
+            w[0] = R[0] | Gc[0] << 8 | B[0] << 16 | R[1] << 24;
+            w[1] = Gc[1] | B[1] << 8 | R[2] << 16 | Gc[2] << 24;
+            w[2] = B[2] | R[3] << 8 | Gc[3] << 16 | B[3] << 24;
+        } else {
+            for (int j = 0; j < 4 && x0 + j < G.W; j++) { d[3 * j] = (uint8_t)R[j]; d[3 * j + 1] = (uint8_t)Gc[j]; d[3 * j + 2] = (uint8_t)B[j]; }
+        }
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------
+static const uint8_t h_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+static int jpeg_validate(const ibt_jpeg_info_t *I)
+{
+    if (!I || I->width <= 0 || I->height <= 0 || I->width > 65535 || I->height > 65535) return IBT_E_INVALID;
+    if (I->ncomp != 1 && I->ncomp != 3) return IBT_E_UNSUPPORTED;
+    if (I->restart_interval != 0) return IBT_E_UNSUPPORTED;
+    if (I->scan_bytes <= 0 || I->scan_offset < 0 || I->scan_bytes > 0x1fffffff) return IBT_E_INVALID;
+    for (int c = 0; c < I->ncomp; c++) {
+        if (I->hsamp[c] < 1 || I->vsamp[c] < 1 || I->qsel[c] < 0 || I->qsel[c] > 3 || I->dcsel[c] < 0 || I->dcsel[c] > 3 ||
+            I->acsel[c] < 0 || I->acsel[c] > 3)
+            return IBT_E_INVALID;
+    }
+    if (I->ncomp == 3) {
+        if (I->hsamp[1] != 1 || I->vsamp[1] != 1 || I->hsamp[2] != 1 || I->vsamp[2] != 1) return IBT_E_UNSUPPORTED;
+        const int h = I->hsamp[0], v = I->vsamp[0];
+        if (!((h == 1 && v == 1) || (h == 2 && v == 1) || (h == 2 && v == 2))) return IBT_E_UNSUPPORTED;
+    }
+    return IBT_OK;
+}
+
+struct JpgLayout {
+    JpgGeom G;
+    int nmcu, nblocks, nsub, nchunks;
+    size_t off_stream, off_counts, off_offsets, off_meta, off_changed, off_start, off_dirty, off_nblk, off_base, off_partial,
+        off_coef, off_dcs, off_dcpre, off_plane[3], total;
+    size_t stream_bytes, coef_bytes;
+};
+constexpr int JPG_MAX_ROUNDS_BATCH = 64;
+
+static void jpeg_layout(const ibt_jpeg_info_t *I, JpgLayout &L)
+{
+    memset(&L, 0, sizeof(L));
+    JpgGeom &G = L.G;
+    G.ncomp = I->ncomp; G.W = I->width; G.H = I->height;
+    G.hmax = G.vmax = 1;
+    for (int c = 0; c < I->ncomp; c++) {
+        G.hs[c] = I->ncomp == 1 ? 1 : I->hsamp[c];
+        G.vs[c] = I->ncomp == 1 ? 1 : I->vsamp[c];
+        if (G.hs[c] > G.hmax) G.hmax = G.hs[c];
+        if (G.vs[c] > G.vmax) G.vmax = G.vs[c];
+    }
+    G.mcux = (G.W + 8 * G.hmax - 1) / (8 * G.hmax);
+    G.mcuy = (G.H + 8 * G.vmax - 1) / (8 * G.vmax);
+    int off = 0;
+    for (int c = 0; c < I->ncomp; c++) {
+        G.blkoff[c] = off;
+        off += G.hs[c] * G.vs[c];
+        G.bw[c] = G.mcux * G.hs[c]; G.bh[c] = G.mcuy * G.vs[c];
+        G.pw[c] = G.bw[c] * 8; G.ph[c] = G.bh[c] * 8;
+        G.dw[c] = (G.W * G.hs[c] + G.hmax - 1) / G.hmax;
+        G.dh[c] = (G.H * G.vs[c] + G.vmax - 1) / G.vmax;
+        for (int i = 0; i < 64; i++) G.quant[c][i] = I->quant[I->qsel[c]][i];
+    }
+    G.nblk_mcu = off;
+    L.nmcu = G.mcux * G.mcuy;
+    L.nblocks = L.nmcu * G.nblk_mcu;
+    L.nsub = (int)((I->scan_bytes * 8 + JPG_S - 1) / JPG_S);
+    L.nchunks = (int)((I->scan_bytes + JPG_CHUNK - 1) / JPG_CHUNK);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    L.stream_bytes = ((size_t)I->scan_bytes + 64 + 3) & ~(size_t)3;
+    L.off_stream = take(L.stream_bytes);
+    L.off_counts = take((size_t)L.nchunks * 4);
+    L.off_offsets = take((size_t)L.nchunks * 4);
+    L.off_meta = take(64);
+    L.off_changed = take(JPG_MAX_ROUNDS_BATCH * 4);
+    L.off_start = take((size_t)L.nsub * 8);
+    L.off_dirty = take((size_t)L.nsub * 2);
+    L.off_nblk = take((size_t)L.nsub * 4);
+    L.off_base = take((size_t)L.nsub * 4);
+    const size_t np1 = (size_t)(L.nsub + 1023) / 1024 + 1, np2 = 3 * ((size_t)(L.nmcu + 1023) / 1024 + 1), np3 = (size_t)(L.nchunks + 1023) / 1024 + 1;
+    L.off_partial = take((np1 > np2 ? (np1 > np3 ? np1 : np3) : (np2 > np3 ? np2 : np3)) * 4);
+    L.coef_bytes = (size_t)L.nblocks * 64 * 2;
+    L.off_coef = take(L.coef_bytes);
+    L.off_dcs = take((size_t)3 * L.nmcu * 4);
+    L.off_dcpre = take((size_t)3 * L.nmcu * 4);
+    for (int c = 0; c < I->ncomp; c++) L.off_plane[c] = take((size_t)G.pw[c] * G.ph[c]);
+    L.total = o;
+}
+
+static int build_tables(const ibt_jpeg_info_t *I, const JpgGeom &G, JpgTables &T)
+{
+    memset(&T, 0, sizeof(T));
+    for (int c = 0; c < I->ncomp; c++)
+        for (int ac = 0; ac < 2; ac++) {
+            const uint8_t *bits = ac ? I->ac_bits[I->acsel[c]] : I->dc_bits[I->dcsel[c]];
+            const uint8_t *vals = ac ? I->ac_vals[I->acsel[c]] : I->dc_vals[I->dcsel[c]];
+            const int t = c * 2 + ac, nvals_max = ac ? 256 : 16;
+            int code = 0, k = 0;
+            for (int l = 1; l <= 16; l++) {
+                const int n = bits[l - 1];
+                if (k + n > nvals_max || code + n > (1 << l)) return IBT_E_INVALID;
+                T.valoff[t][l] = k - code;
+                for (int i = 0; i < n; i++, code++, k++) {
+                    T.vals[t][k] = vals[k];
+                    if (l <= JPG_LUT_BITS) {
+                        const int lo = code << (JPG_LUT_BITS - l), cnt = 1 << (JPG_LUT_BITS - l);
+                        for (int j = 0; j < cnt; j++) T.lut[t][lo + j] = (uint16_t)((l << 8) | vals[k]);
+                    }
+                }
+                T.limit[t][l] = (uint32_t)code << (16 - l);
+                code <<= 1;
+            }
+            if (k == 0) return IBT_E_INVALID;
+        }
+    T.nblk_mcu = G.nblk_mcu;
+    for (int c = 0; c < I->ncomp; c++)
+        for (int j = 0; j < G.hs[c] * G.vs[c]; j++) T.blk_comp[G.blkoff[c] + j] = (uint8_t)c;
+    return IBT_OK;
+}
+
+} // namespace ibt
+
+// ---- HOST: marker parsing (ITU-T T.81 Annex B) ------------------------------------------------------------------------------
+IBT_API int ibt_jpeg_parse(const uint8_t *d, int64_t n, ibt_jpeg_info_t *I)
+{
+    if (!d || !I || n < 4) return IBT_E_INVALID;
+    memset(I, 0, sizeof(*I));
+    if (d[0] != 0xFF || d[1] != 0xD8) return IBT_E_INVALID;
+    int64_t p = 2;
+    int comp_id[3] = {0, 0, 0};
+    bool have_sof = false, have_q[4] = {false, false, false, false}, have_dc[4] = {false, false, false, false},
+         have_ac[4] = {false, false, false, false};
+    for (;;) {
+        if (p + 4 > n || d[p] != 0xFF) return IBT_E_INVALID;
+        while (p < n && d[p] == 0xFF) p++;
+        if (p >= n) return IBT_E_INVALID;
+        const int m = d[p++];
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+        if (m == 0xD9 || p + 2 > n) return IBT_E_INVALID;
+        const int len = (d[p] << 8) | d[p + 1];
+        if (len < 2 || p + len > n) return IBT_E_INVALID;
+        const uint8_t *s = d + p + 2;
+        const int sl = len - 2;
+        if (m == 0xC0 || m == 0xC1) {
+            if (sl < 6) return IBT_E_INVALID;
+            if (s[0] != 8) return IBT_E_UNSUPPORTED;
+            I->height = (s[1] << 8) | s[2];
+            I->width = (s[3] << 8) | s[4];
+            I->ncomp = s[5];
+            if (I->ncomp != 1 && I->ncomp != 3) return IBT_E_UNSUPPORTED;
+            if (sl < 6 + 3 * I->ncomp) return IBT_E_INVALID;
+            for (int i = 0; i < I->ncomp; i++) {
+                comp_id[i] = s[6 + 3 * i];
+                I->hsamp[i] = s[7 + 3 * i] >> 4;
+                I->vsamp[i] = s[7 + 3 * i] & 15;
+                I->qsel[i] = s[8 + 3 * i] & 3;
+            }
+            have_sof = true;
+        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return IBT_E_UNSUPPORTED;                       // progressive, lossless, arithmetic, differential
+        } else if (m == 0xC4) {
+            int o = 0;
+            while (o < sl) {
+                if (o + 17 > sl) return IBT_E_INVALID;
+                const int tc = s[o] >> 4, th = s[o] & 15;
+                if (tc > 1 || th > 3) return IBT_E_INVALID;
+                int cnt = 0;
+                for (int l = 0; l < 16; l++) cnt += s[o + 1 + l];
+                if (cnt > (tc ? 256 : 16) || o + 17 + cnt > sl) return IBT_E_INVALID;
+                uint8_t *bits = tc ? I->ac_bits[th] : I->dc_bits[th];
+                uint8_t *vals = tc ? I->ac_vals[th] : I->dc_vals[th];
+                memcpy(bits, s + o + 1, 16);
+                memset(vals, 0, tc ? 256 : 16);
+                memcpy(vals, s + o + 17, cnt);
+                (tc ? have_ac : have_dc)[th] = true;
+                o += 17 + cnt;
+            }
+        } else if (m == 0xDB) {
+            int o = 0;
+            while (o < sl) {
+                const int pq = s[o] >> 4, tq = s[o] & 15;
+                if (tq > 3 || pq > 1) return IBT_E_INVALID;
+                o++;
+                if (o + 64 * (pq + 1) > sl) return IBT_E_INVALID;
+                for (int i = 0; i < 64; i++) {
+                    I->quant[tq][ibt::h_zigzag[i]] = (uint16_t)(pq ? ((s[o] << 8) | s[o + 1]) : s[o]);
+                    o += pq + 1;
+                }
+                have_q[tq] = true;
+            }
+        } else if (m == 0xDD) {
+            if (sl < 2) return IBT_E_INVALID;
+            I->restart_interval = (s[0] << 8) | s[1];
+        } else if (m == 0xDA) {
+            if (!have_sof || sl < 1) return IBT_E_INVALID;
+            const int ns = s[0];
+            if (ns != I->ncomp) return IBT_E_UNSUPPORTED;   // one interleaved scan only
+            if (sl < 1 + 2 * ns + 3) return IBT_E_INVALID;
+            for (int i = 0; i < ns; i++) {
+                if (s[1 + 2 * i] != comp_id[i]) return IBT_E_UNSUPPORTED;
+                I->dcsel[i] = s[2 + 2 * i] >> 4;
+                I->acsel[i] = s[2 + 2 * i] & 15;
+                if (I->dcsel[i] > 3 || I->acsel[i] > 3) return IBT_E_INVALID;
+            }
+            p += len;
+            break;
+        }
+        p += len;
+    }
+    for (int i = 0; i < I->ncomp; i++)
+        if (!have_q[I->qsel[i]] || !have_dc[I->dcsel[i]] || !have_ac[I->acsel[i]]) return IBT_E_INVALID;
+    // the entropy-coded segment ends at the first marker that is neither stuffing (FF 00) nor RSTn
+    I->scan_offset = p;
+    int64_t q = p;
+    for (;;) {
+        const uint8_t *f = q < n ? static_cast<const uint8_t *>(memchr(d + q, 0xFF, (size_t)(n - q))) : nullptr;
+        if (!f) { q = n; break; }
+        q = f - d;
+        if (q + 1 >= n) { q = n; break; }
+        const int nx = d[q + 1];
+        if (nx == 0x00 || (nx >= 0xD0 && nx <= 0xD7)) { q += 2; continue; }
+        if (nx == 0xFF) { q += 1; continue; }
+        break;
+    }
+    I->scan_bytes = q - p;
+    if (I->scan_bytes <= 0) return IBT_E_INVALID;
+    return ibt::jpeg_validate(I);
+}
+
+IBT_API int64_t ibt_jpeg_workspace_bytes(const ibt_jpeg_info_t *I)
+{
+    if (ibt::jpeg_validate(I) != IBT_OK) return 0;
+    ibt::JpgLayout L;
+    ibt::jpeg_layout(I, L);
+    return (int64_t)L.total;
+}
+
+IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, void *d_ws, int64_t ws_bytes, uint8_t *d_rgb,
+                            int64_t rgb_pitch, uint8_t *d_gray, int64_t gray_pitch, int coeffset, int *out_rounds, void *stream)
+{
+    using namespace ibt;
+    int rc = jpeg_validate(I);
+    if (rc) return rc;
+    if (!d_file || !d_ws || (!d_rgb && !d_gray)) return IBT_E_INVALID;
+    if (d_rgb && (I->ncomp != 3 || rgb_pitch < (int64_t)I->width * 3)) return IBT_E_INVALID;
+    if (d_gray && gray_pitch < I->width) return IBT_E_INVALID;
+    if (coeffset != IBT_GRAY_CV4_15BIT && coeffset != IBT_GRAY_CV3_14BIT) return IBT_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(d_ws) % 256 != 0) return IBT_E_INVALID;
+    static thread_local JpgLayout L;                        // ~1 KB of geometry, reused as a kernel parameter below
+    jpeg_layout(I, L);
+    if ((size_t)ws_bytes < L.total) return IBT_E_WORKSPACE;
+    static thread_local JpgTables T;
+    rc = build_tables(I, L.G, T);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t *ws = static_cast<uint8_t *>(d_ws);
+    uint8_t *sbytes = ws + L.off_stream;
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(sbytes);
+    uint32_t *counts = reinterpret_cast<uint32_t *>(ws + L.off_counts), *offsets = reinterpret_cast<uint32_t *>(ws + L.off_offsets);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_meta), *changed = reinterpret_cast<uint32_t *>(ws + L.off_changed);
+    unsigned long long *start = reinterpret_cast<unsigned long long *>(ws + L.off_start);
+    uint8_t *dirty = ws + L.off_dirty;
+    uint32_t *nblk = reinterpret_cast<uint32_t *>(ws + L.off_nblk), *base = reinterpret_cast<uint32_t *>(ws + L.off_base);
+    uint32_t *partial = reinterpret_cast<uint32_t *>(ws + L.off_partial);
+    int16_t *coef = reinterpret_cast<int16_t *>(ws + L.off_coef);
+    uint32_t *dcs = reinterpret_cast<uint32_t *>(ws + L.off_dcs), *dcpre = reinterpret_cast<uint32_t *>(ws + L.off_dcpre);
+    for (int c = 0; c < I->ncomp; c++) L.G.plane[c] = ws + L.off_plane[c];
+    const uint8_t *scan = d_file + I->scan_offset;
+
+    // 1. destuff
+    IBT_CUDA_TRY(cudaMemsetAsync(sbytes, 0, L.stream_bytes, st));
+    IBT_CUDA_TRY(cudaMemsetAsync(coef, 0, L.coef_bytes, st));
+    jpg_destuff_count<<<L.nchunks, 256, 0, st>>>(scan, I->scan_bytes, counts);
+    rc = launch_scan(counts, offsets, partial, L.nchunks, 1, 0, st);
+    if (rc) return rc;
+    jpg_destuff_write<<<L.nchunks, 256, 0, st>>>(scan, I->scan_bytes, offsets, sbytes, meta);
+
+    // 2. synchronisation rounds; the host reads the per-round change counters once per batch
+    static thread_local uint32_t *h_flag = nullptr;
+    if (!h_flag) IBT_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_flag), JPG_MAX_ROUNDS_BATCH * 4, cudaHostAllocDefault));
+    jpg_sync_init<<<(L.nsub + 255) / 256, 256, 0, st>>>(start, dirty, L.nsub);
+    const int sync_ctas = (L.nsub + 127) / 128;
+    int round = 0, batch = 8, rounds_used = -1;
+    while (rounds_used < 0) {
+        IBT_CUDA_TRY(cudaMemsetAsync(changed, 0, JPG_MAX_ROUNDS_BATCH * 4, st));
+        for (int r = 0; r < batch; r++)
+            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, T, start, dirty, nblk, L.nsub, round + r, changed + r);
+        IBT_CUDA_TRY(cudaMemcpyAsync(h_flag, changed, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+        IBT_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int r = 0; r < batch; r++)
+            if (h_flag[r] == 0) { rounds_used = round + r + 1; break; }     // a round without changes: fixed point reached
+        round += batch;
+        if (round > L.nsub + 8) break;                                     // cannot happen: one subsequence settles per round
+        batch = batch * 2 > JPG_MAX_ROUNDS_BATCH ? JPG_MAX_ROUNDS_BATCH : batch * 2;
+    }
+    rc = check_launch("jpeg sync");
+    if (rc) return rc;
+    if (rounds_used < 0) return IBT_E_INVALID;
+    if (out_rounds) *out_rounds = rounds_used;
+
+    // 3. output block of every subsequence, coefficient pass
+    rc = launch_scan(nblk, base, partial, L.nsub, 1, 0, st);
+    if (rc) return rc;
+    jpg_huff_write<<<sync_ctas, 128, 0, st>>>(words, meta, T, start, base, coef, L.nsub, (uint32_t)L.nblocks);
+
+    // 4. DC prediction: prefix sums over MCUs per component
+    jpg_dc_sums<<<(L.nmcu + 255) / 256, 256, 0, st>>>(coef, L.G, dcs, L.nmcu);
+    rc = launch_scan(dcs, dcpre, partial, L.nmcu, I->ncomp, L.nmcu, st);
+    if (rc) return rc;
+
+    // 5. inverse DCT into the component planes, 6. upsampling + colour conversion (+ gray)
+    jpg_idct<<<(L.nblocks + 127) / 128, 128, 0, st>>>(coef, dcpre, L.G, L.nmcu, L.nblocks);
+    const dim3 cgrid((unsigned)((I->width + 4 * 256 - 1) / (4 * 256)), (unsigned)I->height);
+    if (coeffset == IBT_GRAY_CV4_15BIT)
+        jpg_color<15><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, 3735, 19235, 9798);
+    else
+        jpg_color<14><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, 1868, 9617, 4899);
+    return check_launch("ibt_jpeg_decode");
+}

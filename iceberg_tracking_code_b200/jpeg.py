@@ -1,0 +1,111 @@
+"""`np.array(Image.open(image))` on the GPU (s1_lucaskanade_tracking.py:310, s0_1_test_lucaskanade_tracking.py:79).
+
+The reference decodes every time-lapse frame with Pillow (libjpeg-turbo, ~0.25 s per 24 MP frame on one core) and
+hands the (H,W,3) RGB array to cv2.cvtColor.  Here the compressed file goes to the GPU as it is (a few MB instead of
+72 MB of pixels) and `ibt_jpeg_decode` (csrc/jpeg.cu) produces the same RGB array bit for bit -- and, fused, the gray
+plane cv2.cvtColor would make of it, which is all the tracker consumes.
+
+    imread(path_or_bytes)                 -> (H,W,3) u8 RGB CUDA tensor   == np.array(Image.open(path))
+    imread(path_or_bytes, gray=True)      -> (H,W) u8 CUDA tensor         == cv2.cvtColor(that, cv2.COLOR_BGR2GRAY)
+    JpegDecoder                           reusable pinned staging + device workspace (steady state allocates nothing)
+
+Files the kernels do not handle (progressive, restart markers, CMYK, 12-bit ...) raise `Unsupported`;
+`tracking.load_image` is the caller's way out (Pillow on the host, pixels uploaded) -- the compute path itself has no
+CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import cv
+
+
+class Unsupported(ValueError):
+    """A valid JPEG this decoder does not handle (IBT_E_UNSUPPORTED)."""
+
+
+def parse(data):
+    """Marker parsing on the host (ibt_jpeg_parse).  data: bytes-like.  Returns the filled ibt_jpeg_info_t."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    info = N.ibt_jpeg_info_t()
+    rc = N.lib().ibt_jpeg_parse(C.c_void_p(buf.ctypes.data), buf.size, C.byref(info))
+    if rc == N.IBT_E_UNSUPPORTED:
+        raise Unsupported("JPEG variant not handled on the GPU (progressive / restart markers / sampling / components)")
+    N.check(rc, "ibt_jpeg_parse")
+    return info
+
+
+class JpegDecoder:
+    """One per (GPU, decoding thread).  decode() is asynchronous on the current stream up to the convergence check of
+    the speculative Huffman pass (one small host read per file)."""
+
+    def __init__(self, device=None):
+        self.device = cv._device() if device is None else torch.device(device)
+        self._pinned = [None, None]
+        self._k = 0
+        self._dev_file = None
+        self._ws = None
+        self.last_rounds = 0
+
+    def _stage(self, buf):
+        """file bytes -> device (through a pinned double buffer)."""
+        n = buf.size
+        k = self._k
+        self._k ^= 1
+        slot = self._pinned[k]
+        if slot is None or slot[0].numel() < n:
+            slot = (torch.empty((max(n, 1 << 20) * 5 // 4,), dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+            self._pinned[k] = slot
+        host, ev = slot
+        ev.synchronize()
+        host[:n].numpy()[:] = buf
+        if self._dev_file is None or self._dev_file.numel() < n:
+            self._dev_file = torch.empty((max(n, 1 << 20) * 5 // 4,), dtype=torch.uint8, device=self.device)
+        self._dev_file[:n].copy_(host[:n], non_blocking=True)
+        ev.record(torch.cuda.current_stream())
+        return self._dev_file
+
+    def decode(self, data, rgb=True, gray=False, coeffset=0):
+        """data: bytes-like holding a JPEG file.  Returns (rgb, gray) CUDA tensors (None where not requested)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        info = parse(buf)
+        H, W = info.height, info.width
+        if info.ncomp == 1:
+            rgb, gray = False, True                       # mode "L": np.array(Image.open(f)) is already (H,W)
+        need = N.lib().ibt_jpeg_workspace_bytes(C.byref(info))
+        if need <= 0:
+            raise Unsupported("JPEG variant not handled on the GPU")
+        with torch.cuda.device(self.device):
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty((int(need * 1.1) + 256,), dtype=torch.uint8, device=self.device)
+            dfile = self._stage(buf)
+            out_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=self.device) if rgb else None
+            out_gray = torch.empty((H, W), dtype=torch.uint8, device=self.device) if gray else None
+            rounds = C.c_int(0)
+            N.check(N.lib().ibt_jpeg_decode(cv._ptr(dfile), C.byref(info), cv._ptr(self._ws), self._ws.numel(),
+                                            cv._ptr(out_rgb), W * 3, cv._ptr(out_gray), W, int(coeffset),
+                                            C.byref(rounds), cv._stream()), "ibt_jpeg_decode")
+            self.last_rounds = rounds.value
+        return out_rgb, out_gray
+
+
+_default = {}
+
+
+def _decoder(device=None):
+    dev = cv._device() if device is None else torch.device(device)
+    if dev not in _default:
+        _default[dev] = JpegDecoder(dev)
+    return _default[dev]
+
+
+def imread(src, gray=False, device=None, coeffset=0):
+    """src: path or bytes.  gray=False: (H,W,3) RGB like np.array(Image.open(src)); gray=True: the (H,W) plane
+    cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) makes of it (s1:310-311)."""
+    if not isinstance(src, (bytes, bytearray, memoryview, np.ndarray)):
+        with open(str(src), "rb") as f:
+            src = f.read()
+    r, g = _decoder(device).decode(src, rgb=not gray, gray=gray, coeffset=coeffset)
+    return g if (gray or r is None) else r

@@ -38,6 +38,12 @@ def load_image(path):
     return np.array(Image.open(path))
 
 
+def read_file(path):
+    """The compressed frame as it lies on disk (the GPU decodes it: jpeg.py)."""
+    with open(str(path), "rb") as f:
+        return f.read()
+
+
 class FrameStager:
     """Pinned double buffer + copy stream: the host->device copy of frame t+1 overlaps the kernels of frame t."""
 
@@ -203,10 +209,22 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
     first_group / n_groups select a contiguous block of groups (time-block sharding): group g of start s
     covers frames s+g*T .. s+(g+1)*T; a block needs one halo frame shared with the next block.
 
-    decode_workers: the loader (PIL JPEG decode, ~0.25 s per 24 MP frame, far slower than the GPU step) runs in a thread
-    pool that keeps `decode_workers` frames decoded ahead of the tracker; the order of processing is unchanged."""
+    loader: callable path -> (H,W,3) u8 RGB host array (default: Pillow, as the reference, s1:310), None for in-memory
+    frames, or the string "gpu": the file bytes go to the GPU compressed and csrc/jpeg.cu decodes them (bit-exact with
+    Pillow) straight into the gray plane; files it does not handle raise jpeg.Unsupported.
+
+    decode_workers: the loader (PIL JPEG decode, ~0.25 s per 24 MP frame, far slower than the GPU step; or the file
+    read of the "gpu" loader) runs in a thread pool that keeps `decode_workers` frames ahead of the tracker; the order
+    of processing is unchanged."""
     T = int(track_len)
     trk = tracker or SequenceTracker(feature_params, lk_params)
+    gpu_dec = None
+    if isinstance(loader, str):
+        if loader != "gpu":
+            raise ValueError("loader must be a callable, None or 'gpu'")
+        from . import jpeg as _jpeg
+        gpu_dec = _jpeg.JpegDecoder(trk.device)
+        loader = read_file
     if mask is not None:
         mask = cv._to_dev(mask, np.uint8, "mask")
     results = []
@@ -235,6 +253,8 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
                 decoded = pending.pop(counter).result()
             else:
                 decoded = loader(item) if loader is not None else item
+            if gpu_dec is not None:
+                decoded = gpu_dec.decode(decoded, rgb=False, gray=True)[1]       # s1:310-311 in one pass
             cur = trk.prepare(decoded)
             if prev is not None and trk.n > 0:
                 trk.track(prev, cur)
@@ -277,21 +297,25 @@ def lucaskanade_tracking(file_path, ws_source, ws_target, camname, track_len, tr
         os.makedirs(ws_target)
     cam.crop_image_parallel(imagelist, ws_target, n_proc)              # s1:272
     imagelist = sorted(glob.glob(ws_target + '/*.jpg'))                # s1:278
-    first = load_image(imagelist[0])
-    h, w = first.shape[:2]
+    from . import jpeg as _jpeg
+    info = _jpeg.parse(read_file(imagelist[0]))
+    h, w = info.height, info.width
     if mask_switch == 1:                                               # s1:285-294
         mask = cam.mask_image(h, w)
     else:
         mask = np.full((h, w), 255, np.uint8)
-    track_sequence(imagelist, mask, track_len, track_len_sec, startlist)
+    # the cropping step above re-saved every frame with Pillow (baseline JPEG): the GPU decoder handles all of them
+    track_sequence(imagelist, mask, track_len, track_len_sec, startlist, loader="gpu")
 
 
 class LucasKanade:
     """s0_1_test_lucaskanade_tracking.py:29-181 without the plots: same constructor, same printed track counts,
     `self.tracks` ends up as the same list of lists of (x, y) vertices."""
 
-    def __init__(self, workspace, detect_interval, time_spacing):
+    def __init__(self, workspace, detect_interval, time_spacing, loader="gpu"):
+        """loader: "gpu" (frames decoded by csrc/jpeg.cu) or a callable path -> RGB array such as load_image (Pillow)."""
         from pathlib import Path
+        self.loader = loader
         workspace = Path(workspace)
         self.detect_interval = detect_interval
         self.time_spacing = time_spacing
@@ -309,8 +333,15 @@ class LucasKanade:
     def run(self):
         trk = SequenceTracker(self.feature_params, self.lk_params, fb_threshold=self.distthreshold)
         prev = None
+        dec = None
+        if self.loader == "gpu":
+            from . import jpeg as _jpeg
+            dec = _jpeg.JpegDecoder(trk.device)
         for counter, image in enumerate(self.imagelist):
-            cur = trk.prepare(load_image(image))
+            if dec is not None:
+                cur = trk.prepare(dec.decode(read_file(image), rgb=False, gray=True)[1])
+            else:
+                cur = trk.prepare(self.loader(image))
             if prev is not None and trk.n > 0:
                 trk.track(prev, cur)
             if counter % self.detect_interval == 0:

@@ -33,6 +33,7 @@ extern "C" {
 #define IBT_E_CUDA (-2)           /* a CUDA runtime call / kernel launch failed */
 #define IBT_E_WORKSPACE (-3)      /* workspace too small */
 #define IBT_E_CAPACITY (-4)       /* output capacity too small (count is still reported) */
+#define IBT_E_UNSUPPORTED (-5)    /* valid input this library does not handle (e.g. progressive JPEG) */
 
 /* flags of ibt_lk / ibt_lk_fb: same values as cv2.OPTFLOW_* */
 #define IBT_LK_USE_INITIAL_FLOW 4
@@ -159,6 +160,37 @@ int ibt_track_velocities(const float *tracks, int M, int T, const double *cam, d
  *      out[y*pitch + x] = inside ? inside_value : 0. */
 int ibt_polygon_mask(const double *poly_xy, int E, int H, int W, uint8_t *out, int64_t pitch, int inside_value,
                      void *stream);
+
+/* ---- K5: frame = np.array(Image.open(image))  s1_lucaskanade_tracking.py:310; s0_1_test_lucaskanade_tracking.py:79
+ *      (+ the cv2.cvtColor of s1:311 / s0_1:80 fused): baseline JPEG decoding on the GPU, bit-exact with Pillow's
+ *      libjpeg-turbo defaults (islow IDCT, fancy upsampling, fixed-point YCbCr->RGB).
+ *      Handled: baseline / extended sequential 8-bit Huffman (SOF0, SOF1), one interleaved scan, grey-scale or YCbCr with
+ *      4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling, no restart markers.  Anything else -> IBT_E_UNSUPPORTED
+ *      (callers fall back to their own decoder and upload the pixels). */
+typedef struct ibt_jpeg_info {
+    int32_t width, height, ncomp;                 /* ncomp 1 (grey) or 3 (YCbCr) */
+    int32_t hsamp[3], vsamp[3];                   /* sampling factors per component */
+    int32_t qsel[3], dcsel[3], acsel[3];          /* table selectors per component */
+    int32_t restart_interval;                     /* DRI value (0 = none) */
+    int32_t reserved;
+    int64_t scan_offset, scan_bytes;              /* entropy-coded segment inside the file */
+    uint16_t quant[4][64];                        /* quantisation tables, natural (row-major) order */
+    uint8_t dc_bits[4][16], dc_vals[4][16];       /* Huffman tables as in DHT: counts per length 1..16, symbols */
+    uint8_t ac_bits[4][16], ac_vals[4][256];
+} ibt_jpeg_info_t;
+
+/* HOST only (no GPU work): parse the markers of a JPEG file held in host memory. */
+int ibt_jpeg_parse(const uint8_t *host_file, int64_t nbytes, ibt_jpeg_info_t *info);
+/* bytes of device scratch ibt_jpeg_decode needs for this file (0 if the info is not decodable) */
+int64_t ibt_jpeg_workspace_bytes(const ibt_jpeg_info_t *info);
+/* d_file: the whole file in DEVICE memory (4-byte aligned).  info: HOST.  workspace: 256-byte aligned.
+ * rgb (H,W,3) u8 = what np.array(Image.open(f)) holds (NULL to skip; must be NULL for grey-scale files);
+ * gray (H,W) u8 = cv2.cvtColor(that, COLOR_BGR2GRAY) with the reference's channel order (NULL to skip; for a
+ * grey-scale file: the decoded plane).  coeffset as ibt_gray_u8.  out_rounds: HOST int* or NULL, receives the number
+ * of Huffman synchronisation rounds.  SYNCHRONISES `stream` (convergence of the speculative Huffman decode). */
+int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *info, void *workspace, int64_t workspace_bytes,
+                    uint8_t *rgb, int64_t rgb_pitch, uint8_t *gray, int64_t gray_pitch, int coeffset,
+                    int *out_rounds, void *stream);
 
 #ifdef __cplusplus
 }

@@ -30,8 +30,8 @@ OPTFLOW_LK_GET_MIN_EIGENVALS = 8
 
 def build(force=False):
     """Compile the C restatement with gcc (oracle/Makefile)."""
-    src = os.path.join(_HERE, "ibt_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "ibt_oracle.c"), os.path.join(_HERE, "jpeg_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return _SO
 
@@ -236,3 +236,25 @@ def track_velocities(tracks, cam, tracking_interval, min_speed, max_speed, max_s
                 if max(rat) > max_speedfactor or max(ang) > max_angle:
                     keep[m] = False
     return EN, uv, sp, keep
+
+
+# ---- JPEG (oracle/jpeg_oracle.c): np.array(Image.open(image)) at s1:310 -------------------------------------------
+class JpegUnsupported(ValueError):
+    pass
+
+
+def imread_jpeg(data):
+    """bytes of a baseline JPEG -> what np.array(PIL.Image.open(...)) holds: (H,W,3) RGB u8, or (H,W) u8 for mode L."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    L = lib()
+    w, h, nc = C.c_int(), C.c_int(), C.c_int()
+    rc = L.orc_jpeg_info(_p(buf), C.c_long(buf.size), C.byref(w), C.byref(h), C.byref(nc))
+    if rc == -5:
+        raise JpegUnsupported("oracle: JPEG variant not handled")
+    if rc != 0:
+        raise ValueError("oracle: not a decodable JPEG (%d)" % rc)
+    out = np.zeros((h.value, w.value, 3) if nc.value == 3 else (h.value, w.value), np.uint8)
+    rc = L.orc_jpeg_decode(_p(buf), C.c_long(buf.size), _p(out))
+    if rc != 0:
+        raise ValueError("oracle: JPEG decode failed (%d)" % rc)
+    return out

