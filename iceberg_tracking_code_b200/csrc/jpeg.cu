@@ -26,17 +26,19 @@
 namespace ibt {
 
 constexpr int JPG_S = 1024;              // subsequence length, bits
-constexpr int JPG_LUT_BITS = 9;
+constexpr int JPG_LUT_BITS = 10;
 constexpr int JPG_CHUNK = 4096;          // destuff: bytes per CTA (256 threads x 16)
 constexpr int JPG_MAX_BLK = 10;          // blocks per MCU (T.81 B.2.3)
 
-struct JpgTables {                       // kernel parameter (~9 KB): one (DC, AC) table pair per component
-    uint16_t lut[6][1 << JPG_LUT_BITS];  // [comp*2 + ac]: len << 8 | symbol; 0 = code longer than JPG_LUT_BITS
+struct __align__(16) JpgTables {          // device copy in the workspace (~27 KB): one (DC, AC) table pair per component
+    uint32_t lut[6][1 << JPG_LUT_BITS];  // [comp*2 + ac]: symbol | len << 8 | (len + extra bits) << 16; 0 = longer code
     uint32_t limit[6][17];               // left-justified 16-bit value of the first code longer than l
     int32_t valoff[6][17];               // vals index = valoff[l] + (w16 >> (16 - l))
     uint8_t vals[6][256];
-    uint8_t blk_comp[12];
+    uint8_t blk_comp[16];
     int nblk_mcu;
+    uint32_t compmap;                    // component of block b of the MCU in bits [2b, 2b+1]
+    uint32_t pad[2];
 };
 
 struct JpgGeom {
@@ -175,68 +177,77 @@ __global__ void __launch_bounds__(256) jpg_destuff_write(const uint8_t *__restri
 }
 
 // ---- Huffman ---------------------------------------------------------------------------------------------------
-struct JpgSmemTables {
-    uint16_t lut[6][1 << JPG_LUT_BITS];
+struct __align__(16) JpgSmemTables {
+    uint32_t lut[6][1 << JPG_LUT_BITS];
     uint32_t limit[6][17];
     int32_t valoff[6][17];
     uint8_t vals[6][256];
-    uint8_t blk_comp[12];
+    uint8_t blk_comp[16];
     uint8_t zigzag[64];
 };
-__device__ __forceinline__ void load_tables(JpgSmemTables &S, const JpgTables &T)
+__device__ __forceinline__ void load_tables(JpgSmemTables &S, const JpgTables *__restrict__ T)
 {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(&T);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&S);
-    constexpr int nw = (int)(offsetof(JpgTables, nblk_mcu) / 4);
-    static_assert(offsetof(JpgTables, nblk_mcu) % 4 == 0, "layout");
+    // the tables sit in global memory (L2-resident after the first CTA): 16-byte coalesced copies
+    const uint4 *src = reinterpret_cast<const uint4 *>(T);
+    uint4 *dst = reinterpret_cast<uint4 *>(&S);
+    constexpr int nq = (int)(offsetof(JpgTables, nblk_mcu) / 16);
+    static_assert(offsetof(JpgTables, nblk_mcu) % 16 == 0, "layout");
     static_assert(offsetof(JpgSmemTables, zigzag) == offsetof(JpgTables, nblk_mcu), "layout");
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) dst[i] = __ldg(src + i);
     if (threadIdx.x < 64) S.zigzag[threadIdx.x] = c_zigzag[threadIdx.x];
     __syncthreads();
 }
 
 // Decode symbols from bit `pos` while pos < end.  State (pos, blk = block inside the MCU, k = next zig-zag index,
 // 0 = DC expected).  done counts completed blocks.  WRITE: coefficients go to coef[(base + done) * 64 + natural index].
+// One thread walks one subsequence, so the loop is a latency chain: window -> LUT (shared memory) -> advance.  The body
+// is branch-free (a warp holds 32 unrelated decoders), the stream window lives in three registers with the next word
+// already in flight, and the DC case is folded into the AC rule (run 0, index k + run = 0).
 template <bool WRITE>
-__device__ __forceinline__ void huff_run(const uint32_t *__restrict__ words, const JpgSmemTables &S, int nblk_mcu, uint32_t &pos,
-                                         int &blk, int &k, uint32_t end, uint32_t &done, int16_t *__restrict__ coef, uint32_t base,
-                                         uint32_t nblocks)
+__device__ __forceinline__ void huff_run(const uint32_t *__restrict__ words, const JpgSmemTables &S, const uint32_t compmap,
+                                         const int nblk_mcu, uint32_t &pos, int &blk, int &k, const uint32_t end, uint32_t &done,
+                                         int16_t *__restrict__ coef, const uint32_t base, const uint32_t nblocks)
 {
+    constexpr int LUTN = 1 << JPG_LUT_BITS;
+    uint32_t wcur = pos >> 5;
+    const uint32_t *wp = words + wcur + 2;
+    uint32_t hi = wp[-2], lo = wp[-1], nxt = wp[0];
+    const uint32_t *lut0 = &S.lut[0][0];
+    int set2 = (int)((compmap >> (2 * blk)) & 3u) * 2;               // table pair of the current block
     while (pos < end) {
-        const int tbl = S.blk_comp[blk] * 2 + (k > 0);
-        const uint32_t wi = pos >> 5;
-        const uint32_t win = __funnelshift_l(words[wi + 1], words[wi], pos & 31u);
-        const uint32_t e = S.lut[tbl][win >> (32 - JPG_LUT_BITS)];
-        int len, sym;
-        if (e) { len = (int)(e >> 8); sym = (int)(e & 255u); }
-        else {
+        const uint32_t win = __funnelshift_l(lo, hi, pos);          // shift amount taken mod 32
+        const int tbl = set2 + (k > 0);
+        uint32_t e = lut0[tbl * LUTN + (win >> (32 - JPG_LUT_BITS))];
+        if (__builtin_expect(e == 0u, 0)) {                         // code longer than the LUT: canonical length search
             const uint32_t w16 = win >> 16;
-            int l = JPG_LUT_BITS + 1;
-            while (l <= 16 && w16 >= S.limit[tbl][l]) l++;
-            if (l > 16) { len = 16; sym = 0; }                       // not a code (only a mis-synchronised decoder gets here)
-            else { len = l; sym = S.vals[tbl][(S.valoff[tbl][l] + (int)(w16 >> (16 - l))) & 255]; }
+            const uint32_t *lim = S.limit[tbl];
+            int len = JPG_LUT_BITS + 1;
+#pragma unroll
+            for (int l = JPG_LUT_BITS + 1; l < 16; l++) len += w16 >= lim[l];
+            // w16 >= lim[16]: not a code (only a mis-synchronised decoder gets here): 16 bits, symbol 0
+            const uint32_t sym = w16 >= lim[16] ? 0u : S.vals[tbl][(S.valoff[tbl][len] + (int)(w16 >> (16 - len))) & 255];
+            e = sym | (uint32_t)len << 8 | (uint32_t)(len + (sym & 15u)) << 16;
         }
-        const int s = sym & 15;
-        int val = 0;
-        if (WRITE && s) {
-            const uint32_t r = (win << len) >> (32 - s);
-            val = r < (1u << (s - 1)) ? (int)r - (1 << s) + 1 : (int)r;
-        }
-        pos += (uint32_t)(len + s);
-        bool fin = false;
-        int widx = -1;
-        if (k == 0) { widx = 0; k = 1; }
-        else {
-            const int r = sym >> 4;
-            if (s) { k += r; if (k <= 63) widx = S.zigzag[k]; k++; fin = k > 63; }
-            else if (r == 15) { k += 16; fin = k > 63; }
-            else fin = true;
-        }
-        if (WRITE && widx >= 0) {
+        const int s = (int)(e & 15u), r = (int)((e >> 4) & 15u);
+        const int kz = k + r;                                       // zig-zag index of this coefficient (DC: 0)
+        if (WRITE) {
             const uint32_t b = base + done;
-            if (b < nblocks) coef[(size_t)b * 64 + widx] = (int16_t)val;
+            if (s != 0 && kz <= 63 && b < nblocks) {
+                const int len = (int)((e >> 8) & 255u);
+                const uint32_t v = (win << len) >> (32 - s);
+                const int val = v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v;
+                coef[(size_t)b * 64 + S.zigzag[kz]] = (int16_t)val;
+            }
         }
-        if (fin) { k = 0; blk = blk + 1 == nblk_mcu ? 0 : blk + 1; done++; }
+        pos += e >> 16;
+        const bool fin = (k != 0 && s == 0 && r != 15) || kz >= 63;  // EOB, or the block is full
+        k = fin ? 0 : kz + 1;
+        done += fin ? 1u : 0u;
+        const int b1 = blk + 1 == nblk_mcu ? 0 : blk + 1;
+        blk = fin ? b1 : blk;
+        set2 = (int)((compmap >> (2 * blk)) & 3u) * 2;
+        const uint32_t wnew = pos >> 5;
+        if (wnew != wcur) { hi = lo; lo = nxt; nxt = *++wp; wcur = wnew; }
     }
 }
 
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(256) jpg_sync_init(unsigned long long *__restr
 }
 // One round: threads whose entry state changed decode their subsequence and publish the exit state to their successor.
 __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
-                                                      const __grid_constant__ JpgTables T, unsigned long long *__restrict__ start,
+                                                      const JpgTables *__restrict__ T, unsigned long long *__restrict__ start,
                                                       uint8_t *__restrict__ dirty, uint32_t *__restrict__ nblk, int nsub, int round,
                                                       uint32_t *__restrict__ changed_slot)
 {
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict
     uint32_t pos = (uint32_t)st;
     int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
     uint32_t done = 0;
-    huff_run<false>(words, S, T.nblk_mcu, pos, blk, k, (uint32_t)hi, done, nullptr, 0, 0);
+    huff_run<false>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, nullptr, 0, 0);
     nblk[i] = done;
     if (i + 1 < nsub && hi < total_bits) {
         const unsigned long long out = (unsigned long long)pos | ((unsigned long long)(blk * 64 + k) << 32);
@@ -284,7 +295,7 @@ __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict
     }
 }
 __global__ void __launch_bounds__(128) jpg_huff_write(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
-                                                      const __grid_constant__ JpgTables T, const unsigned long long *__restrict__ start,
+                                                      const JpgTables *__restrict__ T, const unsigned long long *__restrict__ start,
                                                       const uint32_t *__restrict__ base, int16_t *__restrict__ coef, int nsub,
                                                       uint32_t nblocks)
 {
@@ -300,7 +311,7 @@ __global__ void __launch_bounds__(128) jpg_huff_write(const uint32_t *__restrict
     uint32_t pos = (uint32_t)st;
     int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
     uint32_t done = 0;
-    huff_run<true>(words, S, T.nblk_mcu, pos, blk, k, (uint32_t)hi, done, coef, base[i], nblocks);
+    huff_run<true>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, coef, base[i], nblocks);
 }
 
 // ---- DC differences -> per-MCU sums per component (rows of dcs: [comp][nmcu]) ------------------------------------------------
@@ -398,77 +409,105 @@ __global__ void __launch_bounds__(128) jpg_idct(const int16_t *__restrict__ coef
 }
 
 // ---- chroma upsampling (jdsample.c "fancy") + YCbCr -> RGB (jdcolor.c) + optional cvtColor gray ---------------------------------
-// 4 chroma samples for pixels x0..x0+3 of row y
-__device__ __forceinline__ void chroma4(const JpgGeom &G, int c, int x0, int y, int *out)
+// six neighbouring samples of one chroma row: columns cx0-1 .. cx0+4 (cx0 a multiple of 4), clamped to [0, dw-1]
+__device__ __forceinline__ void chroma_row6(const uint8_t *__restrict__ row, int cx0, int dw, int *v)
+{
+    if (cx0 > 0 && cx0 + 4 <= dw - 1) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(row + cx0);
+        v[0] = row[cx0 - 1]; v[1] = w & 255; v[2] = (w >> 8) & 255; v[3] = (w >> 16) & 255; v[4] = w >> 24; v[5] = row[cx0 + 4];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 6; j++) v[j] = row[min(max(cx0 - 1 + j, 0), dw - 1)];
+    }
+}
+// 8 chroma samples for pixels x0..x0+7 (x0 a multiple of 8) of row y
+__device__ __forceinline__ void chroma8(const JpgGeom &G, int c, int x0, int y, int *out)
 {
     const uint8_t *P = G.plane[c];
     const int pw = G.pw[c], dw = G.dw[c], dh = G.dh[c];
     const int hsub = G.hmax / G.hs[c], vsub = G.vmax / G.vs[c];
     if (hsub == 1) {
-        const uint32_t w = *reinterpret_cast<const uint32_t *>(P + (size_t)y * pw + x0);
-        out[0] = w & 255; out[1] = (w >> 8) & 255; out[2] = (w >> 16) & 255; out[3] = w >> 24;
+        const uint2 w = *reinterpret_cast<const uint2 *>(P + (size_t)y * pw + x0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { out[j] = (w.x >> (8 * j)) & 255; out[4 + j] = (w.y >> (8 * j)) & 255; }
         return;
     }
-    const int cx = x0 >> 1;                               // x0 is a multiple of 4: columns cx-1 .. cx+2
-    const int xa = max(cx - 1, 0), xb = min(cx, dw - 1), xc = min(cx + 1, dw - 1), xd = min(cx + 2, dw - 1);
+    const int cx0 = x0 >> 1;
+    int a[6];
     if (vsub == 1) {
-        const uint8_t *r = P + (size_t)y * pw;
-        const int a = r[xa], b = r[xb], cc = r[xc], d = r[xd];
-        if (dw <= 2) { out[0] = out[1] = b; out[2] = out[3] = cc; return; }
-        out[0] = (3 * b + a + 1) >> 2; out[1] = (3 * b + cc + 2) >> 2;
-        out[2] = (3 * cc + b + 1) >> 2; out[3] = (3 * cc + d + 2) >> 2;
+        chroma_row6(P + (size_t)y * pw, cx0, dw, a);
+        if (dw <= 2) {                                             // h2v1_upsample: plain replication
+#pragma unroll
+            for (int j = 0; j < 8; j++) out[j] = a[1 + (j >> 1)];
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            out[2 * j] = (3 * a[1 + j] + a[j] + 1) >> 2;
+            out[2 * j + 1] = (3 * a[1 + j] + a[2 + j] + 2) >> 2;
+        }
         return;
     }
     const int cy = y >> 1;
-    const uint8_t *r0 = P + (size_t)cy * pw;
-    if (dw <= 2) { out[0] = out[1] = r0[xb]; out[2] = out[3] = r0[xc]; return; }
-    const int fy = min(max((y & 1) ? cy + 1 : cy - 1, 0), dh - 1);
-    const uint8_t *r1 = P + (size_t)fy * pw;
-    const int a = 3 * r0[xa] + r1[xa], b = 3 * r0[xb] + r1[xb], cc = 3 * r0[xc] + r1[xc], d = 3 * r0[xd] + r1[xd];
-    out[0] = (3 * b + a + 8) >> 4; out[1] = (3 * b + cc + 7) >> 4;
-    out[2] = (3 * cc + b + 8) >> 4; out[3] = (3 * cc + d + 7) >> 4;
+    chroma_row6(P + (size_t)cy * pw, cx0, dw, a);
+    if (dw <= 2) {                                                 // h2v2_upsample: plain replication
+#pragma unroll
+        for (int j = 0; j < 8; j++) out[j] = a[1 + (j >> 1)];
+        return;
+    }
+    int f[6];
+    chroma_row6(P + (size_t)min(max((y & 1) ? cy + 1 : cy - 1, 0), dh - 1) * pw, cx0, dw, f);
+#pragma unroll
+    for (int j = 0; j < 6; j++) a[j] = 3 * a[j] + f[j];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        out[2 * j] = (3 * a[1 + j] + a[j] + 8) >> 4;
+        out[2 * j + 1] = (3 * a[1 + j] + a[2 + j] + 7) >> 4;
+    }
 }
 
 template <int SH>
 __global__ void __launch_bounds__(256) jpg_color(const __grid_constant__ JpgGeom G, uint8_t *__restrict__ rgb, int64_t rgb_pitch,
                                                  uint8_t *__restrict__ gray, int64_t gray_pitch, int k0, int k1, int k2)
 {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     const int y = blockIdx.y;
     if (x0 >= G.W) return;
-    const uint32_t yw = *reinterpret_cast<const uint32_t *>(G.plane[0] + (size_t)y * G.pw[0] + x0);
-    uint32_t R[4], Gc[4], B[4], g[4];
+    const uint2 yw = *reinterpret_cast<const uint2 *>(G.plane[0] + (size_t)y * G.pw[0] + x0);
+    uint32_t R[8], Gc[8], B[8], g[8];
     if (G.ncomp == 1) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) g[j] = (yw >> (8 * j)) & 255u;
+        for (int j = 0; j < 8; j++) g[j] = ((j < 4 ? yw.x : yw.y) >> (8 * (j & 3))) & 255u;
     } else {
-        int cb[4], cr[4];
-        chroma4(G, 1, x0, y, cb);
-        chroma4(G, 2, x0, y, cr);
+        int cb[8], cr[8];
+        chroma8(G, 1, x0, y, cb);
+        chroma8(G, 2, x0, y, cr);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int Y = (int)((yw >> (8 * j)) & 255u), b = cb[j] - 128, r = cr[j] - 128;
+        for (int j = 0; j < 8; j++) {
+            const int Y = (int)(((j < 4 ? yw.x : yw.y) >> (8 * (j & 3))) & 255u), b = cb[j] - 128, r = cr[j] - 128;
             R[j] = sat_u8(Y + ((91881 * r + 32768) >> 16));
             Gc[j] = sat_u8(Y + ((-22554 * b + 32768 - 46802 * r) >> 16));
             B[j] = sat_u8(Y + ((116130 * b + 32768) >> 16));
             g[j] = (R[j] * k0 + Gc[j] * k1 + B[j] * k2 + (1u << (SH - 1))) >> SH;      // channel 0 takes the "B" weight (s1:311)
         }
     }
-    const bool full = x0 + 4 <= G.W;
+    const bool full = x0 + 8 <= G.W;
     if (gray) {
         uint8_t *d = gray + (size_t)y * gray_pitch + x0;
-        if (full && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) *reinterpret_cast<uint32_t *>(d) = g[0] | g[1] << 8 | g[2] << 16 | g[3] << 24;
-        else for (int j = 0; j < 4 && x0 + j < G.W; j++) d[j] = (uint8_t)g[j];
+        if (full && ((reinterpret_cast<uintptr_t>(d) & 7) == 0))
+            *reinterpret_cast<uint2 *>(d) = make_uint2(g[0] | g[1] << 8 | g[2] << 16 | g[3] << 24, g[4] | g[5] << 8 | g[6] << 16 | g[7] << 24);
+        else
+            for (int j = 0; j < 8 && x0 + j < G.W; j++) d[j] = (uint8_t)g[j];
     }
     if (rgb && G.ncomp == 3) {
         uint8_t *d = rgb + (size_t)y * rgb_pitch + (size_t)x0 * 3;
-        if (full && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
-            uint32_t *w = reinterpret_cast<uint32_t *>(d);
-            w[0] = R[0] | Gc[0] << 8 | B[0] << 16 | R[1] << 24;
-            w[1] = Gc[1] | B[1] << 8 | R[2] << 16 | Gc[2] << 24;
-            w[2] = B[2] | R[3] << 8 | Gc[3] << 16 | B[3] << 24;
+        if (full && ((reinterpret_cast<uintptr_t>(d) & 7) == 0)) {
+            uint2 *w = reinterpret_cast<uint2 *>(d);
+            w[0] = make_uint2(R[0] | Gc[0] << 8 | B[0] << 16 | R[1] << 24, Gc[1] | B[1] << 8 | R[2] << 16 | Gc[2] << 24);
+            w[1] = make_uint2(B[2] | R[3] << 8 | Gc[3] << 16 | B[3] << 24, R[4] | Gc[4] << 8 | B[4] << 16 | R[5] << 24);
+            w[2] = make_uint2(Gc[5] | B[5] << 8 | R[6] << 16 | Gc[6] << 24, B[6] | R[7] << 8 | Gc[7] << 16 | B[7] << 24);
         } else {
-            for (int j = 0; j < 4 && x0 + j < G.W; j++) { d[3 * j] = (uint8_t)R[j]; d[3 * j + 1] = (uint8_t)Gc[j]; d[3 * j + 2] = (uint8_t)B[j]; }
+            for (int j = 0; j < 8 && x0 + j < G.W; j++) { d[3 * j] = (uint8_t)R[j]; d[3 * j + 1] = (uint8_t)Gc[j]; d[3 * j + 2] = (uint8_t)B[j]; }
         }
     }
 }
@@ -500,7 +539,7 @@ static int jpeg_validate(const ibt_jpeg_info_t *I)
 struct JpgLayout {
     JpgGeom G;
     int nmcu, nblocks, nsub, nchunks;
-    size_t off_stream, off_counts, off_offsets, off_meta, off_changed, off_start, off_dirty, off_nblk, off_base, off_partial,
+    size_t off_stream, off_counts, off_offsets, off_meta, off_tables, off_changed, off_start, off_dirty, off_nblk, off_base, off_partial,
         off_coef, off_dcs, off_dcpre, off_plane[3], total;
     size_t stream_bytes, coef_bytes;
 };
@@ -542,6 +581,7 @@ static void jpeg_layout(const ibt_jpeg_info_t *I, JpgLayout &L)
     L.off_counts = take((size_t)L.nchunks * 4);
     L.off_offsets = take((size_t)L.nchunks * 4);
     L.off_meta = take(64);
+    L.off_tables = take(sizeof(JpgTables));
     L.off_changed = take(JPG_MAX_ROUNDS_BATCH * 4);
     L.off_start = take((size_t)L.nsub * 8);
     L.off_dirty = take((size_t)L.nsub * 2);
@@ -571,10 +611,12 @@ static int build_tables(const ibt_jpeg_info_t *I, const JpgGeom &G, JpgTables &T
                 if (k + n > nvals_max || code + n > (1 << l)) return IBT_E_INVALID;
                 T.valoff[t][l] = k - code;
                 for (int i = 0; i < n; i++, code++, k++) {
+                    if (!ac && vals[k] > 15) return IBT_E_INVALID;          // DC categories are 0..11 (T.81 F.1.2.1)
                     T.vals[t][k] = vals[k];
                     if (l <= JPG_LUT_BITS) {
                         const int lo = code << (JPG_LUT_BITS - l), cnt = 1 << (JPG_LUT_BITS - l);
-                        for (int j = 0; j < cnt; j++) T.lut[t][lo + j] = (uint16_t)((l << 8) | vals[k]);
+                        for (int j = 0; j < cnt; j++)
+                            T.lut[t][lo + j] = (uint32_t)vals[k] | (uint32_t)l << 8 | (uint32_t)(l + (vals[k] & 15)) << 16;
                     }
                 }
                 T.limit[t][l] = (uint32_t)code << (16 - l);
@@ -584,7 +626,10 @@ static int build_tables(const ibt_jpeg_info_t *I, const JpgGeom &G, JpgTables &T
         }
     T.nblk_mcu = G.nblk_mcu;
     for (int c = 0; c < I->ncomp; c++)
-        for (int j = 0; j < G.hs[c] * G.vs[c]; j++) T.blk_comp[G.blkoff[c] + j] = (uint8_t)c;
+        for (int j = 0; j < G.hs[c] * G.vs[c]; j++) {
+            T.blk_comp[G.blkoff[c] + j] = (uint8_t)c;
+            T.compmap |= (uint32_t)c << (2 * (G.blkoff[c] + j));
+        }
     return IBT_OK;
 }
 
@@ -719,7 +764,12 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     static thread_local JpgLayout L;                        // ~1 KB of geometry, reused as a kernel parameter below
     jpeg_layout(I, L);
     if ((size_t)ws_bytes < L.total) return IBT_E_WORKSPACE;
-    static thread_local JpgTables T;
+    // pinned per-thread staging: [0, 256) round counters read back, then the Huffman tables on their way to the device.
+    // The function synchronises the stream before it returns, so the staging is free again at the next call.
+    static thread_local uint8_t *h_pinned = nullptr;
+    if (!h_pinned) IBT_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_pinned), 256 + sizeof(JpgTables), cudaHostAllocDefault));
+    uint32_t *h_flag = reinterpret_cast<uint32_t *>(h_pinned);
+    JpgTables &T = *reinterpret_cast<JpgTables *>(h_pinned + 256);
     rc = build_tables(I, L.G, T);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -737,6 +787,8 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     for (int c = 0; c < I->ncomp; c++) L.G.plane[c] = ws + L.off_plane[c];
     const uint8_t *scan = d_file + I->scan_offset;
 
+    const JpgTables *dT = reinterpret_cast<const JpgTables *>(ws + L.off_tables);
+    IBT_CUDA_TRY(cudaMemcpyAsync(ws + L.off_tables, &T, sizeof(JpgTables), cudaMemcpyHostToDevice, st));
     // 1. destuff
     IBT_CUDA_TRY(cudaMemsetAsync(sbytes, 0, L.stream_bytes, st));
     IBT_CUDA_TRY(cudaMemsetAsync(coef, 0, L.coef_bytes, st));
@@ -746,15 +798,13 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     jpg_destuff_write<<<L.nchunks, 256, 0, st>>>(scan, I->scan_bytes, offsets, sbytes, meta);
 
     // 2. synchronisation rounds; the host reads the per-round change counters once per batch
-    static thread_local uint32_t *h_flag = nullptr;
-    if (!h_flag) IBT_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_flag), JPG_MAX_ROUNDS_BATCH * 4, cudaHostAllocDefault));
     jpg_sync_init<<<(L.nsub + 255) / 256, 256, 0, st>>>(start, dirty, L.nsub);
     const int sync_ctas = (L.nsub + 127) / 128;
     int round = 0, batch = 8, rounds_used = -1;
     while (rounds_used < 0) {
         IBT_CUDA_TRY(cudaMemsetAsync(changed, 0, JPG_MAX_ROUNDS_BATCH * 4, st));
         for (int r = 0; r < batch; r++)
-            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, T, start, dirty, nblk, L.nsub, round + r, changed + r);
+            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, dirty, nblk, L.nsub, round + r, changed + r);
         IBT_CUDA_TRY(cudaMemcpyAsync(h_flag, changed, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
         IBT_CUDA_TRY(cudaStreamSynchronize(st));
         for (int r = 0; r < batch; r++)
@@ -771,7 +821,7 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     // 3. output block of every subsequence, coefficient pass
     rc = launch_scan(nblk, base, partial, L.nsub, 1, 0, st);
     if (rc) return rc;
-    jpg_huff_write<<<sync_ctas, 128, 0, st>>>(words, meta, T, start, base, coef, L.nsub, (uint32_t)L.nblocks);
+    jpg_huff_write<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, base, coef, L.nsub, (uint32_t)L.nblocks);
 
     // 4. DC prediction: prefix sums over MCUs per component
     jpg_dc_sums<<<(L.nmcu + 255) / 256, 256, 0, st>>>(coef, L.G, dcs, L.nmcu);
@@ -780,7 +830,7 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
 
     // 5. inverse DCT into the component planes, 6. upsampling + colour conversion (+ gray)
     jpg_idct<<<(L.nblocks + 127) / 128, 128, 0, st>>>(coef, dcpre, L.G, L.nmcu, L.nblocks);
-    const dim3 cgrid((unsigned)((I->width + 4 * 256 - 1) / (4 * 256)), (unsigned)I->height);
+    const dim3 cgrid((unsigned)((I->width + 8 * 256 - 1) / (8 * 256)), (unsigned)I->height);
     if (coeffset == IBT_GRAY_CV4_15BIT)
         jpg_color<15><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, 3735, 19235, 9798);
     else

@@ -44,6 +44,31 @@ def read_file(path):
         return f.read()
 
 
+class GpuJpegLoader:
+    """loader="gpu": path -> (gray CUDA tensor, ready event), the handle SequenceTracker.prepare() accepts.
+    Each decoding thread owns a jpeg.JpegDecoder and a CUDA stream, so reading + decoding frame t+k overlaps the
+    tracking kernels of frame t (the decoder's one host synchronisation blocks only its own thread)."""
+
+    def __init__(self, device, coeffset=0):
+        import threading
+        self.device = device
+        self.coeffset = coeffset
+        self._tls = threading.local()
+
+    def __call__(self, path):
+        from . import jpeg as _jpeg
+        tls = self._tls
+        if not hasattr(tls, "dec"):
+            tls.dec = _jpeg.JpegDecoder(self.device)
+            tls.stream = torch.cuda.Stream(device=self.device)
+        data = read_file(path)
+        with torch.cuda.device(self.device), torch.cuda.stream(tls.stream):
+            gray = tls.dec.decode(data, rgb=False, gray=True, coeffset=self.coeffset)[1]   # s1:310-311 in one pass
+            ev = torch.cuda.Event()
+            ev.record(tls.stream)
+        return gray, ev
+
+
 class FrameStager:
     """Pinned double buffer + copy stream: the host->device copy of frame t+1 overlaps the kernels of frame t."""
 
@@ -218,13 +243,10 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
     of processing is unchanged."""
     T = int(track_len)
     trk = tracker or SequenceTracker(feature_params, lk_params)
-    gpu_dec = None
     if isinstance(loader, str):
         if loader != "gpu":
             raise ValueError("loader must be a callable, None or 'gpu'")
-        from . import jpeg as _jpeg
-        gpu_dec = _jpeg.JpegDecoder(trk.device)
-        loader = read_file
+        loader = GpuJpegLoader(trk.device)
     if mask is not None:
         mask = cv._to_dev(mask, np.uint8, "mask")
     results = []
@@ -253,8 +275,6 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
                 decoded = pending.pop(counter).result()
             else:
                 decoded = loader(item) if loader is not None else item
-            if gpu_dec is not None:
-                decoded = gpu_dec.decode(decoded, rgb=False, gray=True)[1]       # s1:310-311 in one pass
             cur = trk.prepare(decoded)
             if prev is not None and trk.n > 0:
                 trk.track(prev, cur)
@@ -333,15 +353,9 @@ class LucasKanade:
     def run(self):
         trk = SequenceTracker(self.feature_params, self.lk_params, fb_threshold=self.distthreshold)
         prev = None
-        dec = None
-        if self.loader == "gpu":
-            from . import jpeg as _jpeg
-            dec = _jpeg.JpegDecoder(trk.device)
+        loader = GpuJpegLoader(trk.device) if self.loader == "gpu" else self.loader
         for counter, image in enumerate(self.imagelist):
-            if dec is not None:
-                cur = trk.prepare(dec.decode(read_file(image), rgb=False, gray=True)[1])
-            else:
-                cur = trk.prepare(self.loader(image))
+            cur = trk.prepare(loader(image))
             if prev is not None and trk.n > 0:
                 trk.track(prev, cur)
             if counter % self.detect_interval == 0:
