@@ -6,7 +6,7 @@
 //
 //   destuff       remove the 0x00 after every 0xFF of the entropy-coded segment (count / scan / write); bytes are stored
 //                 so that a 32-bit load returns them in bit-stream (big-endian) order
-//   Huffman       the segment has no restart markers, so it is decoded speculatively: thread i owns bits
+//   Huffman       decoded speculatively (restart markers, if any, are not needed for parallelism): thread i owns bits
 //                 [i*S, (i+1)*S) and starts from a guessed decoder state (block 0 of an MCU, DC expected).  Huffman
 //                 streams self-synchronise: after a few symbols a decoder that started in the wrong state is in the
 //                 right one.  Rounds: every thread whose entry state changed decodes its subsequence again and hands its
@@ -49,6 +49,7 @@ struct JpgGeom {
     int pw[3], ph[3];                    // plane size (samples, whole blocks)
     int dw[3], dh[3];                    // real downsampled size
     int hmax, vmax;
+    int restart_interval;                // MCUs per restart interval (0 = none): DC predictions restart there
     uint8_t *plane[3];
     uint16_t quant[3][64];               // per component, natural order
 };
@@ -137,42 +138,55 @@ static int launch_scan(const uint32_t *in, uint32_t *out, uint32_t *partial, int
 }
 
 // ---- destuff ------------------------------------------------------------------------------------------------
-// byte j of the segment is dropped iff it is the 0x00 that follows a 0xFF
-__device__ __forceinline__ uint32_t destuff_keepmask(const uint8_t *__restrict__ src, int64_t n, int64_t j0, uint8_t *b)
+// byte j of the segment is dropped iff it is the 0x00 that follows a 0xFF, or belongs to an RSTn marker (FF D0..D7);
+// rmask marks the first byte of each RSTn marker (the next restart interval starts at the output position reached there)
+__device__ __forceinline__ uint32_t destuff_keepmask(const uint8_t *__restrict__ src, int64_t n, int64_t j0, uint8_t *b, uint32_t &rmask)
 {
     uint32_t keep = 0;
+    rmask = 0;
     uint8_t prev = j0 > 0 && j0 <= n ? src[j0 - 1] : 0;
+    uint8_t c = j0 < n ? src[j0] : 0;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
         const int64_t g = j0 + j;
-        const uint8_t c = g < n ? src[g] : 0;
+        const uint8_t nx = g + 1 < n ? src[g + 1] : 0;
         b[j] = c;
-        if (g < n && !(c == 0x00 && prev == 0xFF)) keep |= 1u << j;
+        const bool stuffing = c == 0x00 && prev == 0xFF;
+        const bool rst0 = c == 0xFF && nx >= 0xD0 && nx <= 0xD7;
+        const bool rst1 = prev == 0xFF && c >= 0xD0 && c <= 0xD7;
+        if (g < n && !(stuffing || rst0 || rst1)) keep |= 1u << j;
+        if (g < n && rst0) rmask |= 1u << j;
         prev = c;
+        c = nx;
     }
     return keep;
 }
 __global__ void __launch_bounds__(256) jpg_destuff_count(const uint8_t *__restrict__ src, int64_t n, uint32_t *__restrict__ counts)
 {
     uint8_t b[16];
+    uint32_t rmask;
     const int64_t j0 = (int64_t)blockIdx.x * JPG_CHUNK + threadIdx.x * 16;
-    const uint32_t keep = destuff_keepmask(src, n, j0, b);
+    const uint32_t keep = destuff_keepmask(src, n, j0, b, rmask);
     uint32_t tot;
     cta_exclusive_scan(__popc(keep), &tot);
     if (threadIdx.x == 0) counts[blockIdx.x] = tot;
 }
-// dst byte k lives at address k ^ 3: a 32-bit load then holds four stream bytes most-significant first
+// dst byte k lives at address k ^ 3: a 32-bit load then holds four stream bytes most-significant first.
+// rst (restart intervals only): bit k set = a restart interval starts at destuffed byte k.
 __global__ void __launch_bounds__(256) jpg_destuff_write(const uint8_t *__restrict__ src, int64_t n, const uint32_t *__restrict__ offsets,
-                                                         uint8_t *__restrict__ dst, uint32_t *__restrict__ meta)
+                                                         uint8_t *__restrict__ dst, uint32_t *__restrict__ meta, uint32_t *__restrict__ rst)
 {
     uint8_t b[16];
+    uint32_t rmask;
     const int64_t j0 = (int64_t)blockIdx.x * JPG_CHUNK + threadIdx.x * 16;
-    const uint32_t keep = destuff_keepmask(src, n, j0, b);
+    const uint32_t keep = destuff_keepmask(src, n, j0, b, rmask);
     uint32_t tot;
     uint32_t o = cta_exclusive_scan(__popc(keep), &tot) + offsets[blockIdx.x];
 #pragma unroll
-    for (int j = 0; j < 16; j++)
+    for (int j = 0; j < 16; j++) {
+        if (rst && (rmask >> j & 1u)) atomicOr(&rst[o >> 5], 1u << (o & 31u));
         if (keep >> j & 1u) { dst[o ^ 3u] = b[j]; o++; }
+    }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) meta[0] = offsets[blockIdx.x] + tot;      // destuffed bytes
 }
 
@@ -206,7 +220,8 @@ __device__ __forceinline__ void load_tables(JpgSmemTables &S, const JpgTables *_
 template <bool WRITE>
 __device__ __forceinline__ void huff_run(const uint32_t *__restrict__ words, const JpgSmemTables &S, const uint32_t compmap,
                                          const int nblk_mcu, uint32_t &pos, int &blk, int &k, const uint32_t end, uint32_t &done,
-                                         int16_t *__restrict__ coef, const uint32_t base, const uint32_t nblocks)
+                                         int16_t *__restrict__ coef, const uint32_t base, const uint32_t nblocks,
+                                         const uint32_t *__restrict__ rst)
 {
     constexpr int LUTN = 1 << JPG_LUT_BITS;
     uint32_t wcur = pos >> 5;
@@ -246,8 +261,23 @@ __device__ __forceinline__ void huff_run(const uint32_t *__restrict__ words, con
         const int b1 = blk + 1 == nblk_mcu ? 0 : blk + 1;
         blk = fin ? b1 : blk;
         set2 = (int)((compmap >> (2 * blk)) & 3u) * 2;
-        const uint32_t wnew = pos >> 5;
+        uint32_t wnew = pos >> 5;
         if (wnew != wcur) { hi = lo; lo = nxt; nxt = *++wp; wcur = wnew; }
+        if (rst != nullptr && fin && blk == 0) {
+            // An MCU is complete.  If a restart interval starts at the next byte boundary and only padding (1-bits: no
+            // code word is all ones, T.81 C.2) lies before it, this was the last MCU of its interval: skip the padding.
+            // (The RSTn marker itself was removed by the destuff pass; the DC predictions restart in jpg_idct.)
+            const uint32_t bp = (pos + 7u) >> 3;
+            if (rst[bp >> 5] >> (bp & 31u) & 1u) {
+                const uint32_t n = 8u * bp - pos;
+                const uint32_t w = __funnelshift_l(lo, hi, pos);
+                if (n == 0u || (w >> (32u - n)) == (1u << n) - 1u) {
+                    pos = 8u * bp;
+                    wnew = pos >> 5;
+                    if (wnew != wcur) { hi = lo; lo = nxt; nxt = *++wp; wcur = wnew; }
+                }
+            }
+        }
     }
 }
 
@@ -264,7 +294,7 @@ __global__ void __launch_bounds__(256) jpg_sync_init(unsigned long long *__restr
 __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
                                                       const JpgTables *__restrict__ T, unsigned long long *__restrict__ start,
                                                       uint8_t *__restrict__ dirty, uint32_t *__restrict__ nblk, int nsub, int round,
-                                                      uint32_t *__restrict__ changed_slot)
+                                                      uint32_t *__restrict__ changed_slot, const uint32_t *__restrict__ rst)
 {
     __shared__ JpgSmemTables S;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,7 +313,7 @@ __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict
     uint32_t pos = (uint32_t)st;
     int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
     uint32_t done = 0;
-    huff_run<false>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, nullptr, 0, 0);
+    huff_run<false>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, nullptr, 0, 0, rst);
     nblk[i] = done;
     if (i + 1 < nsub && hi < total_bits) {
         const unsigned long long out = (unsigned long long)pos | ((unsigned long long)(blk * 64 + k) << 32);
@@ -297,7 +327,7 @@ __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict
 __global__ void __launch_bounds__(128) jpg_huff_write(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
                                                       const JpgTables *__restrict__ T, const unsigned long long *__restrict__ start,
                                                       const uint32_t *__restrict__ base, int16_t *__restrict__ coef, int nsub,
-                                                      uint32_t nblocks)
+                                                      uint32_t nblocks, const uint32_t *__restrict__ rst)
 {
     __shared__ JpgSmemTables S;
     load_tables(S, T);
@@ -311,7 +341,7 @@ __global__ void __launch_bounds__(128) jpg_huff_write(const uint32_t *__restrict
     uint32_t pos = (uint32_t)st;
     int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
     uint32_t done = 0;
-    huff_run<true>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, coef, base[i], nblocks);
+    huff_run<true>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, coef, base[i], nblocks, rst);
 }
 
 // ---- DC differences -> per-MCU sums per component (rows of dcs: [comp][nmcu]) ------------------------------------------------
@@ -372,6 +402,7 @@ __global__ void __launch_bounds__(128) jpg_idct(const int16_t *__restrict__ coef
     const int jl = (by % v) * h + (bx % h);
     const size_t b0 = (size_t)m * G.nblk_mcu + G.blkoff[c];
     int dc = (int)dcpre[(size_t)c * nmcu + m];
+    if (G.restart_interval) dc -= (int)dcpre[(size_t)c * nmcu + m - m % G.restart_interval];
     for (int j = 0; j <= jl; j++) dc += coef[(b0 + j) * 64];
     const uint4 *src = reinterpret_cast<const uint4 *>(coef + (b0 + jl) * 64);
     int ws[64];
@@ -521,7 +552,7 @@ static int jpeg_validate(const ibt_jpeg_info_t *I)
 {
     if (!I || I->width <= 0 || I->height <= 0 || I->width > 65535 || I->height > 65535) return IBT_E_INVALID;
     if (I->ncomp != 1 && I->ncomp != 3) return IBT_E_UNSUPPORTED;
-    if (I->restart_interval != 0) return IBT_E_UNSUPPORTED;
+    if (I->restart_interval < 0) return IBT_E_INVALID;
     if (I->scan_bytes <= 0 || I->scan_offset < 0 || I->scan_bytes > 0x1fffffff) return IBT_E_INVALID;
     for (int c = 0; c < I->ncomp; c++) {
         if (I->hsamp[c] < 1 || I->vsamp[c] < 1 || I->qsel[c] < 0 || I->qsel[c] > 3 || I->dcsel[c] < 0 || I->dcsel[c] > 3 ||
@@ -539,9 +570,9 @@ static int jpeg_validate(const ibt_jpeg_info_t *I)
 struct JpgLayout {
     JpgGeom G;
     int nmcu, nblocks, nsub, nchunks;
-    size_t off_stream, off_counts, off_offsets, off_meta, off_tables, off_changed, off_start, off_dirty, off_nblk, off_base, off_partial,
+    size_t off_stream, off_counts, off_offsets, off_meta, off_tables, off_rst, off_changed, off_start, off_dirty, off_nblk, off_base, off_partial,
         off_coef, off_dcs, off_dcpre, off_plane[3], total;
-    size_t stream_bytes, coef_bytes;
+    size_t stream_bytes, coef_bytes, rst_bytes;
 };
 constexpr int JPG_MAX_ROUNDS_BATCH = 64;
 
@@ -550,6 +581,7 @@ static void jpeg_layout(const ibt_jpeg_info_t *I, JpgLayout &L)
     memset(&L, 0, sizeof(L));
     JpgGeom &G = L.G;
     G.ncomp = I->ncomp; G.W = I->width; G.H = I->height;
+    G.restart_interval = I->restart_interval;
     G.hmax = G.vmax = 1;
     for (int c = 0; c < I->ncomp; c++) {
         G.hs[c] = I->ncomp == 1 ? 1 : I->hsamp[c];
@@ -582,6 +614,8 @@ static void jpeg_layout(const ibt_jpeg_info_t *I, JpgLayout &L)
     L.off_offsets = take((size_t)L.nchunks * 4);
     L.off_meta = take(64);
     L.off_tables = take(sizeof(JpgTables));
+    L.rst_bytes = I->restart_interval ? ((L.stream_bytes / 8 + 8 + 3) & ~(size_t)3) : 0;
+    L.off_rst = take(L.rst_bytes);
     L.off_changed = take(JPG_MAX_ROUNDS_BATCH * 4);
     L.off_start = take((size_t)L.nsub * 8);
     L.off_dirty = take((size_t)L.nsub * 2);
@@ -795,7 +829,9 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     jpg_destuff_count<<<L.nchunks, 256, 0, st>>>(scan, I->scan_bytes, counts);
     rc = launch_scan(counts, offsets, partial, L.nchunks, 1, 0, st);
     if (rc) return rc;
-    jpg_destuff_write<<<L.nchunks, 256, 0, st>>>(scan, I->scan_bytes, offsets, sbytes, meta);
+    uint32_t *rst = L.rst_bytes ? reinterpret_cast<uint32_t *>(ws + L.off_rst) : nullptr;
+    if (rst) IBT_CUDA_TRY(cudaMemsetAsync(rst, 0, L.rst_bytes, st));
+    jpg_destuff_write<<<L.nchunks, 256, 0, st>>>(scan, I->scan_bytes, offsets, sbytes, meta, rst);
 
     // 2. synchronisation rounds; the host reads the per-round change counters once per batch
     jpg_sync_init<<<(L.nsub + 255) / 256, 256, 0, st>>>(start, dirty, L.nsub);
@@ -804,7 +840,7 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     while (rounds_used < 0) {
         IBT_CUDA_TRY(cudaMemsetAsync(changed, 0, JPG_MAX_ROUNDS_BATCH * 4, st));
         for (int r = 0; r < batch; r++)
-            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, dirty, nblk, L.nsub, round + r, changed + r);
+            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, dirty, nblk, L.nsub, round + r, changed + r, rst);
         IBT_CUDA_TRY(cudaMemcpyAsync(h_flag, changed, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
         IBT_CUDA_TRY(cudaStreamSynchronize(st));
         for (int r = 0; r < batch; r++)
@@ -821,7 +857,7 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     // 3. output block of every subsequence, coefficient pass
     rc = launch_scan(nblk, base, partial, L.nsub, 1, 0, st);
     if (rc) return rc;
-    jpg_huff_write<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, base, coef, L.nsub, (uint32_t)L.nblocks);
+    jpg_huff_write<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, base, coef, L.nsub, (uint32_t)L.nblocks, rst);
 
     // 4. DC prediction: prefix sums over MCUs per component
     jpg_dc_sums<<<(L.nmcu + 255) / 256, 256, 0, st>>>(coef, L.G, dcs, L.nmcu);

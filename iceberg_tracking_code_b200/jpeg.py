@@ -9,7 +9,7 @@ plane cv2.cvtColor would make of it, which is all the tracker consumes.
     imread(path_or_bytes, gray=True)      -> (H,W) u8 CUDA tensor         == cv2.cvtColor(that, cv2.COLOR_BGR2GRAY)
     JpegDecoder                           reusable pinned staging + device workspace (steady state allocates nothing)
 
-Files the kernels do not handle (progressive, restart markers, CMYK, 12-bit ...) raise `Unsupported`;
+Files the kernels do not handle (progressive, arithmetic coding, CMYK, 12-bit, exotic sampling) raise `Unsupported`;
 `tracking.load_image` is the caller's way out (Pillow on the host, pixels uploaded) -- the compute path itself has no
 CPU fallback.
 """
@@ -32,7 +32,7 @@ def parse(data):
     info = N.ibt_jpeg_info_t()
     rc = N.lib().ibt_jpeg_parse(C.c_void_p(buf.ctypes.data), buf.size, C.byref(info))
     if rc == N.IBT_E_UNSUPPORTED:
-        raise Unsupported("JPEG variant not handled on the GPU (progressive / restart markers / sampling / components)")
+        raise Unsupported("JPEG variant not handled on the GPU (progressive / arithmetic / sampling / components)")
     N.check(rc, "ibt_jpeg_parse")
     return info
 

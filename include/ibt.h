@@ -165,7 +165,7 @@ int ibt_polygon_mask(const double *poly_xy, int E, int H, int W, uint8_t *out, i
  *      (+ the cv2.cvtColor of s1:311 / s0_1:80 fused): baseline JPEG decoding on the GPU, bit-exact with Pillow's
  *      libjpeg-turbo defaults (islow IDCT, fancy upsampling, fixed-point YCbCr->RGB).
  *      Handled: baseline / extended sequential 8-bit Huffman (SOF0, SOF1), one interleaved scan, grey-scale or YCbCr with
- *      4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling, no restart markers.  Anything else -> IBT_E_UNSUPPORTED
+ *      4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling, with or without restart markers.  Anything else -> IBT_E_UNSUPPORTED
  *      (callers fall back to their own decoder and upload the pixels). */
 typedef struct ibt_jpeg_info {
     int32_t width, height, ncomp;                 /* ncomp 1 (grey) or 3 (YCbCr) */

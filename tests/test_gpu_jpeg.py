@@ -33,10 +33,6 @@ def expected():
 @pytest.mark.parametrize("name", NAMES)
 def test_decode_matches_pillow_golden(jpeg, ibt, oracle, expected, name):
     data = _read(name)
-    if name.startswith("dri_"):
-        with pytest.raises(jpeg.Unsupported):
-            jpeg.imread(data)
-        return
     exp = expected[name]
     out = jpeg.imread(data).cpu().numpy()
     assert out.shape == exp.shape
@@ -75,7 +71,38 @@ def test_decode_live_matrix(jpeg):
     assert n > 180
 
 
-@pytest.mark.parametrize("scene,kw", [("texture", {}), ("iceberg", {}), ("texture", dict(quality=92, subsampling=1))])
+def test_decode_restart_intervals(jpeg):
+    """DRI files (restart markers every k MCUs / rows), all samplings, odd sizes: RSTn removal, padding skip, DC reset."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(13)
+    n = 0
+    for (h, w) in [(64, 96), (37, 53), (200, 333), (9, 130)]:
+        smooth = np.cumsum(np.cumsum(rng.normal(0, 3, (h, w, 3)), 0), 1)
+        smooth = ((smooth - smooth.min()) / (np.ptp(smooth) + 1e-9) * 255).astype(np.uint8)
+        flat = np.full((h, w, 3), 77, np.uint8)
+        for img in (rng.integers(0, 256, (h, w, 3), dtype=np.uint8), smooth, flat):
+            for sub in (0, 1, 2):
+                for kw in (dict(restart_marker_blocks=1), dict(restart_marker_blocks=3), dict(restart_marker_blocks=7),
+                           dict(restart_marker_rows=1), dict(restart_marker_rows=2)):
+                    for opt in (False, True):
+                        bio = io.BytesIO()
+                        try:
+                            Image.fromarray(img).save(bio, "JPEG", quality=85, subsampling=sub, optimize=opt, **kw)
+                        except OSError:
+                            continue
+                        data = bio.getvalue()
+                        assert b"\xff\xdd" in data
+                        ref = np.array(Image.open(io.BytesIO(data)))
+                        assert np.array_equal(jpeg.imread(data).cpu().numpy(), ref), (h, w, sub, kw, opt)
+                        n += 1
+        g = smooth[..., 0]
+        bio = io.BytesIO()
+        Image.fromarray(g).save(bio, "JPEG", quality=80, restart_marker_blocks=2)
+        assert np.array_equal(jpeg.imread(bio.getvalue()).cpu().numpy(), np.array(Image.open(io.BytesIO(bio.getvalue()))))
+    assert n > 300
+
+
+@pytest.mark.parametrize("scene,kw", [("texture", dict(restart_marker_rows=1)), ("texture", {}), ("iceberg", {}), ("texture", dict(quality=92, subsampling=1))])
 def test_decode_24mp(jpeg, ibt, scene, kw):
     """BASELINE config-2 frame size: a 6000x4000 synthetic frame saved like the reference's cropping step saves it
     (imports/camtools.py:80 `img_crop.save(outpath)`), decoded here and by Pillow."""
