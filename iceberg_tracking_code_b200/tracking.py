@@ -46,27 +46,25 @@ def read_file(path):
 
 class GpuJpegLoader:
     """loader="gpu": path -> (gray CUDA tensor, ready event), the handle SequenceTracker.prepare() accepts.
-    Each decoding thread owns a jpeg.JpegDecoder and a CUDA stream, so reading + decoding frame t+k overlaps the
-    tracking kernels of frame t (the decoder's one host synchronisation blocks only its own thread)."""
+    The decode runs on its own CUDA stream: issued right after a frame's tracking kernels, its kernels (and the one
+    host wait of the Huffman convergence check) overlap that frame's work on the main stream."""
 
     def __init__(self, device, coeffset=0):
-        import threading
+        from . import jpeg as _jpeg
         self.device = device
         self.coeffset = coeffset
-        self._tls = threading.local()
+        self.dec = _jpeg.JpegDecoder(device)
+        self.stream = torch.cuda.Stream(device=device)
+
+    def decode(self, data):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            gray = self.dec.decode(data, rgb=False, gray=True, coeffset=self.coeffset)[1]   # s1:310-311 in one pass
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return gray, ev
 
     def __call__(self, path):
-        from . import jpeg as _jpeg
-        tls = self._tls
-        if not hasattr(tls, "dec"):
-            tls.dec = _jpeg.JpegDecoder(self.device)
-            tls.stream = torch.cuda.Stream(device=self.device)
-        data = read_file(path)
-        with torch.cuda.device(self.device), torch.cuda.stream(tls.stream):
-            gray = tls.dec.decode(data, rgb=False, gray=True, coeffset=self.coeffset)[1]   # s1:310-311 in one pass
-            ev = torch.cuda.Event()
-            ev.record(tls.stream)
-        return gray, ev
+        return self.decode(read_file(path))
 
 
 class FrameStager:
@@ -238,8 +236,8 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
     frames, or the string "gpu": the file bytes go to the GPU compressed and csrc/jpeg.cu decodes them (bit-exact with
     Pillow) straight into the gray plane; files it does not handle raise jpeg.Unsupported.
 
-    decode_workers: the loader (PIL JPEG decode, ~0.25 s per 24 MP frame, far slower than the GPU step; or the file
-    read of the "gpu" loader) runs in a thread pool that keeps `decode_workers` frames ahead of the tracker; the order
+    decode_workers: the loader (PIL JPEG decode, ~0.25 s per 24 MP frame, far slower than the GPU step; for the "gpu"
+    loader only the file read) runs in a thread pool that keeps `decode_workers` frames ahead of the tracker; the order
     of processing is unchanged."""
     T = int(track_len)
     trk = tracker or SequenceTracker(feature_params, lk_params)
@@ -247,6 +245,8 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         if loader != "gpu":
             raise ValueError("loader must be a callable, None or 'gpu'")
         loader = GpuJpegLoader(trk.device)
+    gpu = loader if isinstance(loader, GpuJpegLoader) else None
+    host_loader = read_file if gpu is not None else loader          # what the thread pool runs
     if mask is not None:
         mask = cv._to_dev(mask, np.uint8, "mask")
     results = []
@@ -261,23 +261,30 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         seed_idx = None
         counters = range(g0 * T, g1 * T + 1)
         pool, pending = None, {}
-        if loader is not None and decode_workers and decode_workers > 1:
+        if host_loader is not None and decode_workers and decode_workers > 1:
             from concurrent.futures import ThreadPoolExecutor
             pool = ThreadPoolExecutor(max_workers=int(decode_workers))
             for c in counters[:decode_workers]:
-                pending[c] = pool.submit(loader, frames[c])
-        for counter in counters:
-            item = frames[counter]
+                pending[c] = pool.submit(host_loader, frames[c])
+
+        def fetch(c):
+            """frame c as prepare() takes it (host array, device tensor, or (device tensor, event) from the GPU decoder)"""
             if pool is not None:
-                nxt = counter + decode_workers
+                nxt = c + decode_workers
                 if nxt <= counters[-1]:
-                    pending[nxt] = pool.submit(loader, frames[nxt])
-                decoded = pending.pop(counter).result()
+                    pending[nxt] = pool.submit(host_loader, frames[nxt])
+                data = pending.pop(c).result()
             else:
-                decoded = loader(item) if loader is not None else item
-            cur = trk.prepare(decoded)
+                data = host_loader(frames[c]) if host_loader is not None else frames[c]
+            return gpu.decode(data) if gpu is not None else data
+
+        upcoming = fetch(counters[0])
+        for counter in counters:
+            cur = trk.prepare(upcoming)
             if prev is not None and trk.n > 0:
                 trk.track(prev, cur)
+            # the next frame is fetched now: a GPU decode (side stream, one host wait) overlaps this frame's kernels
+            upcoming = fetch(counter + 1) if counter < counters[-1] else None
             if (counter - g0 * T) % T == 0:
                 if seed_idx is not None:
                     tracks, quality = trk.harvest()
