@@ -67,6 +67,9 @@ SIGNATURES = {
     "ibt_photo_to_utm": (_i, [_vp, _i64, C.POINTER(C.c_double), _vp, _vp]),
     "ibt_track_velocities": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "ibt_polygon_mask": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp]),
+    "ibt_grid_bin_workspace_bytes": (_i64, [_i64, _i, _i]),
+    "ibt_grid_bin": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ibt_points_in_polygon": (_i, [_vp, _i, _vp, _i64, _vp, _vp]),
     "ibt_jpeg_parse": (_i, [_vp, _i64, _JPG]),
     "ibt_jpeg_workspace_bytes": (_i64, [_JPG]),
     "ibt_jpeg_decode": (_i, [_vp, _JPG, _vp, _i64, _vp, _i64, _vp, _i64, _i, C.POINTER(C.c_int), _vp]),

@@ -109,6 +109,11 @@ inline bool make_map_2d(CUtensorMap *m, CUtensorMapDataType dt, const void *base
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// gftt.cu: stable LSD radix sort of 64-bit keys on a byte range (also used by grid.cu)
+size_t radix_sort_scratch_words(uint32_t n);
+unsigned long long *radix_sort_u64_bytes(unsigned long long *keys0, unsigned long long *keys1, uint32_t n, int first_byte,
+                                         int last_byte, uint32_t *scratch, cudaStream_t st);
+
 constexpr int kNumSMs = 148;             // B200: 2 dies x 74 SMs
 
 } // namespace ibt

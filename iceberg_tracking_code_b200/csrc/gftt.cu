@@ -393,6 +393,29 @@ rs_scatter_kernel(const unsigned long long *__restrict__ src, unsigned long long
     }
 }
 
+// Stable LSD radix sort of n 64-bit keys on bytes [first_byte, last_byte] (shared with grid.cu).  keys0 holds the input,
+// keys1 is the ping-pong buffer; returns the buffer that holds the result.  scratch: radix_sort_scratch_words(n) uint32.
+size_t radix_sort_scratch_words(uint32_t n)
+{
+    const size_t nblocks = ((size_t)n + RS_TILE - 1) / RS_TILE;
+    return 256 * nblocks + (256 * nblocks) / SCAN_TILE + 4;
+}
+unsigned long long *radix_sort_u64_bytes(unsigned long long *keys0, unsigned long long *keys1, uint32_t n, int first_byte,
+                                         int last_byte, uint32_t *scratch, cudaStream_t st)
+{
+    if (n <= 1) return keys0;
+    const uint32_t nblocks = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t *blockhist = scratch, *scan_scratch = scratch + 256 * (size_t)nblocks;
+    unsigned long long *src = keys0, *dst = keys1;
+    for (int p = first_byte; p <= last_byte; p++) {
+        rs_count_kernel<<<nblocks, 256, 0, st>>>(src, n, 8 * p, nblocks, blockhist);
+        scan_u32(blockhist, 256u * nblocks, nullptr, scan_scratch, st);
+        rs_scatter_kernel<<<nblocks, 256, 0, st>>>(src, dst, n, 8 * p, nblocks, blockhist);
+        unsigned long long *t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
 // After the stable sort on the response bytes, equal responses keep their arrival order: order each run of equal
 // responses by address (complemented keys ascending = address descending, OpenCV's tie-break).  Runs are rare and short;
 // the first element of a run sorts it.

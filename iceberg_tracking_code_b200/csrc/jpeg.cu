@@ -28,7 +28,6 @@ namespace ibt {
 constexpr int JPG_S = 1024;              // subsequence length, bits
 constexpr int JPG_LUT_BITS = 10;
 constexpr int JPG_CHUNK = 4096;          // destuff: bytes per CTA (256 threads x 16)
-constexpr int JPG_MAX_BLK = 10;          // blocks per MCU (T.81 B.2.3)
 
 struct __align__(16) JpgTables {          // device copy in the workspace (~27 KB): one (DC, AC) table pair per component
     uint32_t lut[6][1 << JPG_LUT_BITS];  // [comp*2 + ac]: symbol | len << 8 | (len + extra bits) << 16; 0 = longer code

@@ -192,6 +192,20 @@ int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *info, void *wo
                     uint8_t *rgb, int64_t rgb_pitch, uint8_t *gray, int64_t gray_pitch, int coeffset,
                     int *out_rounds, void *stream);
 
+/* ---- s3 consumer: the cell-binning loop of s3_utm_to_gridded_utm.py:391-421 over the square grid of
+ *      imports/tracking_misc.py:25-58.  Cell (i, j), i < cols, j < rows, is the square with top-left corner
+ *      (topleft_x + i*spacing, topleft_y - j*spacing); membership is matplotlib.path.Path(poly).contains_points (radius 0).
+ *      x, y, u, v: (n) f64 each.  Outputs indexed i*rows + j: count (observations in the cell), sum_u, sum_v =
+ *      np.sum of the selected displacements in point order (numpy's pairwise summation, bit-exact). */
+int64_t ibt_grid_bin_workspace_bytes(int64_t n, int cols, int rows);
+int ibt_grid_bin(const double *x, const double *y, const double *u, const double *v, int64_t n,
+                 double topleft_x, double topleft_y, double spacing, int cols, int rows,
+                 void *workspace, int64_t workspace_bytes,
+                 int32_t *count, double *sum_u, double *sum_v, void *stream);
+/* matplotlib.path.Path(poly).contains_points(pts) (radius 0; polygon implicitly closed; 3 <= E <= 4096), e.g. the
+ * cell centres inside the fjord outline, imports/tracking_misc.py:34-52.  poly_xy (E,2) f64, pts_xy (n,2) f64, out (n) u8. */
+int ibt_points_in_polygon(const double *poly_xy, int E, const double *pts_xy, int64_t n, uint8_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -258,3 +258,50 @@ def imread_jpeg(data):
     if rc != 0:
         raise ValueError("oracle: JPEG decode failed (%d)" % rc)
     return out
+
+
+# ---- s3 gridding (numpy restatement of s3_utm_to_gridded_utm.py:391-421 + imports/tracking_misc.py:15-58) -----------------
+def contains_points(poly, points):
+    """matplotlib.path.Path(poly).contains_points(points), radius 0: the even-odd "crossings" rule of matplotlib's
+    src/_path.h point_in_path_impl (polygon implicitly closed), elementwise fp64."""
+    v = np.asarray(poly, np.float64).reshape(-1, 2)
+    p = np.asarray(points, np.float64).reshape(-1, 2)
+    tx, ty = p[:, 0], p[:, 1]
+    inside = np.zeros(len(p), bool)
+    for e in range(len(v)):
+        v0, v1 = v[e], v[(e + 1) % len(v)]
+        yflag0, yflag1 = v0[1] >= ty, v1[1] >= ty
+        cross = ((v1[1] - ty) * (v0[0] - v1[0]) >= (v1[0] - tx) * (v0[1] - v1[1])) == yflag1
+        inside ^= (yflag0 != yflag1) & cross
+    return inside
+
+
+def grid_cells(fjord_x, fjord_y, spacing):
+    """tracking_misc.py:25-58: (polygons, centerpoints, indices, rows, cols) of the cells whose centre is in the fjord."""
+    import math
+    topleft = [min(fjord_x), max(fjord_y)]
+    cols = int(math.ceil((max(fjord_x) - min(fjord_x)) / spacing))
+    rows = int(math.ceil((max(fjord_y) - min(fjord_y)) / spacing))
+    fj = np.vstack((fjord_x, fjord_y)).T
+    polys, cents, idx = [], [], []
+    for i in range(cols):
+        for j in range(rows):
+            x, y = topleft[0] + i * spacing, topleft[1] - j * spacing
+            point = [x + 0.5 * spacing, y - 0.5 * spacing]
+            if contains_points(fj, [point])[0]:
+                polys.append([(x, y), (x + spacing, y), (x + spacing, y - spacing), (x, y - spacing)])
+                cents.append(point)
+                idx.append([i, j])
+    return polys, cents, idx, rows, cols
+
+
+def grid_bin(polys, x, y, u, v):
+    """s3:391-411 per cell polygon: (count, np.sum(u_selected), np.sum(v_selected))."""
+    points = np.vstack((x, y)).T
+    disp = np.vstack((u, v)).T
+    out = []
+    for poly in polys:
+        sel = contains_points(poly, points)
+        d = disp[sel == 1]
+        out.append((len(d), np.sum(d[:, 0]), np.sum(d[:, 1])))
+    return out
