@@ -48,8 +48,9 @@ def pack_results(results, track_len):
 
 
 def unpack_results(meta, tracks, quality):
+    """tracks / quality may be numpy arrays or torch tensors (device-resident gather): groups are views into them."""
     out, o = [], 0
-    for seed, m in meta.tolist():
+    for seed, m in (meta.tolist() if hasattr(meta, "tolist") else meta):
         if m:
             out.append((int(seed), tracks[o:o + m], quality[o:o + m]))
         else:
@@ -58,10 +59,12 @@ def unpack_results(meta, tracks, quality):
     return out
 
 
-def gather_results(results, track_len, device=None):
+def gather_results(results, track_len, device=None, to_host=True):
     """The single collective of the path: every rank contributes its groups' track arrays; returns, on EVERY rank,
     the list [(seed_index, tracks, trackquality)] of all ranks in time order (all_gather of sizes, then all_gather of
-    the padded payloads).  Without an initialised process group this is the identity."""
+    the padded payloads).  Without an initialised process group this is the identity.
+    to_host=False leaves the gathered payloads on the device (the groups are views into one CUDA tensor per array):
+    copying 8 ranks' worth of a day (0.6 GB) into fresh host memory costs more than tracking the day."""
     import torch.distributed as dist
     meta, tracks, quality = pack_results(results, track_len)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -79,17 +82,23 @@ def gather_results(results, track_len, device=None):
     def padded(a, n, dtype):
         t = torch.zeros((n,) + a.shape[1:], dtype=dtype, device=device)
         if a.shape[0]:
-            t[:a.shape[0]] = torch.from_numpy(a).to(device)
+            t[:a.shape[0]] = torch.from_numpy(a).to(device, non_blocking=True)
         return t
 
-    def allg(t):
-        out = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        return [o.cpu().numpy() for o in out]
+    def allg(t, host=True):
+        """one collective into a tensor concatenated along dim 0; returns the per-rank slices"""
+        n = t.shape[0]
+        if n == 0:
+            return [t.cpu().numpy() if host else t] * world
+        out = torch.empty((world * n,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+        dist.all_gather_into_tensor(out, t)
+        if host:
+            out = out.cpu().numpy()
+        return [out[r * n:(r + 1) * n] for r in range(world)]
 
     metas = allg(padded(meta, gmax, torch.int64))
-    trs = allg(padded(tracks, mmax, torch.float32)) if mmax else [np.zeros((0, T + 1, 2), np.float32)] * world
-    qus = allg(padded(quality, mmax, torch.float32)) if mmax else [np.zeros((0, T), np.float32)] * world
+    trs = allg(padded(tracks, mmax, torch.float32), to_host) if mmax else [np.zeros((0, T + 1, 2), np.float32)] * world
+    qus = allg(padded(quality, mmax, torch.float32), to_host) if mmax else [np.zeros((0, T), np.float32)] * world
     out = []
     for r in range(world):
         g, m = int(all_sizes[r, 0]), int(all_sizes[r, 1])

@@ -6,7 +6,7 @@ NCCL gather of all tracks; with UTM=1 every track vertex is also projected to ma
 
 Each rank synthesises the frames of its own block ON DEVICE before the timed region (180 frames + 1 halo = 13 GB of
 RGB per rank at N=8); nothing is shipped from the host.  Timed: gray, pyramids, GFTT, LK fwd/bwd/FB, compaction, D2H of
-every group's tracks, and the gather.  Device time = max over ranks (barrier + synchronize on both sides)."""
+every group's tracks, and the gather (payloads stay on the device unless GATHER_HOST=1).  Time = max over ranks (barrier + synchronize on both sides)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -57,8 +57,10 @@ if os.environ.get("UTM", "0") == "1":
                 utm_vertices += tracks.shape[0] * tracks.shape[1]
         torch.cuda.synchronize()
 t_utm = time.perf_counter() - t0 - t_track
-allres = sh.gather_results(res, T) if world > 1 else [(s, t, q) for s, _p, t, q in res]
+tg0 = time.perf_counter()
+allres = sh.gather_results(res, T, to_host=os.environ.get('GATHER_HOST', '0') == '1') if world > 1 else [(s, t, q) for s, _p, t, q in res]
 torch.cuda.synchronize()
+t_gather = time.perf_counter() - tg0
 if world > 1:
     dist.barrier()
 dt = time.perf_counter() - t0
@@ -72,6 +74,6 @@ if rank == 0:
                       "world": world, "groups": len(allres), "tracks_gathered": ntracks, "frame_pairs": pairs,
                       "seconds": float(tt[0]), "track_seconds_max_rank": float(tt[1]),
                       "frames_per_s": pairs / float(tt[0]), "tracked_points_per_s": ntracks * T / float(tt[0]),
-                      "utm_vertices_rank0": utm_vertices, "utm_seconds_rank0": t_utm}))
+                      "utm_vertices_rank0": utm_vertices, "utm_seconds_rank0": t_utm, "gather_seconds_rank0": t_gather}))
 if world > 1:
     dist.destroy_process_group()
