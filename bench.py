@@ -404,7 +404,7 @@ def main():
         frames_np = [f.numpy() for f in host_frames]
         grays_np = [g.cpu().numpy() for g in grays]
         pts_np = [p.cpu().numpy().reshape(-1, 1, 2) for p in pts]
-        cb, _, _ = run_cpu(frames_np, grays_np, pts_np, steps=30, warmup=1, budget_s=15.0)
+        cb, _, _ = run_cpu(frames_np, grays_np, pts_np, steps=100, warmup=1, budget_s=12.0)
         out["cpu_baseline"] = cb
     print(json.dumps(out))
     if dist is not None:

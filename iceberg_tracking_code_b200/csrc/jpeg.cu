@@ -48,6 +48,7 @@ struct JpgGeom {
     int pw[3], ph[3];                    // plane size (samples, whole blocks)
     int dw[3], dh[3];                    // real downsampled size
     int hmax, vmax;
+    int hsub[3], vsub[3];                // hmax / hs[c], vmax / vs[c] (1 or 2)
     int restart_interval;                // MCUs per restart interval (0 = none): DC predictions restart there
     uint8_t *plane[3];
     uint16_t quant[3][64];               // per component, natural order
@@ -382,7 +383,7 @@ __device__ __forceinline__ void idct8(int i0, int i1, int i2, int i3, int i4, in
     o[2] = (tmp12 + tmp1 + R) >> SHIFT; o[5] = (tmp12 - tmp1 + R) >> SHIFT;
     o[3] = (tmp13 + tmp0 + R) >> SHIFT; o[4] = (tmp13 - tmp0 + R) >> SHIFT;
 }
-__device__ __forceinline__ uint32_t sat_u8(int v) { return (uint32_t)min(max(v, 0), 255); }
+__device__ __forceinline__ uint32_t sat_u8(int v) { return (uint32_t)__vimin_s32_relu(v, 255); }     // max(min(v, 255), 0), one VIMNMX
 
 // one thread per block, blocks numbered in plane order per component (component 0 first)
 __global__ void __launch_bounds__(128) jpg_idct(const int16_t *__restrict__ coef, const uint32_t *__restrict__ dcpre,
@@ -450,12 +451,13 @@ __device__ __forceinline__ void chroma_row6(const uint8_t *__restrict__ row, int
         for (int j = 0; j < 6; j++) v[j] = row[min(max(cx0 - 1 + j, 0), dw - 1)];
     }
 }
-// 8 chroma samples for pixels x0..x0+7 (x0 a multiple of 8) of row y
+// 8 chroma samples for pixels x0..x0+7 (x0 a multiple of 8) of row y; HSUB x VSUB = luma samples per chroma sample
+template <int HSUB, int VSUB>
 __device__ __forceinline__ void chroma8(const JpgGeom &G, int c, int x0, int y, int *out)
 {
     const uint8_t *P = G.plane[c];
     const int pw = G.pw[c], dw = G.dw[c], dh = G.dh[c];
-    const int hsub = G.hmax / G.hs[c], vsub = G.vmax / G.vs[c];
+    constexpr int hsub = HSUB, vsub = VSUB;
     if (hsub == 1) {
         const uint2 w = *reinterpret_cast<const uint2 *>(P + (size_t)y * pw + x0);
 #pragma unroll
@@ -496,7 +498,7 @@ __device__ __forceinline__ void chroma8(const JpgGeom &G, int c, int x0, int y, 
     }
 }
 
-template <int SH>
+template <int SH, int NCOMP, int HSUB, int VSUB>
 __global__ void __launch_bounds__(256) jpg_color(const __grid_constant__ JpgGeom G, uint8_t *__restrict__ rgb, int64_t rgb_pitch,
                                                  uint8_t *__restrict__ gray, int64_t gray_pitch, int k0, int k1, int k2)
 {
@@ -505,13 +507,13 @@ __global__ void __launch_bounds__(256) jpg_color(const __grid_constant__ JpgGeom
     if (x0 >= G.W) return;
     const uint2 yw = *reinterpret_cast<const uint2 *>(G.plane[0] + (size_t)y * G.pw[0] + x0);
     uint32_t R[8], Gc[8], B[8], g[8];
-    if (G.ncomp == 1) {
+    if (NCOMP == 1) {
 #pragma unroll
         for (int j = 0; j < 8; j++) g[j] = ((j < 4 ? yw.x : yw.y) >> (8 * (j & 3))) & 255u;
     } else {
         int cb[8], cr[8];
-        chroma8(G, 1, x0, y, cb);
-        chroma8(G, 2, x0, y, cr);
+        chroma8<HSUB, VSUB>(G, 1, x0, y, cb);
+        chroma8<HSUB, VSUB>(G, 2, x0, y, cr);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int Y = (int)(((j < 4 ? yw.x : yw.y) >> (8 * (j & 3))) & 255u), b = cb[j] - 128, r = cr[j] - 128;
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(256) jpg_color(const __grid_constant__ JpgGeom
         else
             for (int j = 0; j < 8 && x0 + j < G.W; j++) d[j] = (uint8_t)g[j];
     }
-    if (rgb && G.ncomp == 3) {
+    if (NCOMP == 3 && rgb) {
         uint8_t *d = rgb + (size_t)y * rgb_pitch + (size_t)x0 * 3;
         if (full && ((reinterpret_cast<uintptr_t>(d) & 7) == 0)) {
             uint2 *w = reinterpret_cast<uint2 *>(d);
@@ -598,6 +600,7 @@ static void jpeg_layout(const ibt_jpeg_info_t *I, JpgLayout &L)
         G.pw[c] = G.bw[c] * 8; G.ph[c] = G.bh[c] * 8;
         G.dw[c] = (G.W * G.hs[c] + G.hmax - 1) / G.hmax;
         G.dh[c] = (G.H * G.vs[c] + G.vmax - 1) / G.vmax;
+        G.hsub[c] = G.hmax / G.hs[c]; G.vsub[c] = G.vmax / G.vs[c];
         for (int i = 0; i < 64; i++) G.quant[c][i] = I->quant[I->qsel[c]][i];
     }
     G.nblk_mcu = off;
@@ -866,9 +869,16 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     // 5. inverse DCT into the component planes, 6. upsampling + colour conversion (+ gray)
     jpg_idct<<<(L.nblocks + 127) / 128, 128, 0, st>>>(coef, dcpre, L.G, L.nmcu, L.nblocks);
     const dim3 cgrid((unsigned)((I->width + 8 * 256 - 1) / (8 * 256)), (unsigned)I->height);
-    if (coeffset == IBT_GRAY_CV4_15BIT)
-        jpg_color<15><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, 3735, 19235, 9798);
-    else
-        jpg_color<14><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, 1868, 9617, 4899);
+    const int mode = I->ncomp == 1 ? 0 : (L.G.hmax == 1 ? 1 : (L.G.vmax == 1 ? 2 : 3));        // grey, 4:4:4, 4:2:2, 4:2:0
+#define IBT_JPG_COLOR(SH, K0, K1, K2)                                                                                              \
+    switch (mode) {                                                                                                                \
+    case 0: jpg_color<SH, 1, 1, 1><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, K0, K1, K2); break;           \
+    case 1: jpg_color<SH, 3, 1, 1><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, K0, K1, K2); break;           \
+    case 2: jpg_color<SH, 3, 2, 1><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, K0, K1, K2); break;           \
+    default: jpg_color<SH, 3, 2, 2><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, K0, K1, K2); break;          \
+    }
+    if (coeffset == IBT_GRAY_CV4_15BIT) { IBT_JPG_COLOR(15, 3735, 19235, 9798) }
+    else { IBT_JPG_COLOR(14, 1868, 9617, 4899) }
+#undef IBT_JPG_COLOR
     return check_launch("ibt_jpeg_decode");
 }

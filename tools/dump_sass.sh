@@ -11,6 +11,6 @@ dump "eig_kernel" eig_kernel
 dump "cull_round_kernel" cull_round_kernel
 dump "jpg_sync_round" jpg_sync_round
 dump "jpg_idct" jpg_idct
-dump "jpg_colorILi15" jpg_color
+dump "jpg_colorILi15ELi3ELi2ELi2" jpg_color
 cuobjdump -sass "$SO" | grep -oE "^\s+/\*[0-9a-f]+\*/\s+(@!?U?P[0-9T]+\s+)?[A-Z0-9_.]+" | awk '{print $NF}' | grep -E "^(IDP|LDGSTS|REDUX|UTMA|UBLKCP|HMMA|UTC)" | sort | uniq -c | sort -rn > profiles/sass/opcode_evidence.txt
 cat profiles/sass/opcode_evidence.txt
