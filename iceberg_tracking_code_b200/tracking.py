@@ -236,9 +236,9 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
     frames, or the string "gpu": the file bytes go to the GPU compressed and csrc/jpeg.cu decodes them (bit-exact with
     Pillow) straight into the gray plane; files it does not handle raise jpeg.Unsupported.
 
-    decode_workers: the loader (PIL JPEG decode, ~0.25 s per 24 MP frame, far slower than the GPU step; for the "gpu"
-    loader only the file read) runs in a thread pool that keeps `decode_workers` frames ahead of the tracker; the order
-    of processing is unchanged."""
+    decode_workers: a host loader (PIL JPEG decode, ~0.25 s per 24 MP frame, far slower than the GPU step) runs in a
+    thread pool that keeps `decode_workers` frames ahead of the tracker; the order of processing is unchanged.  Ignored
+    by the "gpu" loader (its decode is pipelined on a CUDA stream instead)."""
     T = int(track_len)
     trk = tracker or SequenceTracker(feature_params, lk_params)
     if isinstance(loader, str):
@@ -261,7 +261,8 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         seed_idx = None
         counters = range(g0 * T, g1 * T + 1)
         pool, pending = None, {}
-        if host_loader is not None and decode_workers and decode_workers > 1:
+        # (the "gpu" loader reads the few MB of a file in the calling thread: a pool only adds GIL contention there)
+        if host_loader is not None and gpu is None and decode_workers and decode_workers > 1:
             from concurrent.futures import ThreadPoolExecutor
             pool = ThreadPoolExecutor(max_workers=int(decode_workers))
             for c in counters[:decode_workers]:

@@ -28,8 +28,7 @@ gp = dict(maxCorners=maxc, qualityLevel=0.007, minDistance=10, blockSize=10)
 lp = dict(winSize=(31, 31), maxLevel=4, criteria=(3, 30, 0.01))
 out = {"frames": NF, "jpeg_mb_per_frame": mb}
 ref_res = None
-for name, kw in (("gpu", dict(loader="gpu", decode_workers=int(os.environ.get("DW", 3)))),
-                 ("gpu_serial", dict(loader="gpu", decode_workers=0)),
+for name, kw in (("gpu", dict(loader="gpu")),
                  ("pillow", dict(loader=load_image, decode_workers=os.cpu_count()))):
     trk = SequenceTracker(gp, lp)
     best = None
