@@ -140,3 +140,25 @@ def test_sequence_from_jpeg_files_on_gpu(jpeg, ibt, golden):
         assert a[0] == b[0]
         assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert "counts" in exp or True
+
+
+def test_corrupt_streams_terminate(jpeg):
+    """Truncated and bit-flipped entropy data: the speculative decoder must terminate and return an image of the right shape
+    (Pillow raises / returns grey for such files; there is no defined pixel content to compare)."""
+    data = bytearray(_read("tex_420_default"))
+    info = jpeg.parse(bytes(data))
+    lo, n = info.scan_offset, info.scan_bytes
+    rng = np.random.default_rng(3)
+    cases = [bytes(data[:lo + n // 2]) + b"\xff\xd9", bytes(data[:lo + 5]) + b"\xff\xd9"]
+    for _ in range(4):
+        d = bytearray(data)
+        for p in rng.integers(lo, lo + n, 40):
+            d[p] = int(rng.integers(0, 255))          # never 0xFF: a stray marker would end the scan early (also fine)
+        cases.append(bytes(d))
+    garbage = bytearray(data)
+    garbage[lo:lo + n] = bytes(int(v) for v in rng.integers(0, 255, n))
+    cases.append(bytes(garbage))
+    for c in cases:
+        out = jpeg.imread(c)
+        assert tuple(out.shape) == (info.height, info.width, 3)
+        assert int(out.sum().item()) >= 0                 # forces completion
