@@ -49,16 +49,23 @@ class GpuJpegLoader:
     The decode runs on its own CUDA stream: issued right after a frame's tracking kernels, its kernels (and the one
     host wait of the Huffman convergence check) overlap that frame's work on the main stream."""
 
-    def __init__(self, device, coeffset=0):
+    def __init__(self, device, coeffset=0, crop_box=None):
+        """crop_box = (left, upper, right, lower) as PIL's Image.crop takes it (camtools.py:79): the decoded plane is cropped
+        as a view on the device instead of decoding a cropped, re-encoded copy of the file (see
+        lucaskanade_tracking(crop="view"))."""
         from . import jpeg as _jpeg
         self.device = device
         self.coeffset = coeffset
+        self.crop_box = None if crop_box is None else tuple(int(v) for v in crop_box)
         self.dec = _jpeg.JpegDecoder(device)
         self.stream = torch.cuda.Stream(device=device)
 
     def decode(self, data):
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             gray = self.dec.decode(data, rgb=False, gray=True, coeffset=self.coeffset)[1]   # s1:310-311 in one pass
+            if self.crop_box is not None:
+                l, u, r, b = self.crop_box
+                gray = gray[u:b, l:r].contiguous()
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return gray, ev
@@ -310,10 +317,17 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
 
 
 def lucaskanade_tracking(file_path, ws_source, ws_target, camname, track_len, track_len_sec, startlist, mask_switch,
-                         plot_switch, movie_switch, delete_jpgs_switch, paramfile_path, n_proc, camera=None):
+                         plot_switch, movie_switch, delete_jpgs_switch, paramfile_path, n_proc, camera=None, crop="reencode"):
     """Same positional signature as s1_lucaskanade_tracking.py:234-236; side effect = the .npz files of SURVEY A.8.
     `camera` (keyword, optional) injects a ready camera.Camera instead of reading `paramfile_path`.
-    plot_switch / movie_switch / delete_jpgs_switch are accepted and ignored (matplotlib / mencoder work, out of scope)."""
+    plot_switch / movie_switch / delete_jpgs_switch are accepted and ignored (matplotlib / mencoder work, out of scope).
+
+    crop="reencode" (default) is the reference: every source frame is decoded, cropped and re-saved as a JPEG by Pillow
+    (camtools.py:237-258, ~0.3 s of host time per 24 MP frame) and the tracker reads those files -- the lossy re-encode is
+    part of the pixels the reference tracks, so this is the mode whose tracks equal the reference's.
+    crop="view"  decodes the SOURCE files on the GPU and crops the plane as a view: no host decode, no
+    re-encode, no second generation of JPEG loss -- tracks differ slightly from the reference's by construction; the .npz
+    files are named after <ws_target>/<frame>.jpg exactly as in the other mode."""
     from .camera import Camera
     ws_source, ws_target = str(ws_source), str(ws_target)
     datestring = osp.basename(ws_source)
@@ -323,9 +337,24 @@ def lucaskanade_tracking(file_path, ws_source, ws_target, camname, track_len, tr
         return
     if not osp.isdir(ws_target):
         os.makedirs(ws_target)
+    from . import jpeg as _jpeg
+    if crop == "view":
+        l, u, r, b = (int(v) for v in cam.crop_box())
+        h, w = b - u, r - l
+        if mask_switch == 1:
+            mask = cam.mask_image(h, w)
+        else:
+            mask = np.full((h, w), 255, np.uint8)
+        tracker = SequenceTracker()
+        sources = {osp.join(ws_target, osp.basename(p)): p for p in imagelist}
+        gpu = GpuJpegLoader(tracker.device, crop_box=(l, u, r, b))
+        track_sequence(sorted(sources), mask, track_len, track_len_sec, startlist, tracker=tracker,
+                       loader=lambda name: gpu(sources[name]), decode_workers=0)
+        return
+    if crop != "reencode":
+        raise ValueError("crop must be 'reencode' or 'view'")
     cam.crop_image_parallel(imagelist, ws_target, n_proc)              # s1:272
     imagelist = sorted(glob.glob(ws_target + '/*.jpg'))                # s1:278
-    from . import jpeg as _jpeg
     info = _jpeg.parse(read_file(imagelist[0]))
     h, w = info.height, info.width
     if mask_switch == 1:                                               # s1:285-294

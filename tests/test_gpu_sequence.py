@@ -146,6 +146,16 @@ def test_lucaskanade_tracking_signature(ibt, oracle, tmp_path):
     z = np.load(files[0])
     assert z["tracks"].shape == ref[0][0].shape and np.abs(z["tracks"] - ref[0][0]).max() <= 0.01
 
+    # crop="view" (SURVEY 8f-1): source files decoded on the GPU and cropped as a view -- no re-encoded copies are written,
+    # same .npz name, tracks = the s1 loop on the cropped PIXELS OF THE SOURCE frames (no second JPEG generation)
+    tgt2 = tmp_path / "out2" / "cam1" / "oblique" / "20190724"
+    trk.lucaskanade_tracking(str(tmp_path), str(src), str(tgt2), "cam1", 2, 60, [0], 1, 0, 0, 0, str(pf), 1, crop="view")
+    assert [f.name for f in sorted(tgt2.iterdir())] == ["20190724-130000_120sec_at_60sec_tracks.npz"]
+    view = [f[10:h - 20, 16:w - 8] for f in frames[:3]]
+    ref2 = s1_loop_oracle(oracle, view, ref_mask, 2, trk.FEATURE_PARAMS, trk.LK_PARAMS)
+    z2 = np.load(tgt2 / "20190724-130000_120sec_at_60sec_tracks.npz")
+    assert z2["tracks"].shape == ref2[0][0].shape and np.abs(z2["tracks"] - ref2[0][0]).max() <= 0.01
+
 
 def crossing_mask(poly, xs, ys):
     """numpy restatement of the crossing-number rule matplotlib's Path.contains_points applies (camtools.py:208-209)."""
