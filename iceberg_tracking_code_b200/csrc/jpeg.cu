@@ -895,7 +895,9 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
         jpg_sync_init<<<(L.nsub + 255) / 256, 256, 0, st>>>(start, dirty, L.nsub);
     }
     const int sync_ctas = (L.nsub + 127) / 128;
+    // first batch: the caller's hint (rounds the previous, similar file needed) + 2, else 8
     int round = 0, batch = 8, rounds_used = -1;
+    if (out_rounds && *out_rounds > 0) batch = *out_rounds + 2 > JPG_MAX_ROUNDS_BATCH ? JPG_MAX_ROUNDS_BATCH : *out_rounds + 2;
     while (rounds_used < 0) {
         IBT_CUDA_TRY(cudaMemsetAsync(changed, 0, JPG_MAX_ROUNDS_BATCH * 4, st));
         for (int r = 0; r < batch; r++)

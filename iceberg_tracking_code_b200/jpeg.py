@@ -83,7 +83,7 @@ class JpegDecoder:
             dfile = self._stage(buf)
             out_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=self.device) if rgb else None
             out_gray = torch.empty((H, W), dtype=torch.uint8, device=self.device) if gray else None
-            rounds = C.c_int(0)
+            rounds = C.c_int(self.last_rounds)         # hint: consecutive frames of a sequence need about the same
             N.check(N.lib().ibt_jpeg_decode(cv._ptr(dfile), C.byref(info), cv._ptr(self._ws), self._ws.numel(),
                                             cv._ptr(out_rgb), W * 3, cv._ptr(out_gray), W, int(coeffset),
                                             C.byref(rounds), cv._stream()), "ibt_jpeg_decode")

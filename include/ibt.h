@@ -186,8 +186,9 @@ int64_t ibt_jpeg_workspace_bytes(const ibt_jpeg_info_t *info);
 /* d_file: the whole file in DEVICE memory (4-byte aligned).  info: HOST.  workspace: 256-byte aligned.
  * rgb (H,W,3) u8 = what np.array(Image.open(f)) holds (NULL to skip; must be NULL for grey-scale files);
  * gray (H,W) u8 = cv2.cvtColor(that, COLOR_BGR2GRAY) with the reference's channel order (NULL to skip; for a
- * grey-scale file: the decoded plane).  coeffset as ibt_gray_u8.  out_rounds: HOST int* or NULL, receives the number
- * of Huffman synchronisation rounds.  SYNCHRONISES `stream` (convergence of the speculative Huffman decode). */
+ * grey-scale file: the decoded plane).  coeffset as ibt_gray_u8.  out_rounds: HOST int* or NULL, in/out: on entry a hint
+ * (> 0: rounds a similar file needed; sizes the first batch of rounds), on return the number of Huffman synchronisation
+ * rounds this file needed.  SYNCHRONISES `stream` (convergence of the speculative Huffman decode). */
 int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *info, void *workspace, int64_t workspace_bytes,
                     uint8_t *rgb, int64_t rgb_pitch, uint8_t *gray, int64_t gray_pitch, int coeffset,
                     int *out_rounds, void *stream);
