@@ -87,6 +87,11 @@ for g, (seed, t, q) in enumerate(out):
         assert np.array_equal(t, rng.random((m, T + 1, 2)).astype(np.float32)) and np.array_equal(q, rng.random((m, T)).astype(np.float32))
     else:
         assert t.shape == (0,)
+# payloads left where the collective put them (to_host=False): same groups, tensor views
+out2 = sh.gather_results(res, T, to_host=False)
+assert [o[0] for o in out2] == [o[0] for o in out]
+for (s1, t1, q1), (s2, t2, q2) in zip(out, out2):
+    assert np.array_equal(np.asarray(t1), np.asarray(t2)) and np.array_equal(np.asarray(q1), np.asarray(q2))
 dist.destroy_process_group()
 sys.stdout.write("rank " + str(rank) + " ok\n"); sys.stdout.flush()
 '''
