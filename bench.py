@@ -397,7 +397,13 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            out["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            tf = json.load(open(traffic_file))
+            out["roofline"]["traffic"] = tf.get("dram_bytes_per_launch")
+            if tf.get("ncu_launch_us"):
+                # for information: the kernel's own duration under ncu (no event / launch gap around a ~22 us kernel);
+                # "achieved" and "frac" above stay the CUDA-event figures measured in this run
+                out["roofline"]["ncu_launch_ms"] = tf["ncu_launch_us"] * 1e-3
+                out["roofline"]["frac_at_ncu_duration"] = k1_bytes / (tf["ncu_launch_us"] * 1e-6) / 1e9 / peak
         except Exception:                           # noqa: BLE001
             pass
     if world == 1 and not args.no_cpu_baseline:
