@@ -87,3 +87,8 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "ibt_oracle" not in src, f
                 assert "import cv2" not in src, f
+    # tools/ are measurement scripts around the product path: they must not execute the oracle either
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f

@@ -264,6 +264,35 @@ def test_config4_dense_grid(ibt, oracle):
     assert_lk_parity(p1, st, p1_o, st_o, "config 4")
 
 
+def test_config4_full_size_sample(ibt, oracle):
+    """BASELINE config 4 at FULL size (24 MP pair, np.mgrid[10:4000:11, 10:6000:11] = 197 835 points, maxLevel 5, 30
+    iterations, fwd + bwd + FB in one launch); 600 sampled points are re-tracked by the CPU oracle."""
+    import torch
+    from iceberg_tracking_code_b200 import synthetic as syn
+    H, W = 4000, 6000
+    lp = dict(winSize=(31, 31), maxLevel=5, criteria=(3, 30, 0.01))
+    base = syn.base_texture(H, W, 7, device="cuda")
+    g0, g1 = syn.frame_gray(base, 0), syn.frame_gray(base, 1)
+    del base
+    pts = syn.grid_points(H, W, step=11, start=10).reshape(-1, 2).cuda()
+    n = pts.shape[0]
+    assert n == 197835
+    pa, pb = ibt.FramePyramid(g0, lp["winSize"], lp["maxLevel"], True), ibt.FramePyramid(g1, lp["winSize"], lp["maxLevel"], True)
+    assert pa.maxLevel == 5
+    p1 = torch.empty((n, 2), dtype=torch.float32, device="cuda")
+    fbd = torch.empty((n,), dtype=torch.float32, device="cuda")
+    ibt.lk_fb_into(pa, pb, pts, lp, p1, fbd, None, None)
+    sel = np.random.default_rng(4).choice(n, 600, replace=False)
+    p0s = pts[sel].cpu().numpy()
+    g0n, g1n = g0.cpu().numpy(), g1.cpu().numpy()
+    p1_o, st_o, _ = oracle.calcOpticalFlowPyrLK(g0n, g1n, p0s, None, **lp)
+    p0r_o, _, _ = oracle.calcOpticalFlowPyrLK(g1n, g0n, p1_o, None, **lp)
+    d_o, _ = oracle.fb_check(p0s, p0r_o)
+    dp = np.abs(p1[sel].cpu().numpy() - p1_o.reshape(-1, 2)).max(1)
+    assert (dp <= 0.01).mean() >= 0.99 and np.abs(fbd[sel].cpu().numpy() - d_o).max() <= 0.01
+    assert float((fbd < 1).float().mean()) > 0.99          # the synthetic shift is tracked everywhere
+
+
 def test_config5_tracks_to_utm(ibt, golden):
     from iceberg_tracking_code_b200.camera import Camera
     g = golden("utm_expected.npz")
