@@ -7,7 +7,7 @@
 //   destuff       remove the 0x00 after every 0xFF of the entropy-coded segment (count / scan / write); bytes are stored
 //                 so that a 32-bit load returns them in bit-stream (big-endian) order
 //   Huffman       decoded speculatively (restart markers, if any, are not needed for parallelism): thread i owns bits
-//                 [i*S, (i+1)*S) and starts from a guessed decoder state (block 0 of an MCU, DC expected).  Huffman
+//                 [i*S, (i+1)*S) and starts from a guessed decoder state (see jpg_sync_probe for the guess).  Huffman
 //                 streams self-synchronise: after a few symbols a decoder that started in the wrong state is in the
 //                 right one.  Rounds: every thread whose entry state changed decodes its subsequence again and hands its
 //                 exit state (bit position, block in MCU, zig-zag index) to its successor, until nothing changes
@@ -18,7 +18,8 @@
 //   DC            per-component prefix sum of the DC differences over MCUs (scan) + within the MCU (IDCT kernel)
 //   IDCT          one thread per 8x8 block in PLANE order (a warp stores 256 contiguous bytes per row): dequantise,
 //                 libjpeg "islow" integer IDCT in registers, saturate to u8
-//   colour        4 pixels per thread: fancy h2v2 / h2v1 chroma upsampling, YCbCr->RGB, optional fused cvtColor gray
+//   colour        8 pixels per thread, one kernel per sampling mode: fancy h2v2 / h2v1 chroma upsampling, YCbCr->RGB,
+//                 optional fused cvtColor gray
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>
