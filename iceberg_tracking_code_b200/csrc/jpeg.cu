@@ -26,7 +26,8 @@
 
 namespace ibt {
 
-constexpr int JPG_S = 1024;              // subsequence length, bits
+// subsequence length S = 2^sbits stream bits per decoder thread, chosen per file (jpeg_sbits): every pass costs the latency
+// of one thread walking S bits, dense files need ~15 kbit / S repair rounds, sparse files have too few subsequences at a large S
 constexpr int JPG_LUT_BITS = 10;
 constexpr int JPG_CHUNK = 4096;          // destuff: bytes per CTA (256 threads x 16)
 
@@ -283,11 +284,11 @@ __device__ __forceinline__ void huff_run(const uint32_t *__restrict__ words, con
 }
 
 // entry state of subsequence i: pos | (blk * 64 + k) << 32
-__global__ void __launch_bounds__(256) jpg_sync_init(unsigned long long *__restrict__ start, uint8_t *__restrict__ dirty, int nsub)
+__global__ void __launch_bounds__(256) jpg_sync_init(unsigned long long *__restrict__ start, uint8_t *__restrict__ dirty, int nsub, int sbits)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsub) return;
-    start[i] = (unsigned long long)i * JPG_S;
+    start[i] = (unsigned long long)i << sbits;
     dirty[i] = 1;
     dirty[nsub + i] = 0;
 }
@@ -297,11 +298,11 @@ __global__ void __launch_bounds__(256) jpg_sync_init(unsigned long long *__restr
 // possible place h = 0 .. blocks-per-MCU - 1; where at least two of these decoders end in the same state (two unrelated
 // wrong decoders practically never agree) that state becomes the entry state of subsequence i + 1, else h = 0's exit is
 // used as before.  Still only a guess -- the rounds below verify every subsequence and repair what is wrong.  Measured at
-// 24 MP: 4 -> 2 rounds on the iceberg scene (0.51 -> 0.49 ms), 16 -> 14 on the noise texture, whose MCUs are longer than a
-// subsequence so that the decoders rarely agree (the 90 us of the probe are just paid back there).
+// 24 MP with S = 1024: 4 -> 2 rounds on the iceberg scene (0.51 -> 0.49 ms), 16 -> 14 on the noise texture, where a guessed
+// decoder re-synchronises with probability 1/2 per subsequence (the 90 us of the probe are just paid back there).
 __global__ void __launch_bounds__(128) jpg_sync_probe(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
                                                       const JpgTables *__restrict__ T, unsigned long long *__restrict__ exits,
-                                                      int nsub, int P, const uint32_t *__restrict__ rst)
+                                                      int nsub, int P, const uint32_t *__restrict__ rst, int sbits)
 {
     __shared__ JpgSmemTables S;
     load_tables(S, T);
@@ -309,9 +310,9 @@ __global__ void __launch_bounds__(128) jpg_sync_probe(const uint32_t *__restrict
     if (g >= nsub * P) return;
     const int i = g / P, h = g - i * P;
     const unsigned long long total_bits = (unsigned long long)meta[0] * 8ull;
-    const unsigned long long lo = (unsigned long long)i * JPG_S;
+    const unsigned long long lo = (unsigned long long)i << sbits, S_bits = 1ull << sbits;
     if (lo >= total_bits) { exits[g] = ~0ull; return; }
-    const unsigned long long hi = lo + JPG_S < total_bits ? lo + JPG_S : total_bits;
+    const unsigned long long hi = lo + S_bits < total_bits ? lo + S_bits : total_bits;
     uint32_t pos = (uint32_t)lo, done = 0;
     int blk = h, k = 0;
     huff_run<false>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, nullptr, 0, 0, rst);
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256) jpg_sync_vote(const unsigned long long *_
 __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
                                                       const JpgTables *__restrict__ T, unsigned long long *__restrict__ start,
                                                       uint8_t *__restrict__ dirty, uint32_t *__restrict__ nblk, int nsub, int round,
-                                                      uint32_t *__restrict__ changed_slot, const uint32_t *__restrict__ rst)
+                                                      uint32_t *__restrict__ changed_slot, const uint32_t *__restrict__ rst, int sbits)
 {
     __shared__ JpgSmemTables S;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,9 +356,9 @@ __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict
     if (!mine) return;
     din[i] = 0;
     const unsigned long long total_bits = (unsigned long long)meta[0] * 8ull;
-    const unsigned long long lo = (unsigned long long)i * JPG_S;
+    const unsigned long long lo = (unsigned long long)i << sbits, S_bits = 1ull << sbits;
     if (lo >= total_bits) { nblk[i] = 0; return; }
-    const unsigned long long hi = lo + JPG_S < total_bits ? lo + JPG_S : total_bits;
+    const unsigned long long hi = lo + S_bits < total_bits ? lo + S_bits : total_bits;
     const unsigned long long st = start[i];
     uint32_t pos = (uint32_t)st;
     int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
@@ -376,16 +377,16 @@ __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict
 __global__ void __launch_bounds__(128) jpg_huff_write(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
                                                       const JpgTables *__restrict__ T, const unsigned long long *__restrict__ start,
                                                       const uint32_t *__restrict__ base, int16_t *__restrict__ coef, int nsub,
-                                                      uint32_t nblocks, const uint32_t *__restrict__ rst)
+                                                      uint32_t nblocks, const uint32_t *__restrict__ rst, int sbits)
 {
     __shared__ JpgSmemTables S;
     load_tables(S, T);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsub) return;
     const unsigned long long total_bits = (unsigned long long)meta[0] * 8ull;
-    const unsigned long long lo = (unsigned long long)i * JPG_S;
+    const unsigned long long lo = (unsigned long long)i << sbits, S_bits = 1ull << sbits;
     if (lo >= total_bits) return;
-    const unsigned long long hi = lo + JPG_S < total_bits ? lo + JPG_S : total_bits;
+    const unsigned long long hi = lo + S_bits < total_bits ? lo + S_bits : total_bits;
     const unsigned long long st = start[i];
     uint32_t pos = (uint32_t)st;
     int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
@@ -617,9 +618,20 @@ static int jpeg_validate(const ibt_jpeg_info_t *I)
     return IBT_OK;
 }
 
+// S = 2^sbits: at most ~16 k subsequences per file while 256 <= S <= 2048 (IBT_JPEG_SBITS overrides: the sweep in profiles/)
+static int jpeg_sbits(const ibt_jpeg_info_t *I)
+{
+    static const int forced = getenv("IBT_JPEG_SBITS") ? atoi(getenv("IBT_JPEG_SBITS")) : 0;
+    if (forced >= 7 && forced <= 12) return forced;
+    const long long bits = (long long)I->scan_bytes * 8;
+    int sb = 8;
+    while (sb < 11 && (bits >> sb) > 16000) sb++;
+    return sb;
+}
+
 struct JpgLayout {
     JpgGeom G;
-    int nmcu, nblocks, nsub, nchunks;
+    int nmcu, nblocks, nsub, nchunks, sbits;
     size_t off_stream, off_counts, off_offsets, off_meta, off_tables, off_rst, off_exits, off_changed, off_start, off_dirty, off_nblk, off_base, off_partial,
         off_coef, off_dcs, off_dcpre, off_plane[3], total;
     size_t stream_bytes, coef_bytes, rst_bytes;
@@ -655,7 +667,8 @@ static void jpeg_layout(const ibt_jpeg_info_t *I, JpgLayout &L)
     G.nblk_mcu = off;
     L.nmcu = G.mcux * G.mcuy;
     L.nblocks = L.nmcu * G.nblk_mcu;
-    L.nsub = (int)((I->scan_bytes * 8 + JPG_S - 1) / JPG_S);
+    L.sbits = jpeg_sbits(I);
+    L.nsub = (int)((I->scan_bytes * 8 + (1ll << L.sbits) - 1) >> L.sbits);
     L.nchunks = (int)((I->scan_bytes + JPG_CHUNK - 1) / JPG_CHUNK);
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
@@ -890,10 +903,10 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     if (L.G.nblk_mcu > 1 && !no_probe) {
         unsigned long long *exits = reinterpret_cast<unsigned long long *>(ws + L.off_exits);
         const int P = L.G.nblk_mcu;
-        jpg_sync_probe<<<(L.nsub * P + 127) / 128, 128, 0, st>>>(words, meta, dT, exits, L.nsub, P, rst);
+        jpg_sync_probe<<<(L.nsub * P + 127) / 128, 128, 0, st>>>(words, meta, dT, exits, L.nsub, P, rst, L.sbits);
         jpg_sync_vote<<<(L.nsub + 255) / 256, 256, 0, st>>>(exits, start, dirty, L.nsub, P);
     } else {
-        jpg_sync_init<<<(L.nsub + 255) / 256, 256, 0, st>>>(start, dirty, L.nsub);
+        jpg_sync_init<<<(L.nsub + 255) / 256, 256, 0, st>>>(start, dirty, L.nsub, L.sbits);
     }
     const int sync_ctas = (L.nsub + 127) / 128;
     // first batch: the caller's hint (rounds the previous, similar file needed) + 2, else 8
@@ -902,7 +915,7 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     while (rounds_used < 0) {
         IBT_CUDA_TRY(cudaMemsetAsync(changed, 0, JPG_MAX_ROUNDS_BATCH * 4, st));
         for (int r = 0; r < batch; r++)
-            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, dirty, nblk, L.nsub, round + r, changed + r, rst);
+            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, dirty, nblk, L.nsub, round + r, changed + r, rst, L.sbits);
         IBT_CUDA_TRY(cudaMemcpyAsync(h_flag, changed, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
         IBT_CUDA_TRY(cudaStreamSynchronize(st));
         for (int r = 0; r < batch; r++)
@@ -919,7 +932,7 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     // 3. output block of every subsequence, coefficient pass
     rc = launch_scan(nblk, base, partial, L.nsub, 1, 0, st);
     if (rc) return rc;
-    jpg_huff_write<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, base, coef, L.nsub, (uint32_t)L.nblocks, rst);
+    jpg_huff_write<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, base, coef, L.nsub, (uint32_t)L.nblocks, rst, L.sbits);
 
     // 4. DC prediction: prefix sums over MCUs per component
     jpg_dc_sums<<<(L.nmcu + 255) / 256, 256, 0, st>>>(coef, L.G, dcs, L.nmcu);
