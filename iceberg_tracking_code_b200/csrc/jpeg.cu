@@ -29,6 +29,7 @@ namespace ibt {
 // subsequence length S = 2^sbits stream bits per decoder thread, chosen per file (jpeg_sbits): every pass costs the latency
 // of one thread walking S bits, dense files need ~15 kbit / S repair rounds, sparse files have too few subsequences at a large S
 constexpr int JPG_LUT_BITS = 10;
+constexpr int JPG_Q = 4;                 // pieces per subsequence in the coefficient pass
 constexpr int JPG_CHUNK = 4096;          // destuff: bytes per CTA (256 threads x 16)
 
 struct __align__(16) JpgTables {          // device copy in the workspace (~27 KB): one (DC, AC) table pair per component
@@ -343,7 +344,8 @@ __global__ void __launch_bounds__(256) jpg_sync_vote(const unsigned long long *_
 // One round: threads whose entry state changed decode their subsequence and publish the exit state to their successor.
 __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
                                                       const JpgTables *__restrict__ T, unsigned long long *__restrict__ start,
-                                                      uint8_t *__restrict__ dirty, uint32_t *__restrict__ nblk, int nsub, int round,
+                                                      unsigned long long *__restrict__ qstart, uint8_t *__restrict__ dirty,
+                                                      uint32_t *__restrict__ nblk, int nsub, int round,
                                                       uint32_t *__restrict__ changed_slot, const uint32_t *__restrict__ rst, int sbits)
 {
     __shared__ JpgSmemTables S;
@@ -357,14 +359,26 @@ __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict
     din[i] = 0;
     const unsigned long long total_bits = (unsigned long long)meta[0] * 8ull;
     const unsigned long long lo = (unsigned long long)i << sbits, S_bits = 1ull << sbits;
-    if (lo >= total_bits) { nblk[i] = 0; return; }
+    if (lo >= total_bits) {
+        for (int q = 0; q < JPG_Q; q++) { nblk[(size_t)i * JPG_Q + q] = 0; qstart[(size_t)i * JPG_Q + q] = ~0ull; }
+        return;
+    }
     const unsigned long long hi = lo + S_bits < total_bits ? lo + S_bits : total_bits;
     const unsigned long long st = start[i];
     uint32_t pos = (uint32_t)st;
     int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
-    uint32_t done = 0;
-    huff_run<false>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, nullptr, 0, 0, rst);
-    nblk[i] = done;
+    // decoded in JPG_Q pieces: the state at the entry of every piece and the blocks completed inside it are kept, so that
+    // the coefficient pass can run with JPG_Q times as many (and as short) decoders.  A thread's last decode starts from
+    // its final entry state, so what it leaves behind is final too.
+    const unsigned long long piece = S_bits / JPG_Q;
+#pragma unroll 1
+    for (int q = 0; q < JPG_Q; q++) {
+        const unsigned long long qlo = lo + q * piece, qhi = qlo + piece < hi ? qlo + piece : hi;
+        qstart[(size_t)i * JPG_Q + q] = (unsigned long long)pos | ((unsigned long long)(blk * 64 + k) << 32);
+        uint32_t done = 0;
+        if (qlo < hi) huff_run<false>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)qhi, done, nullptr, 0, 0, rst);
+        nblk[(size_t)i * JPG_Q + q] = done;
+    }
     if (i + 1 < nsub && hi < total_bits) {
         const unsigned long long out = (unsigned long long)pos | ((unsigned long long)(blk * 64 + k) << 32);
         if (start[i + 1] != out) {
@@ -374,24 +388,29 @@ __global__ void __launch_bounds__(128) jpg_sync_round(const uint32_t *__restrict
         }
     }
 }
+// Coefficient pass: one thread per PIECE (S / JPG_Q bits) from the entry state the last sync decode left there.
 __global__ void __launch_bounds__(128) jpg_huff_write(const uint32_t *__restrict__ words, const uint32_t *__restrict__ meta,
-                                                      const JpgTables *__restrict__ T, const unsigned long long *__restrict__ start,
+                                                      const JpgTables *__restrict__ T, const unsigned long long *__restrict__ qstart,
                                                       const uint32_t *__restrict__ base, int16_t *__restrict__ coef, int nsub,
                                                       uint32_t nblocks, const uint32_t *__restrict__ rst, int sbits)
 {
     __shared__ JpgSmemTables S;
     load_tables(S, T);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nsub) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nsub * JPG_Q) return;
+    const int i = g / JPG_Q, q = g - i * JPG_Q;
     const unsigned long long total_bits = (unsigned long long)meta[0] * 8ull;
     const unsigned long long lo = (unsigned long long)i << sbits, S_bits = 1ull << sbits;
     if (lo >= total_bits) return;
     const unsigned long long hi = lo + S_bits < total_bits ? lo + S_bits : total_bits;
-    const unsigned long long st = start[i];
+    const unsigned long long piece = S_bits / JPG_Q;
+    const unsigned long long qlo = lo + q * piece, qhi = qlo + piece < hi ? qlo + piece : hi;
+    if (qlo >= hi) return;
+    const unsigned long long st = qstart[g];
     uint32_t pos = (uint32_t)st;
     int blk = (int)(st >> 38), k = (int)(st >> 32) & 63;
     uint32_t done = 0;
-    huff_run<true>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)hi, done, coef, base[i], nblocks, rst);
+    huff_run<true>(words, S, T->compmap, T->nblk_mcu, pos, blk, k, (uint32_t)qhi, done, coef, base[g], nblocks, rst);
 }
 
 // ---- DC differences -> per-MCU sums per component (rows of dcs: [comp][nmcu]) ------------------------------------------------
@@ -632,7 +651,7 @@ static int jpeg_sbits(const ibt_jpeg_info_t *I)
 struct JpgLayout {
     JpgGeom G;
     int nmcu, nblocks, nsub, nchunks, sbits;
-    size_t off_stream, off_counts, off_offsets, off_meta, off_tables, off_rst, off_exits, off_changed, off_start, off_dirty, off_nblk, off_base, off_partial,
+    size_t off_stream, off_counts, off_offsets, off_meta, off_tables, off_rst, off_exits, off_changed, off_start, off_qstart, off_dirty, off_nblk, off_base, off_partial,
         off_coef, off_dcs, off_dcpre, off_plane[3], total;
     size_t stream_bytes, coef_bytes, rst_bytes;
 };
@@ -684,9 +703,10 @@ static void jpeg_layout(const ibt_jpeg_info_t *I, JpgLayout &L)
     L.off_changed = take(JPG_MAX_ROUNDS_BATCH * 4);
     L.off_start = take((size_t)L.nsub * 8);
     L.off_dirty = take((size_t)L.nsub * 2);
-    L.off_nblk = take((size_t)L.nsub * 4);
-    L.off_base = take((size_t)L.nsub * 4);
-    const size_t np1 = (size_t)(L.nsub + 1023) / 1024 + 1, np2 = 3 * ((size_t)(L.nmcu + 1023) / 1024 + 1), np3 = (size_t)(L.nchunks + 1023) / 1024 + 1;
+    L.off_nblk = take((size_t)L.nsub * JPG_Q * 4);
+    L.off_base = take((size_t)L.nsub * JPG_Q * 4);
+    L.off_qstart = take((size_t)L.nsub * JPG_Q * 8);
+    const size_t np1 = (size_t)(L.nsub * JPG_Q + 1023) / 1024 + 1, np2 = 3 * ((size_t)(L.nmcu + 1023) / 1024 + 1), np3 = (size_t)(L.nchunks + 1023) / 1024 + 1;
     L.off_partial = take((np1 > np2 ? (np1 > np3 ? np1 : np3) : (np2 > np3 ? np2 : np3)) * 4);
     L.coef_bytes = (size_t)L.nblocks * 64 * 2;
     L.off_coef = take(L.coef_bytes);
@@ -879,6 +899,7 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_meta), *changed = reinterpret_cast<uint32_t *>(ws + L.off_changed);
     unsigned long long *start = reinterpret_cast<unsigned long long *>(ws + L.off_start);
     uint8_t *dirty = ws + L.off_dirty;
+    unsigned long long *qstart = reinterpret_cast<unsigned long long *>(ws + L.off_qstart);
     uint32_t *nblk = reinterpret_cast<uint32_t *>(ws + L.off_nblk), *base = reinterpret_cast<uint32_t *>(ws + L.off_base);
     uint32_t *partial = reinterpret_cast<uint32_t *>(ws + L.off_partial);
     int16_t *coef = reinterpret_cast<int16_t *>(ws + L.off_coef);
@@ -915,7 +936,7 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     while (rounds_used < 0) {
         IBT_CUDA_TRY(cudaMemsetAsync(changed, 0, JPG_MAX_ROUNDS_BATCH * 4, st));
         for (int r = 0; r < batch; r++)
-            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, dirty, nblk, L.nsub, round + r, changed + r, rst, L.sbits);
+            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, qstart, dirty, nblk, L.nsub, round + r, changed + r, rst, L.sbits);
         IBT_CUDA_TRY(cudaMemcpyAsync(h_flag, changed, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
         IBT_CUDA_TRY(cudaStreamSynchronize(st));
         for (int r = 0; r < batch; r++)
@@ -930,9 +951,9 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     if (out_rounds) *out_rounds = rounds_used;
 
     // 3. output block of every subsequence, coefficient pass
-    rc = launch_scan(nblk, base, partial, L.nsub, 1, 0, st);
+    rc = launch_scan(nblk, base, partial, L.nsub * JPG_Q, 1, 0, st);
     if (rc) return rc;
-    jpg_huff_write<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, base, coef, L.nsub, (uint32_t)L.nblocks, rst, L.sbits);
+    jpg_huff_write<<<(L.nsub * JPG_Q + 127) / 128, 128, 0, st>>>(words, meta, dT, qstart, base, coef, L.nsub, (uint32_t)L.nblocks, rst, L.sbits);
 
     // 4. DC prediction: prefix sums over MCUs per component
     jpg_dc_sums<<<(L.nmcu + 255) / 256, 256, 0, st>>>(coef, L.G, dcs, L.nmcu);
