@@ -49,27 +49,41 @@ class JpegDecoder:
         self._ws = None
         self.last_rounds = 0
 
-    def _stage(self, buf):
-        """file bytes -> device (through a pinned double buffer)."""
-        n = buf.size
+    def _pinned_slot(self, n):
+        """the next pinned staging buffer (double-buffered), free again, at least n bytes"""
         k = self._k
         self._k ^= 1
         slot = self._pinned[k]
         if slot is None or slot[0].numel() < n:
             slot = (torch.empty((max(n, 1 << 20) * 5 // 4,), dtype=torch.uint8).pin_memory(), torch.cuda.Event())
             self._pinned[k] = slot
+        slot[1].synchronize()                       # the copy that last read this buffer has finished
+        return slot
+
+    def _upload(self, slot, n):
+        """pinned bytes [0, n) -> device, asynchronously on the current stream"""
         host, ev = slot
-        ev.synchronize()
-        host[:n].numpy()[:] = buf
         if self._dev_file is None or self._dev_file.numel() < n:
             self._dev_file = torch.empty((max(n, 1 << 20) * 5 // 4,), dtype=torch.uint8, device=self.device)
         self._dev_file[:n].copy_(host[:n], non_blocking=True)
         ev.record(torch.cuda.current_stream())
         return self._dev_file
 
+    def decode_file(self, path, rgb=True, gray=False, coeffset=0):
+        """decode() of a file on disk.  The file is read into ordinary memory and copied into the pinned staging buffer:
+        reading straight into page-locked memory (readinto on the pinned view) was measured 1.2x .. 30x slower and erratic."""
+        with open(str(path), "rb") as f:
+            return self.decode(f.read(), rgb, gray, coeffset)
+
     def decode(self, data, rgb=True, gray=False, coeffset=0):
         """data: bytes-like holding a JPEG file.  Returns (rgb, gray) CUDA tensors (None where not requested)."""
         buf = np.frombuffer(data, dtype=np.uint8)
+        slot = self._pinned_slot(buf.size)
+        view = slot[0].numpy()
+        view[:buf.size] = buf
+        return self._decode_staged(view[:buf.size], slot, rgb, gray, coeffset)
+
+    def _decode_staged(self, buf, slot, rgb, gray, coeffset):
         info = parse(buf)
         H, W = info.height, info.width
         if info.ncomp == 1:
@@ -80,7 +94,7 @@ class JpegDecoder:
         with torch.cuda.device(self.device):
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty((int(need * 1.1) + 256,), dtype=torch.uint8, device=self.device)
-            dfile = self._stage(buf)
+            dfile = self._upload(slot, buf.size)
             out_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=self.device) if rgb else None
             out_gray = torch.empty((H, W), dtype=torch.uint8, device=self.device) if gray else None
             rounds = C.c_int(self.last_rounds)         # hint: consecutive frames of a sequence need about the same

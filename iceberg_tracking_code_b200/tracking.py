@@ -71,7 +71,14 @@ class GpuJpegLoader:
         return gray, ev
 
     def __call__(self, path):
-        return self.decode(read_file(path))
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            gray = self.dec.decode_file(path, rgb=False, gray=True, coeffset=self.coeffset)[1]
+            if self.crop_box is not None:
+                l, u, r, b = self.crop_box
+                gray = gray[u:b, l:r].contiguous()
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return gray, ev
 
 
 class FrameStager:
@@ -251,9 +258,11 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
     if isinstance(loader, str):
         if loader != "gpu":
             raise ValueError("loader must be a callable, None or 'gpu'")
-        loader = GpuJpegLoader(trk.device)
+        if getattr(trk, "_gpu_loader", None) is None:      # pinned staging, workspace and stream live as long as the tracker
+            trk._gpu_loader = GpuJpegLoader(trk.device)
+        loader = trk._gpu_loader
     gpu = loader if isinstance(loader, GpuJpegLoader) else None
-    host_loader = read_file if gpu is not None else loader          # what the thread pool runs
+    host_loader = None if gpu is not None else loader               # what the thread pool runs
     if mask is not None:
         mask = cv._to_dev(mask, np.uint8, "mask")
     results = []
@@ -282,9 +291,11 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
                 if nxt <= counters[-1]:
                     pending[nxt] = pool.submit(host_loader, frames[nxt])
                 data = pending.pop(c).result()
+            elif gpu is not None:
+                return gpu(frames[c])             # file -> pinned staging -> device -> gray plane, on the decoder's stream
             else:
                 data = host_loader(frames[c]) if host_loader is not None else frames[c]
-            return gpu.decode(data) if gpu is not None else data
+            return data
 
         upcoming = fetch(counters[0])
         for counter in counters:
