@@ -58,6 +58,9 @@ def test_struct_layout_matches_header():
     from iceberg_tracking_code_b200 import _native
     # int32 nlevels + 2*8 int32 + pad to 8 + 4 * 8 * 8 bytes
     assert C.sizeof(_native.ibt_pyramid_t) == 4 + 64 + 4 + 4 * 64
+    # struct ibt_jpeg_info: 20 int32, 2 int64, quant 4x64 u16, dc 2 x (4x16) u8, ac (4x16) + (4x256) u8
+    assert C.sizeof(_native.ibt_jpeg_info_t) == 20 * 4 + 2 * 8 + 4 * 64 * 2 + 2 * 64 + 64 + 1024
+    assert _native.ibt_jpeg_info_t.scan_offset.offset == 80 and _native.ibt_jpeg_info_t.quant.offset == 96
     assert _native.ibt_pyramid_t.img.offset == 72
 
 
