@@ -14,6 +14,7 @@ import torch
 
 from . import _native as N
 from . import cv
+from ._crop import crop_image_standalone
 
 PARAM_COLUMNS = ["camera", "start_day", "end_day", "image_width", "image_height", "sensor_width", "easting", "northing",
                  "elevation", "antenna_height", "theta", "phi", "psi", "sigma", "crop_left", "crop_right", "crop_top",
@@ -83,11 +84,18 @@ class Camera(object):
                 self.pic['height'] - self.pic['cropbottom'])
 
     def crop_image_parallel(self, imagelist, targetworkspace, n_cpus=10):
-        """camtools.py:237-258 (serial here; JPEG decode + re-encode is host work outside the kernel scope)."""
-        from PIL import Image
+        """camtools.py:237-258: crop every source frame and re-save it with Pillow's defaults, in a pool of n_cpus
+        processes like the reference (the lossy re-encode is host work and part of the pixels the reference tracks;
+        `lucaskanade_tracking(crop="view")` is the way around it)."""
         box = tuple(int(v) for v in self.crop_box())
-        for img in imagelist:
-            Image.open(img).crop(box).save(osp.join(targetworkspace, osp.basename(img)))
+        args = [(str(img), osp.join(str(targetworkspace), osp.basename(str(img))), box) for img in imagelist]
+        if n_cpus and n_cpus > 1 and len(args) > 1:
+            import multiprocessing
+            with multiprocessing.get_context("spawn").Pool(processes=min(int(n_cpus), len(args))) as pool:
+                pool.map(crop_image_standalone, args)
+        else:
+            for a in args:
+                crop_image_standalone(a)
 
     # -- mask ---------------------------------------------------------------------------------------------
     def mask_image(self, h, w, device=None):

@@ -130,3 +130,25 @@ def test_bench_reference_arm_contract(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_crop_image_parallel_matches_pillow(tmp_path):
+    """camtools.py:237-258: pool of processes, Pillow defaults, same bytes as the serial reference recipe."""
+    import shutil
+    from PIL import Image
+    from iceberg_tracking_code_b200.camera import Camera
+    seq = os.path.join(ROOT, "tests", "golden", "seq")
+    names = sorted(os.listdir(seq))[:3]
+    src, tgt = tmp_path / "src", tmp_path / "tgt"
+    src.mkdir(); tgt.mkdir()
+    for n in names:
+        shutil.copy(os.path.join(seq, n), src / n)
+    w, h = Image.open(src / names[0]).size
+    cam = Camera(camname="cam1", parameters=dict(image_width=w, image_height=h, sensor_width=22.3, easting=0.0, northing=0.0,
+                 elevation=10.0, antenna_height=0.0, theta=0.0, phi=0.0, psi=0.0, sigma=18.0, crop_left=16, crop_right=8,
+                 crop_top=10, crop_bottom=20))
+    cam.crop_image_parallel([str(src / n) for n in names], str(tgt), 2)
+    for n in names:
+        ref = tmp_path / ("ref_" + n)
+        Image.open(src / n).crop((16, 10, w - 8, h - 20)).save(ref)          # crop_image_standalone, camtools.py:76-80
+        assert (tgt / n).read_bytes() == ref.read_bytes()
