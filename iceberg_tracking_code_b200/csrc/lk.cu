@@ -3,39 +3,53 @@
 // Replaces the two cv2.calcOpticalFlowPyrLK calls and the numpy FB arithmetic at
 // s1_lucaskanade_tracking.py:323-333 (s0_1_test_lucaskanade_tracking.py:92-102).
 //
-// Per level a warp (a) issues cp.async copies of everything the level can touch -- the I window, its Scharr
-// planes, and the J search patch around the propagated guess -- into its private shared-memory slab in one
-// burst (one exposed L2 latency per level instead of one per row), (b) builds the template from shared memory,
-// (c) runs the Newton iterations entirely out of shared memory.
-//   mapping     lane L owns window column L of a strip of <= 32 columns and walks down the rows, keeping the
-//               previous row's (J[x], J[x+1]) byte pair in a register; a bilinear sample is two dp2a
-//               instructions: OpenCV's four 14-bit integer weights are packed as two int16 pairs (top, bottom).
-//   template    per window pixel the slab keeps  T0 = 256 - (Iw << 9)  and (Ix, Iy) packed as int16 pair, so that
-//               diff = dp2a(wbot, Jpair1, dp2a(wtop, Jpair0, T0)) >> 9  is exactly OpenCV's
-//               DESCALE(J taps, 9) - Iw  (the arithmetic shift distributes over the multiple of 512).
-//   borders     intensities REFLECT_101 (resolved while staging, synchronous gather path), derivatives ZERO outside
-//               the image (cp.async zero-fill), as inside OpenCV's padded pyramids.
-//   patch       window + 1 + 2*MARGIN(+3 alignment) px; re-staged only if the window drifts out of it.
-// The 2x2 structure tensor and the mismatch vector are accumulated exactly (int32 per lane, REDUX across the warp)
-// and rounded to float once; OpenCV accumulates in float SIMD lanes, which differs in the last bits only.
-// All float arithmetic that OpenCV does unfused is compiled with -fmad=false.
+// Per level a warp
+//  (a) stages everything the level can touch into its private shared-memory slab in one burst: three TMA bulk tensor
+//      copies (per-warp mbarriers; box origins on 16-byte boundaries) bring the I window, its Scharr planes (TMA zero
+//      fill = OpenCV's zero-padded derivative planes) and the J search patch around the propagated guess (window + 1 +
+//      2*MARGIN px).  Intensity patches that overhang the image are mirrored (REFLECT_101) inside shared memory after the
+//      zero-filling copy; cp.async / gather paths remain for far-out windows and images that are not 16-byte aligned;
+//  (b) builds the template: lane = window column, rows walked top to bottom.  Per window pixel the slab keeps only the
+//      packed int16 pair (Ix, Iy) -- 4 bytes -- and the pass accumulates, exactly, the structure tensor and the two
+//      constants C1 = sum(Iw*Ix), C2 = sum(Iw*Iy).  The template rows overwrite the Scharr patch rows already consumed;
+//  (c) runs the Newton iterations out of shared memory with a different lane mapping: lane = (row group, column quad),
+//      4 adjacent columns x RG consecutive rows.  Per row a lane loads the two aligned words that hold its 5 J bytes,
+//      two PRMTs (warp-uniform selectors) turn them into the byte windows (b0..b3), (b1..b4), and dp2a.lo / dp2a.hi on
+//      those against OpenCV's packed 14-bit weights give the four bilinear samples; one 16-byte load brings the four
+//      template entries.  The mismatch vector is  b = sum(Jw*Ix) - C1  (sum(Jw*Iy) - C2): identical, as an exact
+//      integer, to OpenCV's sum((Jw - Iw)*Ix), and it halves the template.  Template entries outside the window are
+//      zero, so the iteration loop carries no masks.
+// All sums are exact integers (int32 per lane, REDUX across the warp, int64 totals) rounded to float once; OpenCV
+// accumulates in float SIMD lanes, which differs in the last bits only.  Float arithmetic that OpenCV does unfused is
+// compiled with -fmad=false.
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
+#include <vector>
 
 namespace ibt {
 
 constexpr int LK_MARGIN = 3;        // px the window may drift inside a staged patch, each direction
 
-// slab geometry as a function of the window width (shared by host launch code and the specialised kernels)
-__host__ __device__ constexpr int lk_nstrips(int w) { return (w + 31) / 32; }
-__host__ __device__ constexpr int lk_strip_cols(int w) { return (w + lk_nstrips(w) - 1) / lk_nstrips(w); }
+// ---- slab geometry as a function of the window size (shared by host launch code and the specialised kernels) ----------
+// Newton mapping: NL lanes per row group (4 columns each), NG row groups of RG rows; the template is TROWS x TCOLS.
+__host__ __device__ constexpr int lk_nl(int w) { return (w + 3) / 4; }
+__host__ __device__ constexpr int lk_tcols(int w) { return 4 * lk_nl(w); }
+__host__ __device__ constexpr int lk_ng0(int w, int h) { return (32 / lk_nl(w)) < h ? (32 / lk_nl(w)) : h; }
+__host__ __device__ constexpr int lk_rg(int w, int h) { return (h + lk_ng0(w, h) - 1) / lk_ng0(w, h); }
+__host__ __device__ constexpr int lk_ng(int w, int h) { return (h + lk_rg(w, h) - 1) / lk_rg(w, h); }
+__host__ __device__ constexpr int lk_trows(int w, int h) { return lk_ng(w, h) * lk_rg(w, h); }
+// template-build mapping: lane = column of a strip of <= 32 of the TCOLS template columns
+__host__ __device__ constexpr int lk_nstrips(int w) { return (lk_tcols(w) + 31) / 32; }
+__host__ __device__ constexpr int lk_strip_cols(int w) { return (lk_tcols(w) + lk_nstrips(w) - 1) / lk_nstrips(w); }
 // every lane of every strip reads two adjacent elements per row, active or not: pitches keep those reads in the slab
 __host__ __device__ constexpr int lk_reach(int w) { return (lk_nstrips(w) - 1) * lk_strip_cols(w) + 33; }
-__host__ __device__ constexpr int lk_dpitch(int w) { return (lk_reach(w) + 3) & ~3; }                 // words; rows are 16-byte multiples (TMA box)
+__host__ __device__ constexpr int lk_dpitch(int w) { return (lk_reach(w) + 6) & ~3; }                 // words; rows are 16-byte multiples (TMA box); + window offset 0..3
 // TMA boxes start on 16-byte boundaries of the image row: up to 15 extra columns on the left
 __host__ __device__ constexpr int lk_ipitch(int w) { return (15 + lk_reach(w) + 15) & ~15; }
-__host__ __device__ constexpr int lk_jpitch(int w) { return (15 + 2 * LK_MARGIN + lk_reach(w) + 15) & ~15; }
+// Newton lanes read the two aligned words around bytes [ox + 4c, ox + 4c + 4], ox <= 15 + 2*MARGIN
+__host__ __device__ constexpr int lk_jpitch(int w) { return (15 + 2 * LK_MARGIN + lk_tcols(w) + 4 + 15) & ~15; }
 
 struct LKLevel {
     const uint8_t *img;
@@ -59,15 +73,16 @@ struct LKArgs {
     LKPyr pyr[2];               // [0] = prev, [1] = next
     const float *p0;
     int n;
-    int winW, winH, nstrips, strip_cols;
-    // per-warp shared-memory slab: [template uint2 x tmpl_elems][deriv patch][I patch][J patch]
-    int tmpl_elems;
+    int winW, winH;
+    int nl, ng, rg, trows, tcols;           // Newton mapping / template shape
+    int nstrips, strip_cols;                // template-build mapping
+    // per-warp shared-memory slab: [template (Ix,Iy) words, overlaid on the Scharr patch][I patch][J patch]
     int dpitch;                 // deriv patch row pitch, words
-    int ipitch;                 // I patch row pitch, bytes (multiple of 4)
-    int jpitch, jrows;          // J patch row pitch (bytes, multiple of 4) and rows
-    int irpp, jrpp;             // patch rows covered per cp.async pass (32 / words per row)
-    unsigned int *work_counter; // next point index (dynamic point -> warp assignment)
-    int off_deriv, off_ipatch, off_jpatch, warp_smem;     // bytes
+    int ipitch;                 // I patch row pitch, bytes (multiple of 16)
+    int jpitch, jrows;          // J patch row pitch (bytes, multiple of 16) and staged rows (window + 1 + 2*MARGIN)
+    unsigned int *work_counter; // [0] next point index (dynamic point -> warp assignment), [1] warps that have left
+    unsigned int total_warps;
+    int off_ipatch, off_jpatch, warp_smem;     // bytes (template and Scharr patch start at 0)
     int maxCount;
     float eps2, minEigThr;
     int flags;
@@ -88,12 +103,18 @@ __device__ __forceinline__ long long warp_sum_wide(int v)
 
 __device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
 
-// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 with SIGNED 16-bit weights (iw11 = 2^14 - iw00 - iw01 - iw10 can be -1
-// after rounding) and UNSIGNED pixel bytes.
-__device__ __forceinline__ uint32_t dp2a_s16u8(uint32_t a, uint32_t b, uint32_t c)
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (.lo) / b.byte2, b.byte3 (.hi) with SIGNED 16-bit weights (iw11 = 2^14 - iw00 -
+// iw01 - iw10 can be -1 after rounding) and UNSIGNED pixel bytes.
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c)
 {
     int d;
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
+    return (uint32_t)d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
     return (uint32_t)d;
 }
 
@@ -150,13 +171,14 @@ __device__ __noinline__ void stage_bytes_border(const LKLevel &L, int x0a, int y
 
 // Stage image rows [y0, y0+nrows) x bytes [x0a, x0a+pitch) (x0a a multiple of 4) into dst (row pitch `pitch`).
 // Interior patches go as 4-byte cp.async (lane -> (row sr + k*rpp, word sw)); patches that touch the border are
-// gathered through REFLECT_101 (column indices resolved once per lane, rows batched four at a time).
-// The caller commits / waits.
-__device__ __forceinline__ void stage_bytes(const LKLevel &L, int x0a, int y0, int nrows, int pitch, int rpp, int sr, int sw,
-                                            uint8_t *dst, int lane)
+// gathered through REFLECT_101.  The caller commits / waits.
+__device__ __forceinline__ void stage_bytes(const LKLevel &L, int x0a, int y0, int nrows, int pitch, int lane, uint8_t *dst)
 {
     const bool interior = L.word_ok && x0a >= 0 && y0 >= 0 && y0 + nrows <= L.rows && x0a + pitch <= L.cols;
     if (interior) {
+        const int ppw = pitch >> 2;                 // words per row (<= 32: pitches are at most 128 bytes)
+        const int rpp = 32 / ppw;                   // rows covered per pass
+        const int sr = lane / ppw, sw = lane - sr * ppw;
         if (sr < rpp) {
             const uint8_t *src = L.img + (int64_t)(y0 + sr) * L.img_pitch + x0a + 4 * sw;
             unsigned d = smem_u32(dst) + sr * pitch + 4 * sw;
@@ -205,11 +227,10 @@ __device__ __noinline__ void patch_reflect(uint8_t *patch, int pitch, int x0a, i
 }
 
 // Re-stage the J patch synchronously (the window drifted out of the prefetched patch): rare, kept out of line.
-__device__ __noinline__ void restage_sync(const LKLevel &L, int x0a, int y0, int nrows, int pitch, int rpp, int sr, int sw,
-                                          uint8_t *dst, int lane)
+__device__ __noinline__ void restage_sync(const LKLevel &L, int x0a, int y0, int nrows, int pitch, uint8_t *dst, int lane)
 {
     __syncwarp();
-    stage_bytes(L, x0a, y0, nrows, pitch, rpp, sr, sw, dst, lane);
+    stage_bytes(L, x0a, y0, nrows, pitch, lane, dst);
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
@@ -242,44 +263,162 @@ __device__ __forceinline__ void stage_deriv(const LKLevel &L, const LKArgs &a, i
     }
 }
 
-// Sum over the window of  diff*Ix, diff*Iy  (MODE 0)  or  |diff|  (MODE 1),
-// diff = DESCALE(bilinear J at byte offset (ox, oy) inside the patch, 9) - Iw.
-template <int MODE, int WW, int WH>
-__device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__restrict__ patch, int ox, int oy,
-                                            uint32_t wtop, uint32_t wbot, const uint2 *__restrict__ win, int lane,
-                                            long long &S1, long long &S2)
+// ---- template --------------------------------------------------------------------------------------------
+// lane = template column (strips of <= 32 columns), rows top to bottom.  Writes tmpl[row][col] = (Ix << 16) | (Iy & 0xffff)
+// for the TROWS x TCOLS template (zero outside the window) and returns the exact sums
+//   A11 = sum Ix^2, A12 = sum Ix*Iy, A22 = sum Iy^2, C1 = sum Iw*Ix, C2 = sum Iw*Iy.
+// The template row r overwrites Scharr patch bytes below row r+1 only (TCOLS <= DPITCH), which every lane has consumed
+// by then (one __syncwarp per row keeps the lanes within a row of each other).
+template <int WW, int WH>
+__device__ __forceinline__ void build_template(const LKArgs &a, const uint8_t *ip0, const uint32_t *dp0, uint32_t *tmpl,
+                                               uint32_t wtop, uint32_t wbot, int iw00, int iw01, int iw10, int iw11, int lane,
+                                               long long &sA11, long long &sA12, long long &sA22, long long &sC1, long long &sC2)
 {
     const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
-    const int nstrips = WW ? lk_nstrips(WW) : a.nstrips, strip_cols = WW ? lk_strip_cols(WW) : a.strip_cols;
-    const int PP = WW ? lk_jpitch(WW) : a.jpitch;
-    S1 = 0; S2 = 0;
+    constexpr int NS = WW ? lk_nstrips(WW) : 2;                 // strips held in registers (generic kernel: at most 2)
+    const int nstrips = WW ? lk_nstrips(WW) : a.nstrips, SC = WW ? lk_strip_cols(WW) : a.strip_cols;
+    const int TC = WW ? lk_tcols(WW) : a.tcols, TR = (WW && WH) ? lk_trows(WW, WH) : a.trows;
+    const int IP = WW ? lk_ipitch(WW) : a.ipitch, DP = WW ? lk_dpitch(WW) : a.dpitch;
+    int a11[NS], a12[NS], a22[NS], c1[NS], c2[NS];
+    uint32_t ipair[NS];
+    int d00x[NS], d00y[NS], d01x[NS], d01y[NS];
 #pragma unroll
-    for (int s = 0; s < nstrips; s++) {
-        const int cs = s * strip_cols;
-        const uint8_t *p = patch + oy * PP + ox + cs + lane;
-        const uint2 *wrow = win + (s * winH) * 32 + lane;
-        const bool active = lane < min(strip_cols, winW - cs);
-        int b1 = 0, b2 = 0;
-        uint32_t prev = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
-#pragma unroll(MODE == 0 ? (WH ? 8 : 4) : 1)
-        for (int r = 0; r < winH; r++) {
-            const uint32_t cur = (uint32_t)p[(r + 1) * PP] | ((uint32_t)p[(r + 1) * PP + 1] << 8);
-            const uint2 t = wrow[r * 32];
-            uint32_t v = dp2a_s16u8(wtop, prev, t.x);
-            v = dp2a_s16u8(wbot, cur, v);
-            const int diff = (int)v >> 9;
-            if (MODE == 0) {
-                b1 += diff * ((int)t.y >> 16);
-                b2 += diff * (int)(short)(t.y & 0xffffu);
-            } else {
-                b2 += abs(diff);
-            }
-            prev = cur;
+    for (int s = 0; s < NS; s++) {
+        a11[s] = a12[s] = a22[s] = c1[s] = c2[s] = 0;
+        ipair[s] = 0; d00x[s] = d00y[s] = d01x[s] = d01y[s] = 0;
+        if (s < nstrips) {
+            const uint8_t *ip = ip0 + s * SC + lane;
+            const uint32_t *dp = dp0 + s * SC + lane;
+            ipair[s] = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
+            const uint32_t dc = dp[0], dcr = dp[1];
+            d00x[s] = (int)(short)(dc & 0xffffu); d00y[s] = (int)dc >> 16;
+            d01x[s] = (int)(short)(dcr & 0xffffu); d01y[s] = (int)dcr >> 16;
         }
-        if (!active) { b1 = 0; b2 = 0; }                        // lanes beyond the window: masked once per pass
-        if (MODE == 0) S1 += warp_sum_wide(b1);
-        S2 += warp_sum_wide(b2);
     }
+#pragma unroll 4
+    for (int r = 0; r < winH; r++) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            if (s < nstrips) {
+                const int col = s * SC + lane;
+                const bool active = lane < SC && col < winW;
+                const uint8_t *ip = ip0 + (r + 1) * IP + col;
+                const uint32_t *dp = dp0 + (r + 1) * DP + col;
+                const uint32_t cpair = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
+                const uint32_t dc = dp[0], dcr = dp[1];
+                const int d10x = (int)(short)(dc & 0xffffu), d10y = (int)dc >> 16;
+                const int d11x = (int)(short)(dcr & 0xffffu), d11y = (int)dcr >> 16;
+                uint32_t v = dp2a_lo(wtop, ipair[s], 256u);
+                v = dp2a_lo(wbot, cpair, v);                           // v = taps + 256; Iw = v >> 9
+                const int Iw = (int)(v >> 9);
+                int Ix = (d00x[s] * iw00 + d01x[s] * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
+                int Iy = (d00y[s] * iw00 + d01y[s] * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
+                if (!active) { Ix = 0; Iy = 0; }                       // template columns beyond the window hold zeros
+                if (lane < SC && col < TC) tmpl[r * TC + col] = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
+                a11[s] += Ix * Ix; a12[s] += Ix * Iy; a22[s] += Iy * Iy;
+                c1[s] += Iw * Ix; c2[s] += Iw * Iy;
+                ipair[s] = cpair; d00x[s] = d10x; d00y[s] = d10y; d01x[s] = d11x; d01y[s] = d11y;
+            }
+        }
+        __syncwarp();            // the template overlays the Scharr patch rows already consumed (see launch_lk)
+    }
+    for (int i = winH * TC + lane; i < TR * TC; i += 32) tmpl[i] = 0u;       // template rows below the window
+    sA11 = sA12 = sA22 = sC1 = sC2 = 0;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (s < nstrips) {
+            sA11 += warp_sum_wide(a11[s]); sA12 += warp_sum_wide(a12[s]); sA22 += warp_sum_wide(a22[s]);
+            sC1 += warp_sum_wide(c1[s]); sC2 += warp_sum_wide(c2[s]);
+        }
+    }
+    __syncwarp();
+}
+
+// ---- Newton pass ---------------------------------------------------------------------------------------------
+// Lane = (row group, column quad): rows [rowbase, rowbase + RG), template columns [4*cq, 4*cq + 4).
+// S1 = sum Jw * Ix, S2 = sum Jw * Iy over the window, Jw = DESCALE(bilinear J at byte offset (ox, oy) inside the patch, 9).
+// Partial sums are flushed to int64 every 16 rows (64 pixels * 8160 * 4080 < 2^31).
+template <int WW, int WH>
+__device__ __forceinline__ void newton_sums(const LKArgs &a, const uint8_t *__restrict__ patch, int ox, int oy, uint32_t wtop,
+                                            uint32_t wbot, const uint32_t *__restrict__ tmpl, int rowbase, int cq, bool lane_on,
+                                            long long &S1, long long &S2)
+{
+    const int RG = (WW && WH) ? lk_rg(WW, WH) : a.rg;
+    const int JP = WW ? lk_jpitch(WW) : a.jpitch, TC = WW ? lk_tcols(WW) : a.tcols;
+    const uint32_t al = (uint32_t)ox & 3u;                       // the same for every lane: 4*cq keeps the alignment
+    const uint32_t sel0 = 0x3210u + 0x1111u * al, sel1 = sel0 + 0x1111u;
+    const uint32_t *jp = reinterpret_cast<const uint32_t *>(patch + (oy + rowbase) * JP + ((ox + 4 * cq) & ~3));
+    const uint4 *tp = reinterpret_cast<const uint4 *>(tmpl + rowbase * TC + 4 * cq);
+    uint32_t p0, p1;                                             // byte windows (b0..b3), (b1..b4) of the previous row
+    {
+        const uint32_t w0 = jp[0], w1 = jp[1];
+        p0 = __byte_perm(w0, w1, sel0); p1 = __byte_perm(w0, w1, sel1);
+    }
+    S1 = 0; S2 = 0;
+    for (int r0 = 0; r0 < RG; r0 += 16) {
+        const int r1 = (WW && WH) ? ((RG < r0 + 16) ? RG : r0 + 16) : min(RG, r0 + 16);
+        int b1 = 0, b2 = 0;
+#pragma unroll((WW && WH) ? 16 : 2)
+        for (int r = r0; r < r1; r++) {
+            jp += JP >> 2;
+            const uint32_t w0 = jp[0], w1 = jp[1];
+            const uint32_t c0 = __byte_perm(w0, w1, sel0), c1 = __byte_perm(w0, w1, sel1);
+            const uint4 t = tp[r * (TC >> 2)];
+            const int j0 = (int)(dp2a_lo(wbot, c0, dp2a_lo(wtop, p0, 256u)) >> 9);
+            const int j1 = (int)(dp2a_lo(wbot, c1, dp2a_lo(wtop, p1, 256u)) >> 9);
+            const int j2 = (int)(dp2a_hi(wbot, c0, dp2a_hi(wtop, p0, 256u)) >> 9);
+            const int j3 = (int)(dp2a_hi(wbot, c1, dp2a_hi(wtop, p1, 256u)) >> 9);
+            b1 += j0 * ((int)t.x >> 16); b2 += j0 * (int)(short)(t.x & 0xffffu);
+            b1 += j1 * ((int)t.y >> 16); b2 += j1 * (int)(short)(t.y & 0xffffu);
+            b1 += j2 * ((int)t.z >> 16); b2 += j2 * (int)(short)(t.z & 0xffffu);
+            b1 += j3 * ((int)t.w >> 16); b2 += j3 * (int)(short)(t.w & 0xffffu);
+            p0 = c0; p1 = c1;
+        }
+        if (!lane_on) { b1 = 0; b2 = 0; }                       // lanes beyond the last row group
+        S1 += warp_sum_wide(b1); S2 += warp_sum_wide(b2);
+    }
+}
+
+// OpenCV's residual (A.5 step 9): sum |Jw - Iw| over the window, Iw recomputed from the still staged I patch.
+// Same lane mapping as newton_sums; pixels outside the window are masked explicitly.  Runs once per point at most.
+template <int WW, int WH>
+__device__ __noinline__ long long window_err(const LKArgs &a, const uint8_t *jpatch, int ox, int oy, uint32_t wtop, uint32_t wbot,
+                                             const uint8_t *ipatch, int iox, uint32_t iwtop, uint32_t iwbot, int rowbase, int cq,
+                                             bool lane_on)
+{
+    const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
+    const int RG = (WW && WH) ? lk_rg(WW, WH) : a.rg;
+    const int JP = WW ? lk_jpitch(WW) : a.jpitch, IP = WW ? lk_ipitch(WW) : a.ipitch;
+    const uint32_t jsel0 = 0x3210u + 0x1111u * ((uint32_t)ox & 3u), jsel1 = jsel0 + 0x1111u;
+    const uint32_t isel0 = 0x3210u + 0x1111u * ((uint32_t)iox & 3u), isel1 = isel0 + 0x1111u;
+    const uint32_t *jp = reinterpret_cast<const uint32_t *>(jpatch + (oy + rowbase) * JP + ((ox + 4 * cq) & ~3));
+    const uint32_t *ip = reinterpret_cast<const uint32_t *>(ipatch + rowbase * IP + ((iox + 4 * cq) & ~3));
+    uint32_t jp0 = __byte_perm(jp[0], jp[1], jsel0), jp1 = __byte_perm(jp[0], jp[1], jsel1);
+    uint32_t ip0 = __byte_perm(ip[0], ip[1], isel0), ip1 = __byte_perm(ip[0], ip[1], isel1);
+    long long S = 0;
+    for (int r0 = 0; r0 < RG; r0 += 16) {
+        int s = 0;
+        for (int r = r0; r < min(RG, r0 + 16); r++) {
+            jp += JP >> 2; ip += IP >> 2;
+            const uint32_t jc0 = __byte_perm(jp[0], jp[1], jsel0), jc1 = __byte_perm(jp[0], jp[1], jsel1);
+            const uint32_t ic0 = __byte_perm(ip[0], ip[1], isel0), ic1 = __byte_perm(ip[0], ip[1], isel1);
+            if (rowbase + r < winH) {
+                const int d0 = (int)(dp2a_lo(wbot, jc0, dp2a_lo(wtop, jp0, 256u)) >> 9) - (int)(dp2a_lo(iwbot, ic0, dp2a_lo(iwtop, ip0, 256u)) >> 9);
+                const int d1 = (int)(dp2a_lo(wbot, jc1, dp2a_lo(wtop, jp1, 256u)) >> 9) - (int)(dp2a_lo(iwbot, ic1, dp2a_lo(iwtop, ip1, 256u)) >> 9);
+                const int d2 = (int)(dp2a_hi(wbot, jc0, dp2a_hi(wtop, jp0, 256u)) >> 9) - (int)(dp2a_hi(iwbot, ic0, dp2a_hi(iwtop, ip0, 256u)) >> 9);
+                const int d3 = (int)(dp2a_hi(wbot, jc1, dp2a_hi(wtop, jp1, 256u)) >> 9) - (int)(dp2a_hi(iwbot, ic1, dp2a_hi(iwtop, ip1, 256u)) >> 9);
+                const int c = 4 * cq;
+                if (c < winW) s += abs(d0);
+                if (c + 1 < winW) s += abs(d1);
+                if (c + 2 < winW) s += abs(d2);
+                if (c + 3 < winW) s += abs(d3);
+            }
+            jp0 = jc0; jp1 = jc1; ip0 = ic0; ip1 = ic1;
+        }
+        if (!lane_on) s = 0;
+        S += warp_sum_wide(s);
+    }
+    return S;
 }
 
 // One pyramidal pass for one point.  On entry (ox, oy) holds the initial flow if use_init.
@@ -287,20 +426,18 @@ __device__ __forceinline__ void window_pass(const LKArgs &a, const uint8_t *__re
 template <int WW, int WH>
 __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const LKArgs &a, float ptx, float pty,
                                          bool use_init, bool want_status, bool want_err, float &ox, float &oy, int &status,
-                                         float &err, int &iters, unsigned char *slab, int isr, int isw, int jsr, int jsw,
+                                         float &err, int &iters, unsigned char *slab, int rowbase, int cq, bool lane_on,
                                          int lane, const CUtensorMap *mapI, const CUtensorMap *mapJ, const CUtensorMap *mapD,
                                          uint64_t *bars, unsigned &phases)
 {
     const float FLT_SCALE = 1.f / (1 << 20);
     const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
-    const int nstrips = WW ? lk_nstrips(WW) : a.nstrips, strip_cols = WW ? lk_strip_cols(WW) : a.strip_cols;
     const int IPITCH = WW ? lk_ipitch(WW) : a.ipitch, JPITCH = WW ? lk_jpitch(WW) : a.jpitch;
     const int DPITCH = WW ? lk_dpitch(WW) : a.dpitch;
     const int JROWS = winH + 1 + 2 * LK_MARGIN;
-    const int IRPP = 32 / (IPITCH / 4), JRPP = 32 / (JPITCH / 4);
     const float halfx = (winW - 1) * 0.5f, halfy = (winH - 1) * 0.5f;
-    uint2 *win = reinterpret_cast<uint2 *>(slab);
-    uint32_t *dpatch = reinterpret_cast<uint32_t *>(slab + a.off_deriv);
+    uint32_t *tmpl = reinterpret_cast<uint32_t *>(slab);
+    uint32_t *dpatch = reinterpret_cast<uint32_t *>(slab);
     uint8_t *ipatch = slab + a.off_ipatch;
     uint8_t *jpatch = slab + a.off_jpatch;
     status = 1; err = 0.f;
@@ -360,10 +497,10 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
                 tma_load_2d(jpatch, &mapJ[level], px0, py0, &bars[1]);
             }
         }
-        if (!i_tma) stage_bytes(LI, ipxa, ipy, winH + 1, IPITCH, IRPP, isr, isw, ipatch, lane);
+        if (!i_tma) stage_bytes(LI, ipxa, ipy, winH + 1, IPITCH, lane, ipatch);
         if (!d_tma) stage_deriv<WW, WH>(LI, a, ipx, ipy, dpatch, lane);
         cp_async_commit();
-        if (j_ok && !j_tma) stage_bytes(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
+        if (j_ok && !j_tma) stage_bytes(LJ, px0, py0, JROWS, JPITCH, lane, jpatch);
         cp_async_commit();
         cp_async_wait<1>();
         if (i_tma || d_tma) { mbar_wait(&bars[0], phases & 1u); phases ^= 1u; }
@@ -373,42 +510,12 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
         uint32_t wtop, wbot;
         int iw00, iw01, iw10, iw11;
         bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), wtop, wbot, iw00, iw01, iw10, iw11);
+        const uint32_t iwtop = wtop, iwbot = wbot;            // the residual stage at level 0 samples I again
 
-        // ---- template window: T0 = 256 - (Iw << 9), (Ix, Iy); structure tensor ------------------------------------
-        long long sA11 = 0, sA12 = 0, sA22 = 0;
-#pragma unroll
-        for (int s = 0; s < nstrips; s++) {
-            const int cs = s * strip_cols;
-            const bool active = lane < min(strip_cols, winW - cs);
-            const uint8_t *ip = ipatch + (ipx - ipxa) + cs + lane;
-            const uint32_t *dp = dpatch + doff + cs + lane;
-            uint2 *wrow = win + (s * winH) * 32 + lane;
-            int a11 = 0, a12 = 0, a22 = 0;
-            uint32_t ipair = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
-            uint32_t dc = dp[0], dcr = dp[1];
-            int d00x = (int)(short)(dc & 0xffffu), d00y = (int)dc >> 16;
-            int d01x = (int)(short)(dcr & 0xffffu), d01y = (int)dcr >> 16;
-#pragma unroll 4
-            for (int r = 0; r < winH; r++) {
-                const uint32_t cpair = (uint32_t)ip[(r + 1) * IPITCH] | ((uint32_t)ip[(r + 1) * IPITCH + 1] << 8);
-                dc = dp[(r + 1) * DPITCH]; dcr = dp[(r + 1) * DPITCH + 1];
-                const int d10x = (int)(short)(dc & 0xffffu), d10y = (int)dc >> 16;
-                const int d11x = (int)(short)(dcr & 0xffffu), d11y = (int)dcr >> 16;
-                uint32_t v = dp2a_s16u8(wtop, ipair, 256u);
-                v = dp2a_s16u8(wbot, cpair, v);                        // v = taps + 256; Iw = v >> 9
-                const int Ix = (d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
-                const int Iy = (d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
-                uint2 t;
-                t.x = 256u - (v & 0xfffffe00u);
-                t.y = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
-                wrow[r * 32] = t;
-                a11 += Ix * Ix; a12 += Ix * Iy; a22 += Iy * Iy;
-                ipair = cpair; d00x = d10x; d00y = d10y; d01x = d11x; d01y = d11y;
-                __syncwarp();            // the template slab overlaps the Scharr patch rows already consumed (see launch_lk)
-            }
-            if (!active) { a11 = 0; a12 = 0; a22 = 0; }       // lanes beyond the window hold garbage columns: masked here
-            sA11 += warp_sum_wide(a11); sA12 += warp_sum_wide(a12); sA22 += warp_sum_wide(a22);
-        }
+        // ---- template window: (Ix, Iy) per pixel; structure tensor; C1 = sum Iw*Ix, C2 = sum Iw*Iy -------------------------
+        long long sA11, sA12, sA22, sC1, sC2;
+        build_template<WW, WH>(a, ipatch + (ipx - ipxa), dpatch + doff, tmpl, wtop, wbot, iw00, iw01, iw10, iw11, lane,
+                               sA11, sA12, sA22, sC1, sC2);
         cp_async_wait<0>();
         if (j_tma) { mbar_wait(&bars[1], (phases >> 1) & 1u); phases ^= 2u; }
         __syncwarp();
@@ -435,15 +542,15 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             }
             if (!staged || (unsigned)(inx - vx0) > 2u * LK_MARGIN || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
                 vx0 = inx - LK_MARGIN; px0 = vx0 & ~3; py0 = iny - LK_MARGIN;
-                restage_sync(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
+                restage_sync(LJ, px0, py0, JROWS, JPITCH, jpatch, lane);
                 staged = true;
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wtop, wbot, iw00, iw01, iw10, iw11);
             long long sb1, sb2;
-            window_pass<0, WW, WH>(a, jpatch, inx - px0, iny - py0, wtop, wbot, win, lane, sb1, sb2);
+            newton_sums<WW, WH>(a, jpatch, inx - px0, iny - py0, wtop, wbot, tmpl, rowbase, cq, lane_on, sb1, sb2);
             ++iters;
-            const float b1 = __fmul_rn(__ll2float_rn(sb1), FLT_SCALE);
-            const float b2 = __fmul_rn(__ll2float_rn(sb2), FLT_SCALE);
+            const float b1 = __fmul_rn(__ll2float_rn(sb1 - sC1), FLT_SCALE);
+            const float b2 = __fmul_rn(__ll2float_rn(sb2 - sC2), FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -464,12 +571,12 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
             if (!want_err) continue;
             if (!staged || (unsigned)(iqx - vx0) > 2u * LK_MARGIN || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
                 vx0 = iqx - LK_MARGIN; px0 = vx0 & ~3; py0 = iqy - LK_MARGIN;
-                restage_sync(LJ, px0, py0, JROWS, JPITCH, JRPP, jsr, jsw, jpatch, lane);
+                restage_sync(LJ, px0, py0, JROWS, JPITCH, jpatch, lane);
             }
             bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), wtop, wbot, iw00, iw01, iw10, iw11);
-            long long s1, s2;
-            window_pass<1, WW, WH>(a, jpatch, iqx - px0, iqy - py0, wtop, wbot, win, lane, s1, s2);
-            err = __fdiv_rn(__ll2float_rn(s2), (float)(32 * winW * winH));
+            const long long s = window_err<WW, WH>(a, jpatch, iqx - px0, iqy - py0, wtop, wbot, ipatch, ipx - ipxa, iwtop, iwbot,
+                                                   rowbase, cq, lane_on);
+            err = __fdiv_rn(__ll2float_rn(s), (float)(32 * winW * winH));
         }
         __syncwarp();
     }
@@ -478,7 +585,7 @@ __device__ __forceinline__ void lk_point(const LKPyr &PI, const LKPyr &PJ, const
 }
 
 template <int WW, int WH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 lk_kernel(const __grid_constant__ LKArgs a, const __grid_constant__ LKMaps maps)
 {
     extern __shared__ __align__(128) unsigned char lk_smem[];
@@ -491,10 +598,11 @@ lk_kernel(const __grid_constant__ LKArgs a, const __grid_constant__ LKMaps maps)
     __syncwarp();
     unsigned phases = 0u;                                  // bit b = parity to wait for on lk_bars[wib][b]
     unsigned char *slab = lk_smem + (size_t)wib * a.warp_smem;
-    // lane -> (row, word) assignment of the two byte-patch layouts
-    const int ippw = (WW ? lk_ipitch(WW) : a.ipitch) >> 2, jppw = (WW ? lk_jpitch(WW) : a.jpitch) >> 2;
-    const int isr = lane / ippw, isw = lane - isr * ippw;
-    const int jsr = lane / jppw, jsw = lane - jsr * jppw;
+    // Newton mapping of this lane: row group and column quad (lanes beyond the last group idle on group 0's rows)
+    const int NL = WW ? lk_nl(WW) : a.nl, NG = (WW && WH) ? lk_ng(WW, WH) : a.ng, RG = (WW && WH) ? lk_rg(WW, WH) : a.rg;
+    const int grp = lane / NL;
+    const bool lane_on = grp < NG;
+    const int rowbase = lane_on ? grp * RG : 0, cq = lane_on ? lane - grp * NL : 0;
 
   for (;;) {                                            // persistent warp: points are handed out dynamically
     int k = 0;
@@ -514,7 +622,7 @@ lk_kernel(const __grid_constant__ LKArgs a, const __grid_constant__ LKMaps maps)
         const bool want_status = pass == 0 ? a.st1 != nullptr : a.st0 != nullptr;
         const bool want_err = pass == 0 ? a.err1 != nullptr : a.err0 != nullptr;
         lk_point<WW, WH>(a.pyr[pass], a.pyr[pass ^ 1], a, ptx, pty, use_init, want_status, want_err, ox, oy, status, err, iters,
-                         slab, isr, isw, jsr, jsw, lane, maps.imgI[pass], maps.imgJ[pass ^ 1], maps.der[pass], lk_bars[wib],
+                         slab, rowbase, cq, lane_on, lane, maps.imgI[pass], maps.imgJ[pass ^ 1], maps.der[pass], lk_bars[wib],
                          phases);
         if (pass == 0) it_f = iters; else it_b = iters;
         if (lane == 0) {
@@ -542,6 +650,14 @@ lk_kernel(const __grid_constant__ LKArgs a, const __grid_constant__ LKMaps maps)
     }
     __syncwarp();
   }
+    // the last warp to leave re-arms the work queue for the next launch on this stream (no memset node per launch)
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(a.work_counter + 1, 1u) == a.total_warps - 1u) {
+            a.work_counter[0] = 0u; a.work_counter[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 static int fill_pyr(const ibt_pyramid_t *p, LKPyr &o, bool need_deriv)
@@ -567,6 +683,26 @@ static int fill_pyr(const ibt_pyramid_t *p, LKPyr &o, bool need_deriv)
     return IBT_OK;
 }
 
+// Per-device launcher state, shared by every host thread: guarded by one mutex.  A work queue (two words: next point,
+// warps that have left) belongs to one (device, stream): launches on a stream are ordered, and the kernel re-arms its
+// queue when its last warp leaves, so queues of different streams never alias however many launches are in flight.
+struct LKQueue { int dev; cudaStream_t stream; unsigned int *words; };
+static std::mutex lk_mu;
+static std::vector<LKQueue> lk_queues;
+static bool lk_attr_set[64] = {false};
+
+static int lk_queue_for(int dev, cudaStream_t st, unsigned int **out)
+{
+    for (const LKQueue &q : lk_queues)
+        if (q.dev == dev && q.stream == st) { *out = q.words; return IBT_OK; }
+    unsigned int *w = nullptr;
+    IBT_CUDA_TRY(cudaMalloc(&w, 2 * sizeof(unsigned int)));
+    IBT_CUDA_TRY(cudaMemset(w, 0, 2 * sizeof(unsigned int)));      // synchronous: visible to every stream afterwards
+    lk_queues.push_back({dev, st, w});
+    *out = w;
+    return IBT_OK;
+}
+
 static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, int winW, int winH, int max_count,
                      double epsilon, double min_eig, cudaStream_t st)
 {
@@ -581,28 +717,24 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     for (int l = 0; l < A->nlevels; l++)
         if (A->rows[l] != B->rows[l] || A->cols[l] != B->cols[l]) return IBT_E_INVALID;
     a.winW = winW; a.winH = winH;
+    a.nl = lk_nl(winW); a.ng = lk_ng(winW, winH); a.rg = lk_rg(winW, winH);
+    a.trows = lk_trows(winW, winH); a.tcols = lk_tcols(winW);
     a.nstrips = lk_nstrips(winW);
     a.strip_cols = lk_strip_cols(winW);
-    a.tmpl_elems = a.nstrips * winH * 32;
     a.dpitch = lk_dpitch(winW);
     a.ipitch = lk_ipitch(winW);
     a.jpitch = lk_jpitch(winW);
     a.jrows = winH + 1 + 2 * LK_MARGIN;
-    a.irpp = 32 / (a.ipitch / 4);
-    a.jrpp = 32 / (a.jpitch / 4);
-    // The Scharr patch is consumed row by row while the template rows are produced, so it OVERLAPS the template slab of
-    // the last strip: template row r (256 B) is written only after patch row r+1 has been read, and patch row r+1 starts
-    // at or after the end of template row r  <=>  D0 >= off_last + (256 - 4*dpitch) * winH.
-    const size_t off_last = (size_t)(a.nstrips - 1) * winH * 32 * sizeof(uint2);
-    const int slack = 256 - 4 * a.dpitch;
-    size_t d0 = off_last + (slack > 0 ? (size_t)slack * winH : 0);
-    d0 = (d0 + 127) & ~(size_t)127;                     // TMA destinations are 128-byte aligned
-    a.off_deriv = (int)d0;
-    size_t off = d0 + (size_t)(winH + 1) * a.dpitch * 4;
-    if (off < (size_t)a.tmpl_elems * sizeof(uint2)) off = (size_t)a.tmpl_elems * sizeof(uint2);
-    off = (off + 127) & ~(size_t)127;
+    // The Scharr patch is consumed row by row while the template rows are produced, so the template OVERLAYS it: template
+    // row r (4 * tcols bytes at 4 * tcols * r) is written only after patch row r+1 (at 4 * dpitch * (r+1)) has been read
+    // into registers, and tcols <= dpitch keeps every later patch row intact.
+    size_t off = (size_t)a.trows * a.tcols * 4;
+    const size_t dbytes = (size_t)(winH + 1) * a.dpitch * 4;
+    if (off < dbytes) off = dbytes;
+    off = (off + 127) & ~(size_t)127;                     // TMA destinations are 128-byte aligned
     a.off_ipatch = (int)off; off += (size_t)(winH + 1) * a.ipitch; off = (off + 127) & ~(size_t)127;
-    a.off_jpatch = (int)off; off += (size_t)a.jrows * a.jpitch;
+    // Newton lanes of the last row group read (never use) J rows down to trows + 2 * MARGIN
+    a.off_jpatch = (int)off; off += (size_t)(a.trows + 1 + 2 * LK_MARGIN) * a.jpitch;
     a.warp_smem = (int)((off + 127) & ~(size_t)127);
     // tensor maps (boxes: I window ipitch x (winH+1), J patch jpitch x jrows, Scharr window dpitch words x (winH+1))
     static thread_local LKMaps maps;
@@ -626,54 +758,53 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     if (epsilon > 10) epsilon = 10;
     a.eps2 = (float)(epsilon * epsilon);
     a.minEigThr = (float)min_eig;
-    // warps per CTA: the choice that keeps the most warps resident in 227 KB of shared memory per SM
+    // warps per CTA: the choice that keeps the most warps resident in 227 KB of shared memory per SM (at most 24: the
+    // kernel is compiled for 3 CTAs of 8 warps per SM, 85 registers per thread)
     int wpc = 1, best = 0, best_ctas = 1;
     for (int w = 1; w <= 8; w++) {
         const size_t per_cta = (size_t)a.warp_smem * w + 1024;
         if (per_cta > 200 * 1024) break;
         int ctas = (int)((227 * 1024) / per_cta);
         if (ctas > 32) ctas = 32;
+        if (ctas * w > 24) ctas = 24 / w;
         const int warps = ctas * w;
         if (warps >= best) { best = warps; wpc = w; best_ctas = ctas; }
     }
+    if (best == 0) return IBT_E_INVALID;
     if (const char *e = getenv("IBT_LK_WPC")) {             // tuning knob (warps per CTA); the default is the choice above
         const int w = atoi(e);
         if (w >= 1 && w <= 8 && (size_t)a.warp_smem * w + 1024 <= 200 * 1024) {
             wpc = w;
             best_ctas = (int)((227 * 1024) / ((size_t)a.warp_smem * w + 1024));
             if (best_ctas > 32) best_ctas = 32;
+            if (const char *c = getenv("IBT_LK_CTAS")) { const int v = atoi(c); if (v >= 1 && v < best_ctas) best_ctas = v; }
         }
     }
     const size_t smem = (size_t)a.warp_smem * wpc;
-    // per-device state (function attributes and the ring of work counters: one 4-byte slot per launch in flight)
-    constexpr int kMaxDev = 64;
-    static bool attr_set_dev[kMaxDev] = {false};
-    static unsigned int *counters_dev[kMaxDev] = {nullptr};
-    int dev_id = 0;
-    IBT_CUDA_TRY(cudaGetDevice(&dev_id));
-    if (dev_id < 0 || dev_id >= kMaxDev) return IBT_E_INVALID;
-    bool &attr_set = attr_set_dev[dev_id];
-    unsigned int *&counters = counters_dev[dev_id];
-    static unsigned int next_slot = 0;
-    constexpr unsigned int kSlots = 256;
     void (*kern)(const LKArgs, const LKMaps) = lk_kernel<0, 0>;      // generic window; the sizes the configs use are specialised
     if (winW == 21 && winH == 21) kern = lk_kernel<21, 21>;
     else if (winW == 31 && winH == 31) kern = lk_kernel<31, 31>;
     else if (winW == 35 && winH == 35) kern = lk_kernel<35, 35>;
-    if (!attr_set) {
-        const int lim = 200 * 1024;
-        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<21, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<31, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-        IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<35, 35>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-        IBT_CUDA_TRY(cudaMalloc(&counters, kSlots * sizeof(unsigned int)));
-        attr_set = true;
+    int dev_id = 0;
+    IBT_CUDA_TRY(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64) return IBT_E_INVALID;
+    {
+        std::lock_guard<std::mutex> lock(lk_mu);
+        if (!lk_attr_set[dev_id]) {
+            const int lim = 200 * 1024;
+            IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<21, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<31, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            IBT_CUDA_TRY(cudaFuncSetAttribute(lk_kernel<35, 35>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+            lk_attr_set[dev_id] = true;
+        }
+        rc = lk_queue_for(dev_id, st, &a.work_counter);
+        if (rc) return rc;
     }
-    a.work_counter = counters + (next_slot++ % kSlots);
-    IBT_CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), st));
     int blocks = kNumSMs * best_ctas;                   // persistent: one wave, warps pull points until none are left
     const int need = (a.n + wpc - 1) / wpc;
     if (blocks > need) blocks = need;
+    a.total_warps = (unsigned)(blocks * wpc);
     kern<<<blocks, wpc * 32, smem, st>>>(a, maps);          // the tensor maps travel as a __grid_constant__ parameter
     return check_launch("ibt_lk");
 }
