@@ -10,16 +10,23 @@ maxLevel 4, criteria (EPS|COUNT, 30, 0.01), forward-backward check < 1 px.
 One STEP = the body of the reference's frame loop for one new frame (s1_lucaskanade_tracking.py:310-359):
     cvtColor(new frame)  ->  [pyramid + Scharr planes of the new frame]  ->  LK forward  ->  LK backward  ->  FB check
 against the previous frame, on 20 000 points.  goodFeaturesToTrack runs once per track_len frames in the reference; it
-is timed separately ("gftt_ms").  metric = tracked points / s (= 20 000 x frame pairs / s).
+is timed separately ("gftt_ms") and inside "sharded_sequence".  metric = tracked points / s (= 20 000 x frame pairs / s).
 
-  value : inputs (RGB frames, points) resident in HBM; CUDA events on the launch stream; max over ranks.
-  e2e   : the public host API (SequenceTracker.upload/prepare/track) with PINNED HOST frames: every step copies its
+  value : inputs (RGB frames, points) resident in HBM; CUDA events; max over ranks.  Frame pairs of this stream are
+          independent, so consecutive steps are software-pipelined over two CUDA streams (three pyramid slots).
+  e2e   : the public host API (SequenceTracker.upload/prepare + fused LK) with PINNED HOST frames: every step copies its
           72 MB RGB frame host->device and reads p1 / FB distance back to the host, inside the timed region.
+  sharded_sequence : BASELINE configs[2] in small: a fixed list of frames, track_len 2, GFTT re-seeding, sharded by
+          contiguous time blocks over the ranks (sharding.track_sequence_sharded), the NCCL gather of all tracks INSIDE
+          the timed region.  Total work is fixed: this is the strong-scaling line.
+  parity : our outputs on the timed frames against cv2's (BASELINE's four criteria), N = 1 only.
   --impl reference : the reference's own CPU implementation of the same step -- the cv2 calls of s1:311,323,326 +
           the numpy FB arithmetic of s1:329-333 -- on the host cores (falls back to the C oracle port when cv2 is absent).
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import sys
 import threading
@@ -35,7 +42,18 @@ LK = dict(winSize=(31, 31), maxLevel=4, criteria=(3, 30, 0.01))
 GFTT = dict(maxCorners=NPTS, qualityLevel=0.007, minDistance=10, blockSize=10)
 NFRAMES = 6                    # distinct frames in rotation: 6 x 72 MB RGB = 432 MB  >  126 MB L2
 SEED = 7
-WORKLOAD = "config2: 6000x4000 synthetic pair stream, 20k Shi-Tomasi pts, win 31, maxLevel 4, (3,30,0.01), FB<1px"
+METRIC = "tracked points/sec (24MP frame pairs, 20k pts, LK fwd+bwd+FB)"
+# identical in both arms (the driver compares it)
+CONFIG = {
+    "workload": "config2: 6000x4000 synthetic pair stream, 20k Shi-Tomasi pts, win 31, maxLevel 4, (3,30,0.01), FB<1px",
+    "frames_in_rotation": NFRAMES,
+    "l2_policy": "inputs larger than L2: %d distinct 72 MB RGB frames in ping-pong rotation" % NFRAMES,
+    "step": "cvtColor(new) + pyramid/Scharr(new) + LK fwd + LK bwd + FB check vs the previous frame (s1:311,323,326,329-333)",
+    "sharding": "independent frame-pair streams per rank, no data-path collective",
+}
+MIN_TIMED_MS = 500.0           # the timed region is never shorter than this, whatever --steps says (inner repeats)
+SEQ_FRAMES = 8 * 46 + 1        # sharded_sequence: 369 frames = 184 groups of track_len 2 (23 per rank at N = 8)
+SEQ_T = 2
 
 
 def pingpong(i):
@@ -93,7 +111,6 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
-        nv = self.nv
         while not self._halt.is_set():
             self.sample_now()
             self._halt.wait(self.period)
@@ -117,12 +134,12 @@ def make_frames(device):
     return frames
 
 
-def cpu_step_fn():
+def cpu_step_fn(threads=None):
     """The reference's per-frame CPU work (s1:311,323,326,329-333) as a callable; prefers cv2 (the dependency the
     reference itself calls), else the C oracle port."""
     try:
         import cv2
-        cv2.setNumThreads(os.cpu_count())
+        cv2.setNumThreads(os.cpu_count() if threads is None else int(threads))
         kind, cores = "reference", cv2.getNumThreads()
         m = cv2
         desc = "cv2 %s (the OpenCV the reference calls), %d threads" % (cv2.__version__, cores)
@@ -142,8 +159,8 @@ def cpu_step_fn():
     return step, m, kind, cores, desc
 
 
-def run_cpu(frames_np, grays_np, pts_np, steps, warmup, budget_s=None):
-    step, m, kind, cores, desc = cpu_step_fn()
+def run_cpu(frames_np, grays_np, pts_np, steps, warmup, budget_s=None, threads=None):
+    step, m, kind, cores, desc = cpu_step_fn(threads)
     t_total, done = 0.0, 0
     for i in range(warmup + steps):
         a, b = pingpong(i), pingpong(i + 1)
@@ -160,7 +177,74 @@ def run_cpu(frames_np, grays_np, pts_np, steps, warmup, budget_s=None):
                 pairs_per_s=done / t_total), done, t_total
 
 
-def run_from_files(trk, pyr, pts, p1, fbd, h_p1, h_fbd, host_frames, grays, steps, cv):
+# ---------------------------------------------------------------------------------------------------------------------
+class PairPipeline:
+    """The config-2 stream of independent frame pairs, software-pipelined over two CUDA streams and three pyramid slots.
+    Step i runs on stream i & 1: it builds the new frame's gray plane + pyramid into slot i % 3 and tracks the step's
+    points from slot (i-1) % 3 (built by step i-1 on the other stream; one event wait) to it.  Slot i % 3 was last read
+    by step i-2's LK on this same stream, so stream order covers the reuse.  The persistent LK launch of step i+1 fills
+    the SMs as the warps of step i run out of points (a 20 k-point launch otherwise idles ~13 % of its time in the tail)."""
+
+    def __init__(self, trk, dev, frame0, want_status_err=False):
+        import torch
+        from iceberg_tracking_code_b200 import cv
+        self.torch, self.cv, self.trk, self.dev = torch, cv, trk, dev
+        self.streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        self.pyr = [trk.prepare(frame0) for _ in range(3)]
+        self.ready = [torch.cuda.Event() for _ in range(3)]
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        u8 = lambda *s: torch.empty(s, dtype=torch.uint8, device=dev)
+        self.p1 = [f32(NPTS, 2), f32(NPTS, 2)]
+        self.fbd = [f32(NPTS), f32(NPTS)]
+        self.sterr = None
+        if want_status_err:            # what cv2 returns and the reference discards (s1:323,326): st, err of both passes
+            self.sterr = [(u8(NPTS), f32(NPTS), f32(NPTS, 2), u8(NPTS), f32(NPTS)) for _ in range(2)]
+        self.cnt, self.eps = cv._criteria(LK["criteria"])
+        torch.cuda.synchronize()
+
+    def prime(self, frame):
+        """slot 2 (= slot of step -1) must hold the frame that step 0 tracks FROM"""
+        torch = self.torch
+        with torch.cuda.stream(self.streams[1]):
+            self.trk.prepare(frame, reuse=self.pyr[2])
+            self.ready[2].record(self.streams[1])
+
+    def step(self, i, frame, pts, iter_total=None, probe=None):
+        torch, cv = self.torch, self.cv
+        import ctypes as C
+        from iceberg_tracking_code_b200 import _native as N
+        k = i & 1
+        st = self.streams[k]
+        with torch.cuda.stream(st):
+            cur = self.trk.prepare(frame, reuse=self.pyr[i % 3], probe=probe)
+            self.ready[i % 3].record(st)
+            st.wait_event(self.ready[(i - 1) % 3])
+            prev = self.pyr[(i - 1) % 3]
+            p = cv._ptr
+            if self.sterr is None:
+                st1 = err1 = p0r = st0 = err0 = None
+            else:
+                st1, err1, p0r, st0, err0 = self.sterr[k]
+            N.check(N.lib().ibt_lk_fb(C.byref(prev.c), C.byref(cur.c), p(pts), NPTS, 31, 31, self.cnt, self.eps, 1e-4, 1.0,
+                                      p(self.p1[k]), p(st1), p(err1), p(p0r), p(st0), p(err0), p(self.fbd[k]), None, None,
+                                      p(iter_total), cv._stream()), "ibt_lk_fb")
+        return k
+
+    def join(self, stream):
+        """make `stream` wait for everything issued so far on both pipeline streams"""
+        for s in self.streams:
+            ev = self.torch.cuda.Event()
+            ev.record(s)
+            stream.wait_event(ev)
+
+
+def timed_steps(pipe, frames, pts, first, n, iter_total=None, probes=None):
+    for k in range(n):
+        i = first + k
+        pipe.step(i, frames[pingpong(i + 1)], pts[pingpong(i)], iter_total, None if probes is None else probes[k])
+
+
+def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
     """Same step, but the new frame arrives as the JPEG FILE the reference opens with Pillow (s1:310): the bytes are
     copied host->device compressed and csrc/jpeg.cu decodes them straight to the gray plane (bit-exact with Pillow +
     cv2.cvtColor).  The CPU figure beside it is the reference's np.array(Image.open(f)) on the same bytes."""
@@ -173,10 +257,14 @@ def run_from_files(trk, pyr, pts, p1, fbd, h_p1, h_fbd, host_frames, grays, step
         bio = io.BytesIO()
         Image.fromarray(f.numpy()).save(bio, "JPEG")          # Pillow defaults, as the reference's cropping step saves
         blobs.append(bio.getvalue())
-    dec = jpeg.JpegDecoder(trk.device)
+    dec = jpeg.JpegDecoder(dev)
     g = dec.decode(blobs[0], rgb=False, gray=True)[1]
-    ref = cv.cvtColor(torch.from_numpy(np.array(Image.open(io.BytesIO(blobs[0])))).to(trk.device))
+    ref = cv.cvtColor(torch.from_numpy(np.array(Image.open(io.BytesIO(blobs[0])))).to(dev))
     exact = bool(torch.equal(g, ref))
+    h_p1 = torch.empty((NPTS, 2), dtype=torch.float32).pin_memory()
+    h_fbd = torch.empty((NPTS,), dtype=torch.float32).pin_memory()
+    pyr = pipe.pyr
+    p1, fbd = pipe.p1[0], pipe.fbd[0]
 
     def loop(n, first):
         for k in range(n):
@@ -213,6 +301,112 @@ def run_from_files(trk, pyr, pts, p1, fbd, h_p1, h_fbd, host_frames, grays, step
                    "p1 + FB distance read back every step"}
 
 
+def run_sharded_sequence(dev, rank, world, dist):
+    """BASELINE configs[2] in small (reference loop: s1:296-450; its day loop is serial, s1:194-195).  SEQ_FRAMES frames
+    of 24 MP, track_len 2, top-20k Shi-Tomasi re-seeding, consecutive-pair tracking; groups sharded by contiguous time
+    blocks (one halo frame per block), the final gather of every rank's tracks (NCCL) inside the timed region, rank 0
+    then holds all tracks on the host.  Frames are synthesised on device before the timed region."""
+    import torch
+    from iceberg_tracking_code_b200 import sharding as sh, synthetic as syn, tracking as trk
+    total = sh.n_groups(SEQ_FRAMES, SEQ_T)
+    g0, n = sh.shard_groups(total, rank, world)
+    first, last = sh.frame_range(g0, n, SEQ_T)
+    base = syn.base_texture(H, W, 100, device=dev)
+    # the scene drifts and wraps every 12 frames so that a long sequence stays inside the texture margin
+    frames = {t: syn.frame_rgb(base, t % 12, seed=100 + t) for t in range(first, last + 1)}
+    del base
+    torch.cuda.synchronize()
+    imagelist = list(range(SEQ_FRAMES))
+    tracker = trk.SequenceTracker(GFTT, LK)
+    kw = dict(loader=lambda t: frames[t], tracker=tracker, save=False, check_time=False, decode_workers=0)
+    # warm-up (allocator, kernels, NCCL channels) on this rank's first group
+    res = trk.track_sequence(imagelist, None, SEQ_T, 60, first_group=g0, n_groups=1, **kw)
+    sh.gather_results(res, SEQ_T, to_host="rank0")
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = trk.track_sequence(imagelist, None, SEQ_T, 60, first_group=g0, n_groups=n, **kw)
+    torch.cuda.synchronize()
+    t_track = time.perf_counter() - t0
+    allres = sh.gather_results(res, SEQ_T, to_host="rank0")
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    if dist is not None:
+        dist.barrier()
+    tt = torch.tensor([t_all, t_track, t_all - t_track], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_all, t_track, t_gather = [float(v) for v in tt.tolist()]
+    if rank != 0:
+        return None
+    ntracks = sum(len(t) for _s, t, _q in allres if getattr(t, "ndim", 1) == 3)
+    hsh = hashlib.sha1()
+    for _s, t, q in allres:
+        if getattr(t, "ndim", 1) == 3:
+            hsh.update(np.ascontiguousarray(t).tobytes()); hsh.update(np.ascontiguousarray(q).tobytes())
+    pairs = total * SEQ_T
+    return {"workload": "config3 in small: %d synthetic 24 MP frames, track_len %d, top-%d Shi-Tomasi re-seeding every %d frames, "
+                        "win 31, L4; groups sharded by time block, NCCL gather of all tracks inside the timed region"
+                        % (SEQ_FRAMES, SEQ_T, NPTS, SEQ_T),
+            "scaling": "strong", "n_gpus": world, "frames": SEQ_FRAMES, "groups": total, "frame_pairs": pairs,
+            "seconds": t_all, "frame_pairs_per_s": pairs / t_all, "points_per_s": ntracks * SEQ_T / t_all,
+            "tracks_gathered": ntracks, "track_ms_max_rank": t_track * 1e3, "gather_ms": t_gather * 1e3,
+            "ms_per_frame_pair_per_gpu": t_track * 1e3 / (pairs / world),
+            "tracks_sha1": hsh.hexdigest(),
+            "api": "sharding.track_sequence_sharded path: tracking.track_sequence per rank + sharding.gather_results"}
+
+
+def run_parity(frames, grays, pts, trk, dev):
+    """BASELINE's four criteria on the frames the bench times: our outputs vs cv2's on the same inputs (N = 1)."""
+    import torch
+    from iceberg_tracking_code_b200 import cv
+    try:
+        import cv2
+    except Exception as e:                          # noqa: BLE001
+        return {"skipped": "cv2 not importable: %r" % (e,)}
+    cv2.setNumThreads(os.cpu_count())
+    g0, g1 = grays[0].cpu().numpy(), grays[1].cpu().numpy()
+    rgb1 = frames[1].cpu().numpy()
+    out = {"against": "cv2 %s on the timed frames (pair 0 -> 1)" % cv2.__version__}
+    out["gray_bit_exact"] = bool(np.array_equal(cv2.cvtColor(rgb1, cv2.COLOR_BGR2GRAY), g1))
+    pa = cv.FramePyramid(grays[0], LK["winSize"], LK["maxLevel"], True)
+    pb = cv.FramePyramid(grays[1], LK["winSize"], LK["maxLevel"], True)
+    ml, ref = cv2.buildOpticalFlowPyramid(g1, LK["winSize"], LK["maxLevel"], withDerivatives=True)
+    ok = ml == pb.maxLevel
+    for l in range(ml + 1):
+        ok = ok and np.array_equal(pb.levels[l].cpu().numpy(), ref[2 * l]) and np.array_equal(pb.derivs[l].cpu().numpy(), ref[2 * l + 1])
+    out["pyramid_levels_and_scharr_bit_exact"] = bool(ok)
+    c_ref = cv2.goodFeaturesToTrack(g0, **GFTT).reshape(-1, 2)
+    c_our = pts[0].cpu().numpy().reshape(-1, 2)
+    sa = set(map(tuple, c_our.astype(np.int64).tolist())); sb = set(map(tuple, c_ref.astype(np.int64).tolist()))
+    out["corner_overlap"] = len(sa & sb) / max(1, len(sb))
+    nmin = min(len(c_our), len(c_ref))
+    out["corner_count"] = [int(len(c_our)), int(len(c_ref))]
+    out["corner_same_rank_fraction"] = float(np.mean(np.all(c_our[:nmin] == c_ref[:nmin], axis=1))) if nmin else None
+    p0 = c_ref.reshape(-1, 1, 2).astype(np.float32)
+    r = cv.calcOpticalFlowPyrLK_FB(pa, pb, torch.from_numpy(p0).to(dev), **LK)
+    p1c, st1c, _ = cv2.calcOpticalFlowPyrLK(g0, g1, p0, None, **LK)
+    p0rc, st0c, _ = cv2.calcOpticalFlowPyrLK(g1, g0, p1c, None, **LK)
+    p1 = r["p1"].cpu().numpy().reshape(-1, 2); p0r = r["p0r"].cpu().numpy().reshape(-1, 2)
+    st1 = r["st1"].cpu().numpy().reshape(-1); st0 = r["st0"].cpu().numpy().reshape(-1)
+    st1c, st0c = st1c.reshape(-1), st0c.reshape(-1)
+    out["status_agree"] = float(np.mean(np.concatenate([st1 == st1c, st0 == st0c])))
+    both = (st1 == 1) & (st1c == 1)
+    d = np.abs(p1 - p1c.reshape(-1, 2)).max(1)
+    out["pos_within_0.01"] = float(np.mean(d[both] <= 0.01)) if both.any() else None
+    out["pos_max_abs_diff_px"] = float(d[both].max()) if both.any() else None
+    bothb = (st0 == 1) & (st0c == 1)
+    db = np.abs(p0r - p0rc.reshape(-1, 2)).max(1)
+    out["backward_pos_within_0.01"] = float(np.mean(db[bothb] <= 0.01)) if bothb.any() else None
+    distc = np.hypot(*np.abs(p0.reshape(-1, 2) - p0rc.reshape(-1, 2)).T)
+    out["fb_valid_agree"] = float(np.mean((r["dist"].cpu().numpy() < 1) == (distc < 1)))
+    out["points"] = int(p0.shape[0])
+    out["criteria"] = "BASELINE: pyramid bit-exact; status >= 0.995; positions within 0.01 px >= 0.99; corner overlap >= 0.99"
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -221,17 +415,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sequence", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="issue every step on one stream (no overlap between steps)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    steps, warmup = max(1, args.steps), max(3, args.warmup) if args.impl == "ours" else max(0, args.warmup)
+    steps = max(1, args.steps)
 
     import torch
     if args.impl == "reference":
         if rank != 0:
             return 0
-        return main_reference(args, steps, warmup)
+        return main_reference(args, steps, max(0, args.warmup))
+    warmup = max(3, args.warmup)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -253,6 +450,7 @@ def main():
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     pts, gftt_ms = [], []
     for g in grays:
+        cv.goodFeaturesToTrack(g, **GFTT)
         t0.record()
         p = cv.goodFeaturesToTrack(g, **GFTT)
         t1.record(); torch.cuda.synchronize()
@@ -260,81 +458,121 @@ def main():
         assert p is not None and p.shape[0] == NPTS, "synthetic scene must yield %d corners" % NPTS
         pts.append(p.reshape(NPTS, 2).contiguous())
     trk = SequenceTracker(GFTT, LK, count_iterations=True)
-    pyr = [cv.FramePyramid(grays[0], LK["winSize"], LK["maxLevel"], True),
-           cv.FramePyramid(grays[1], LK["winSize"], LK["maxLevel"], True)]
-    nlev = pyr[0].maxLevel + 1
-    p1 = torch.empty((NPTS, 2), dtype=torch.float32, device=dev)
-    fbd = torch.empty((NPTS,), dtype=torch.float32, device=dev)
-
-    def device_step(i, slot, probe=None):
-        """prev pyramid = pyr[slot^1] (frame a), new frame b -> pyr[slot]"""
-        a, b = pingpong(i), pingpong(i + 1)
-        cur = trk.prepare(frames[b], reuse=pyr[slot], probe=probe)
-        cv.lk_fb_into(pyr[slot ^ 1], cur, pts[a], LK, p1, fbd, None, trk.iter_total)
-
-    # pyr[0] must hold frame pingpong(0) before step 0 writes frame pingpong(1) into pyr[1]
-    pyr[0].rebuild(grays[pingpong(0)])
+    pipe = PairPipeline(trk, dev, frames[0])
+    if args.no_pipeline:
+        pipe.streams[1] = pipe.streams[0]
+    nlev = pipe.pyr[0].maxLevel + 1
     own_launches_per_step = 1 + nlev + 1          # gray, one fused pyrDown+Scharr launch per level, fused LK fwd+bwd+FB
-    for i in range(warmup):
-        device_step(i, (i + 1) & 1)
+    main_stream = torch.cuda.current_stream()
+
+    def run_region(pipe_, n, first=0, iter_total=None):
+        """n pipelined steps bracketed by events on the main stream; returns the elapsed ms"""
+        torch.cuda.synchronize()
+        pipe_.prime(frames[pingpong(first)])
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(main_stream)
+        timed_steps(pipe_, frames, pts, first, n, iter_total)
+        pipe_.join(main_stream)
+        e1.record(main_stream)
+        return e0, e1
+
+    # ---- warm-up + pilot (sizes the inner repeats so that the timed region lasts >= MIN_TIMED_MS) -------------------------
+    e0, e1 = run_region(pipe, warmup)
     torch.cuda.synchronize()
+    e0, e1 = run_region(pipe, min(steps, 20))
+    torch.cuda.synchronize()
+    pilot_ms = e0.elapsed_time(e1) / min(steps, 20)
+    repeats = max(1, int(math.ceil(MIN_TIMED_MS / max(1e-3, pilot_ms * steps))))
+    if dist is not None:
+        rp = torch.tensor([repeats], dtype=torch.int64, device=dev)
+        dist.all_reduce(rp, op=dist.ReduceOp.MAX)
+        repeats = int(rp.item())
+
     # ---- timed region: device-resident inputs ---------------------------------------------------------------------
-    probes = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     sampler = ClockSampler(local_rank)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     trk.iter_total.zero_()
     sampler.start()
-    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for k in range(steps):
-        i = warmup + k
-        device_step(i, (i + 1) & 1, probe=probes[k])
-    ev1.record()
+    e0, e1 = run_region(pipe, steps * repeats, 0, trk.iter_total)
     sampler.sample_now()                       # the GPU is still working through the queued steps
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
+    ms = e0.elapsed_time(e1)
+    nsteps = steps * repeats
     iters = int(trk.iter_total.item())
-    alive_frac = float((fbd < 1).float().mean().item())
+    alive_frac = float((pipe.fbd[(nsteps - 1) & 1] < 1).float().mean().item())
+
+    # ---- the same loop returning what cv2 returns: status + err of both passes (OpenCV's level-0 residual stage) ----------
+    pipe_se = PairPipeline(trk, dev, frames[0], want_status_err=True)
+    if args.no_pipeline:
+        pipe_se.streams[1] = pipe_se.streams[0]
+    n_se = max(20, min(nsteps, 200))
+    run_region(pipe_se, 6); torch.cuda.synchronize()
+    e0, e1 = run_region(pipe_se, n_se)
+    torch.cuda.synchronize()
+    ms_se = e0.elapsed_time(e1) / n_se
+    del pipe_se
+
+    # ---- roofline of the HBM-bound part: the whole per-frame prepare (cvtColor + all pyramid levels with Scharr planes),
+    # issued alone on one stream, CUDA events around every prepare and around its level-0 launch --------------------------
+    n_k1 = 60
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k1)]
+    probes = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k1)]
+    torch.cuda._sleep(int(3e7))                 # ~15 ms spin: the host enqueues every prepare before the GPU starts on them
+    for k in range(n_k1 + 4):
+        j = k - 4
+        if j >= 0:
+            ev[j][0].record()
+        trk.prepare(frames[pingpong(k)], reuse=pipe.pyr[k % 3], probe=probes[j] if j >= 0 else None)
+        if j >= 0:
+            ev[j][1].record()
+    torch.cuda.synchronize()
+    prep_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in probes]))
 
     # ---- e2e: public API, pinned host frames, H2D + D2H inside the timed region ----------------------------------------
     host_frames = [f.cpu().pin_memory() for f in frames]
-    h_p1 = torch.empty((NPTS, 2), dtype=torch.float32).pin_memory()
-    h_fbd = torch.empty((NPTS,), dtype=torch.float32).pin_memory()
+    h_p1 = [torch.empty((NPTS, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_fbd = [torch.empty((NPTS,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
 
     def e2e_loop(n, first):
-        handle = trk.upload(host_frames[pingpong(first + 1)])
+        pipe.prime(frames[pingpong(first)])
+        handles = {first: trk.upload(host_frames[pingpong(first + 1)])}
+        if n > 1:
+            handles[first + 1] = trk.upload(host_frames[pingpong(first + 2)])
+        acc = 0.0
         for k in range(n):
             i = first + k
-            slot = (i + 1) & 1
-            cur = trk.prepare(handle, reuse=pyr[slot])
-            if k + 1 < n:
-                handle = trk.upload(host_frames[pingpong(i + 2)])         # prefetch overlaps this step's kernels
-            cv.lk_fb_into(pyr[slot ^ 1], cur, pts[pingpong(i)], LK, p1, fbd, None, None)
-            h_p1.copy_(p1, non_blocking=True); h_fbd.copy_(fbd, non_blocking=True)
-            torch.cuda.current_stream().synchronize()                     # the caller consumes the step's result
-    pyr[0].rebuild(grays[pingpong(0)])
+            s = pipe.step(i, handles.pop(i), pts[pingpong(i)])
+            if k + 2 < n:
+                handles[i + 2] = trk.upload(host_frames[pingpong(i + 3)])      # two uploads in flight on the copy stream
+            with torch.cuda.stream(pipe.streams[s]):
+                h_p1[s].copy_(pipe.p1[s], non_blocking=True); h_fbd[s].copy_(pipe.fbd[s], non_blocking=True)
+                d2h_done[s].record(pipe.streams[s])
+            if k >= 1:                      # the caller consumes step i-1's result while step i runs
+                d2h_done[s ^ 1].synchronize()
+                acc += float(h_fbd[s ^ 1][0])
+        d2h_done[(first + n - 1) & 1].synchronize()
+        acc += float(h_fbd[(first + n - 1) & 1][0])
+        return acc
+    n_e2e = max(steps, int(math.ceil(MIN_TIMED_MS / 1.3)))
     e2e_loop(max(3, warmup // 2) * 2, 0)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    pyr[0].rebuild(grays[pingpong(0)])
     torch.cuda.synchronize()
     tw0 = time.perf_counter()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_loop(steps, 0)
-    e1.record()
+    e2e_loop(n_e2e, 0)
     torch.cuda.synchronize()
-    e2e_wall = (time.perf_counter() - tw0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), e2e_wall)
+    e2e_ms = (time.perf_counter() - tw0) * 1e3            # wall clock around host-visible results (>= any device-side figure)
     h2d = int(host_frames[0].numel())
-    d2h = int(h_p1.numel() * 4 + h_fbd.numel() * 4)
+    d2h = int(h_p1[0].numel() * 4 + h_fbd[0].numel() * 4)
 
     # ---- from files: every step starts from the JPEG bytes the reference reads at s1:310 (host memory).  Every rank runs its
     # own stream (weak scaling); the aggregate uses the slowest rank's time.  3.8 MB instead of 72 MB cross PCIe per step.
@@ -342,7 +580,7 @@ def main():
     try:
         if dist is not None:
             dist.barrier()
-        from_files = run_from_files(trk, pyr, pts, p1, fbd, h_p1, h_fbd, host_frames, grays, min(steps, 60), cv)
+        from_files = run_from_files(trk, pipe, pts, host_frames, min(max(steps, 60), 200), cv, dev)
     except ImportError as e:                        # Pillow missing on the box: the section is skipped, not faked
         from_files = {"skipped": repr(e)}
     if dist is not None and "ms_per_step" in from_files:
@@ -351,11 +589,28 @@ def main():
         from_files["ms_per_step"] = float(tf.item())
         from_files["value"] = world * NPTS / (from_files["ms_per_step"] * 1e-3)
 
+    # ---- parity on the timed frames (N = 1) and the CPU rows need the host copies; free the rest first ---------------------
+    parity = None
+    if world == 1:
+        parity = run_parity(frames, grays, pts, trk, dev)
+    frames_np = grays_np = pts_np = None
+    if world == 1 and not args.no_cpu_baseline:
+        frames_np = [f.numpy() for f in host_frames]
+        grays_np = [g.cpu().numpy() for g in grays]
+        pts_np = [p.cpu().numpy().reshape(-1, 1, 2) for p in pts]
+    del pipe, frames, grays, host_frames
+    torch.cuda.empty_cache()
+
+    # ---- sharded sequence (strong scaling, gather inside the timed region) --------------------------------------------------
+    seq = None
+    if not args.no_sequence:
+        seq = run_sharded_sequence(dev, rank, world, dist)
+
     # ---- reduce over ranks (max time) -------------------------------------------------------------------------------------
     if dist is not None:
-        t = torch.tensor([ms, e2e_ms, k1_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_ms, k1_ms, prep_ms, ms_se], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, k1_ms = [float(v) for v in t.tolist()]
+        ms, e2e_ms, k1_ms, prep_ms, ms_se = [float(v) for v in t.tolist()]
         it_t = torch.tensor([iters], dtype=torch.int64, device=dev)
         dist.all_reduce(it_t)
         iters = int(it_t.item())
@@ -371,53 +626,66 @@ def main():
         pass
     peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback 6.65 TB/s")
     n0 = H * W
-    h1, w1 = (H + 1) // 2, (W + 1) // 2
-    k1_bytes = n0 + 4 * n0 + h1 * w1               # read level 0 once, write (dx,dy) int16, write level 1
-    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
-    value = world * NPTS * steps / (ms * 1e-3)
+    lev = [(H, W)]
+    for _ in range(nlev - 1):
+        lev.append(((lev[-1][0] + 1) // 2, (lev[-1][1] + 1) // 2))
+    npx = [h * w for h, w in lev]
+    # K0 reads 3 B + writes 1 B per pixel; K1 reads every level once, writes levels >= 1 and 4 B of Scharr per pixel
+    prep_bytes = 4 * n0 + sum(npx) + sum(npx[1:]) + 4 * sum(npx)
+    k1_bytes = n0 + 4 * n0 + npx[1]                # level 0 alone: read level 0 once, write (dx,dy) int16, write level 1
+    achieved = prep_bytes / (prep_ms * 1e-3) / 1e9
+    value = world * NPTS * nsteps / (ms * 1e-3)
     out = {
-        "metric": "tracked points/sec (24MP frame pairs, 20k pts, LK fwd+bwd+FB)", "value": value, "unit": "points/s",
-        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "metric": METRIC, "value": value, "unit": "points/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / nsteps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 2x2 solve", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_in_rotation": NFRAMES,
-                   "l2_policy": "inputs larger than L2: %d distinct 72 MB RGB frames in ping-pong rotation" % NFRAMES,
-                   "step": "cvtColor(new) + pyramid/Scharr(new) + fused LK fwd+bwd+FB vs cached previous pyramid",
-                   "sharding": "independent frame-pair streams per rank, no data-path collective"},
-        "frame_pairs_per_s": world * steps / (ms * 1e-3),
+        "config": CONFIG,
+        "inner_repeats": repeats, "timed_steps": nsteps, "timed_region_ms": ms,
+        "pipelining": "none (one stream)" if args.no_pipeline else "consecutive (independent) frame pairs overlap on two CUDA streams, three pyramid slots",
+        "frame_pairs_per_s": world * nsteps / (ms * 1e-3),
         "feature_pair_iterations_per_s": iters / (ms * 1e-3),
-        "iterations_per_point_pair": iters / (world * NPTS * steps),
+        "iterations_per_point_pair": iters / (world * NPTS * nsteps),
         "fb_valid_fraction_last_step": alive_frac,
+        "with_status_err": {"ms_per_step": ms_se, "value": world * NPTS / (ms_se * 1e-3), "unit": "points/s", "steps": n_se,
+                            "note": "same step with st/err buffers of both passes passed (what cv2 returns, s1:323,326): "
+                                    "adds OpenCV's level-0 bounds test and residual"},
         "gftt_ms": float(np.median(gftt_ms)),
-        "gpu_launches": own_launches_per_step * steps,
+        "gpu_launches": own_launches_per_step * nsteps,
         "clocks": clocks,
-        "e2e": {"value": world * NPTS * steps / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
-                "api": "SequenceTracker.upload/prepare + fused LK, pinned host frames, p1 + FB distance read back every step"},
-        "roofline": {"kernel": "pyr_level_kernel<deriv,down> level 0 (fused pyrDown + Scharr)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                     "bytes_per_launch": k1_bytes, "avg_launch_ms": k1_ms, "traffic": None},
-        "lk": {"kernel": "lk_kernel (fwd+bwd+FB, warp per point)", "bound": "issue/shared-memory (not HBM)",
-               "iterations_per_s": iters / (ms * 1e-3), "target_iterations_per_s": 200e6},
+        "e2e": {"value": world * NPTS * n_e2e / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / n_e2e, "steps": n_e2e,
+                "api": "SequenceTracker.upload/prepare + fused LK (ibt_lk_fb), pinned host frames, p1 + FB distance read back "
+                       "to the host every step; wall clock"},
+        "roofline": {"kernel": "per-frame prepare: gray_c3_vec_kernel + pyr_level_tma_kernel x %d levels (fused pyrDown + Scharr)" % nlev,
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "bytes_per_launch": prep_bytes, "avg_launch_ms": prep_ms, "traffic": None,
+                     "launches": 1 + nlev,
+                     "level0": {"kernel": "pyr_level_tma_kernel<deriv,down,4> level 0", "bytes_per_launch": k1_bytes,
+                                "avg_launch_ms": k1_ms, "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9,
+                                "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak}},
+        "lk": {"kernel": "lk_kernel<31,31> (fwd+bwd+FB, warp per point)", "bound": "instruction issue (not HBM, not tensor)",
+               "iterations_per_s": iters / (ms * 1e-3), "target_iterations_per_s": 200e6,
+               "share_of_step": "see profiles/ launch list"},
     }
     if from_files is not None:
         out["from_files"] = from_files
+    if seq is not None:
+        out["sharded_sequence"] = seq
+    if parity is not None:
+        out["parity"] = parity
     traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(traffic_file):
         try:
             tf = json.load(open(traffic_file))
-            out["roofline"]["traffic"] = tf.get("dram_bytes_per_launch")
-            if tf.get("ncu_launch_us"):
-                # for information: the kernel's own duration under ncu (no event / launch gap around a ~22 us kernel);
-                # "achieved" and "frac" above stay the CUDA-event figures measured in this run
-                out["roofline"]["ncu_launch_ms"] = tf["ncu_launch_us"] * 1e-3
-                out["roofline"]["frac_at_ncu_duration"] = k1_bytes / (tf["ncu_launch_us"] * 1e-6) / 1e9 / peak
+            out["roofline"]["traffic"] = tf.get("dram_bytes_per_prepare", tf.get("dram_bytes_per_launch"))
+            out["roofline"]["traffic_source"] = tf.get("source")
+            out["lk"]["ncu"] = tf.get("lk")
         except Exception:                           # noqa: BLE001
             pass
-    if world == 1 and not args.no_cpu_baseline:
-        frames_np = [f.numpy() for f in host_frames]
-        grays_np = [g.cpu().numpy() for g in grays]
-        pts_np = [p.cpu().numpy().reshape(-1, 1, 2) for p in pts]
+    if frames_np is not None:
         cb, _, _ = run_cpu(frames_np, grays_np, pts_np, steps=100, warmup=1, budget_s=12.0)
+        c1, _, _ = run_cpu(frames_np, grays_np, pts_np, steps=3, warmup=0, budget_s=8.0, threads=1)
+        cb["one_thread"] = {"value": c1["value"], "unit": "points/s", "cores": 1, "sample": c1["sample"]}
         out["cpu_baseline"] = cb
     print(json.dumps(out))
     if dist is not None:
@@ -426,7 +694,7 @@ def main():
 
 
 def main_reference(args, steps, warmup):
-    """Reference arm: the CPU path of the reference on this box's host cores, same config / metric / unit."""
+    """Reference arm: the CPU path of the reference on this box's host cores, same config / metric / unit / steps / warmup."""
     import torch
     from iceberg_tracking_code_b200 import synthetic as syn
     dev = "cuda" if torch.cuda.is_available() else "cpu"          # frame SYNTHESIS only; the timed path is pure CPU
@@ -439,15 +707,14 @@ def main_reference(args, steps, warmup):
     for g in grays_np:
         p = m.goodFeaturesToTrack(g, **GFTT)
         pts_np.append(np.ascontiguousarray(p, np.float32).reshape(-1, 1, 2))
-    steps = min(steps, 40)
-    cb, done, t_total = run_cpu(frames_np, grays_np, pts_np, steps=steps, warmup=min(warmup, 2), budget_s=120.0)
+    cb, done, t_total = run_cpu(frames_np, grays_np, pts_np, steps=steps, warmup=warmup)
     out = {
-        "impl": "reference", "metric": "tracked points/sec (24MP frame pairs, 20k pts, LK fwd+bwd+FB)",
-        "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus, "steps": done, "warmup": min(warmup, 2),
+        "impl": "reference", "metric": METRIC,
+        "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus, "steps": done, "warmup": warmup,
         "ms_per_step": t_total / done * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int16 fixed point + f32 (OpenCV CPU)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_in_rotation": NFRAMES,
-                   "step": "cv2.cvtColor + cv2.calcOpticalFlowPyrLK fwd + bwd + numpy FB (s1:311,323,326,329-333)"},
+        "config": CONFIG,
+        "reference_calls": "cv2.cvtColor + cv2.calcOpticalFlowPyrLK fwd + bwd + numpy FB (s1:311,323,326,329-333)",
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -68,10 +68,11 @@ def _ptr(t):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cvtColor(src, code=COLOR_BGR2GRAY, coeffset=0):
+def cvtColor(src, code=COLOR_BGR2GRAY, coeffset=0, dst=None):
     """cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) (s1:311).  (H,W,3|4) u8 -> (H,W) u8.  Channel 0 gets the
     0.114 weight whatever it holds; the reference feeds PIL's RGB array under the BGR code and that quirk is kept.
-    coeffset 0 = OpenCV 4.x 15-bit coefficients, 1 = OpenCV 3.x 14-bit."""
+    coeffset 0 = OpenCV 4.x 15-bit coefficients, 1 = OpenCV 3.x 14-bit.
+    dst: preallocated contiguous (H,W) u8 CUDA tensor to write into (steady-state loops allocate nothing)."""
     if code not in (COLOR_BGR2GRAY, COLOR_RGB2GRAY):
         raise error("cvtColor: only COLOR_BGR2GRAY / COLOR_RGB2GRAY are implemented")
     as_np = _is_np(src)
@@ -81,7 +82,11 @@ def cvtColor(src, code=COLOR_BGR2GRAY, coeffset=0):
     if code == COLOR_RGB2GRAY:
         s = s[..., [2, 1, 0] + ([3] if s.shape[2] == 4 else [])].contiguous()
     H, W, cn = s.shape
-    dst = torch.empty((H, W), dtype=torch.uint8, device=s.device)
+    if dst is None:
+        dst = torch.empty((H, W), dtype=torch.uint8, device=s.device)
+    elif not (isinstance(dst, torch.Tensor) and dst.is_cuda and dst.dtype == torch.uint8 and tuple(dst.shape) == (H, W)
+              and dst.is_contiguous()):
+        raise error("cvtColor: dst must be a contiguous (H,W) u8 CUDA tensor")
     if H and W:
         N.check(N.lib().ibt_gray_u8(_ptr(s), H, W, cn, W * cn, _ptr(dst), W, int(coeffset), _stream()), "ibt_gray_u8")
     return _out(dst, as_np)

@@ -64,7 +64,9 @@ def gather_results(results, track_len, device=None, to_host=True):
     the list [(seed_index, tracks, trackquality)] of all ranks in time order (all_gather of sizes, then all_gather of
     the padded payloads).  Without an initialised process group this is the identity.
     to_host=False leaves the gathered payloads on the device (the groups are views into one CUDA tensor per array):
-    copying 8 ranks' worth of a day (0.6 GB) into fresh host memory costs more than tracking the day."""
+    copying 8 ranks' worth of a day (0.6 GB) into fresh host memory costs more than tracking the day.
+    to_host="rank0" is the single-writer mode: rank 0 copies the gathered arrays to the host once (one D2H per array),
+    the other ranks keep device views."""
     import torch.distributed as dist
     meta, tracks, quality = pack_results(results, track_len)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -72,6 +74,7 @@ def gather_results(results, track_len, device=None, to_host=True):
     world = dist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    host = bool(to_host) if to_host != "rank0" else dist.get_rank() == 0
     T = int(track_len)
     sizes = torch.tensor([meta.shape[0], tracks.shape[0]], dtype=torch.int64, device=device)
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
@@ -97,8 +100,8 @@ def gather_results(results, track_len, device=None, to_host=True):
         return [out[r * n:(r + 1) * n] for r in range(world)]
 
     metas = allg(padded(meta, gmax, torch.int64))
-    trs = allg(padded(tracks, mmax, torch.float32), to_host) if mmax else [np.zeros((0, T + 1, 2), np.float32)] * world
-    qus = allg(padded(quality, mmax, torch.float32), to_host) if mmax else [np.zeros((0, T), np.float32)] * world
+    trs = allg(padded(tracks, mmax, torch.float32), host) if mmax else [np.zeros((0, T + 1, 2), np.float32)] * world
+    qus = allg(padded(quality, mmax, torch.float32), host) if mmax else [np.zeros((0, T), np.float32)] * world
     out = []
     for r in range(world):
         g, m = int(all_sizes[r, 0]), int(all_sizes[r, 1])

@@ -140,21 +140,33 @@ class SequenceTracker:
     def prepare(self, frame, reuse=None, probe=None):
         """frame (H,W,3|4) u8 RGB (host numpy / device tensor / upload() handle) or (H,W) u8 gray -> FramePyramid with
         derivatives = np.array(Image.open(...)) upload + cv2.cvtColor (s1:310-311) + the pyramids cv2 builds inside LK.
-        reuse: a FramePyramid of the same frame size to rebuild in place (steady state allocates nothing)."""
-        if isinstance(frame, tuple):
-            handle = frame
-        elif isinstance(frame, np.ndarray) or (isinstance(frame, torch.Tensor) and not frame.is_cuda):
-            handle = self.stager.upload(frame)
-        else:
-            handle = None
-        if handle is not None:
-            frame, ev = handle
-            torch.cuda.current_stream().wait_event(ev)
-            frame.record_stream(torch.cuda.current_stream())
-        gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY) if frame.ndim == 3 else frame
-        if reuse is not None:
-            return reuse.rebuild(gray, probe)
-        return cv.FramePyramid(gray, self.lk_params["winSize"], self.lk_params["maxLevel"], True)
+        reuse: a FramePyramid of the same frame size to rebuild in place; its gray plane is reused too, so the steady
+        state allocates nothing (and streams never share allocator blocks)."""
+        with torch.cuda.device(self.device):
+            if isinstance(frame, tuple):
+                handle = frame
+            elif isinstance(frame, np.ndarray) or (isinstance(frame, torch.Tensor) and not frame.is_cuda):
+                handle = self.stager.upload(frame)
+            else:
+                handle = None
+            if handle is not None:
+                frame, ev = handle
+                torch.cuda.current_stream().wait_event(ev)
+                frame.record_stream(torch.cuda.current_stream())
+            if frame.ndim == 3:
+                own = getattr(reuse, "_own_gray", None) if reuse is not None else None
+                if own is not None and tuple(own.shape) != tuple(frame.shape[:2]):
+                    own = None
+                gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY, dst=own)
+            else:
+                gray = frame
+            if reuse is not None:
+                pyr = reuse.rebuild(gray, probe)
+            else:
+                pyr = cv.FramePyramid(gray, self.lk_params["winSize"], self.lk_params["maxLevel"], True)
+            if frame.ndim == 3:
+                pyr._own_gray = gray
+            return pyr
 
     # -- group life cycle -----------------------------------------------------------------------------
     def seed(self, pyr, mask=None, track_len=2, points=None):
