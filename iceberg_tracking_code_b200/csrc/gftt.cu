@@ -1,23 +1,30 @@
 // K2: Shi-Tomasi corner seeding.  Replaces
 // cv2.goodFeaturesToTrack(frame_gray, mask=mask, **feature_params), s1_lucaskanade_tracking.py:437
-// (s0_1_test_lucaskanade_tracking.py:167).
+// (s0_1_test_lucaskanade_tracking.py:167).  Two launches, no host round trip in between:
 //
-//   K2a  eig_kernel      Sobel3 -> (sx^2, sx*sy, sy^2) as exact integers -> blockSize^2 box sum by a horizontal
-//                        window sum + a vertical sliding sum (int32, exact, REFLECT_101 on the product image)
-//                        -> lambda_min map + masked global max (ordered-uint atomicMax).  OpenCV rounds every
-//                        product to float before its double box sum; the exact sums sit in the middle of that
-//                        rounding noise (~1e-7 relative, same size as the wheel's own irreproducibility).
-//   K2b  nms_kernel      threshold (q * max), 3x3 non-maximum suppression, mask, 1-px border; candidates appended
-//                        as 64-bit keys (response bits << 32 | linear address)
-//        radix sort      stable LSD, 8-bit digits, warp match_any ranking: all candidates ordered by
-//                        (response desc, address desc) exactly like OpenCV's comparator -> rank
-//   K2c  cells + rounds  OpenCV's sequential greedy min-distance culling restated as a fixed point that is safe to run
-//                        in parallel: candidates are bucketed on OpenCV's cell grid (cell = round(minDistance)); a
-//                        candidate is REJECTED once a stronger candidate within minDistance in its 3x3 cell
-//                        neighbourhood is ACCEPTED, ACCEPTED once all such candidates are REJECTED.  Decisions are
-//                        final and monotone, so rounds may read each other's fresh or stale states.
-//        compaction      accepted candidates in rank order -> (x, y) float32, first maxCorners
+//   K2a  eig_nms_kernel  one warp per (112-column strip, row chunk), 4 adjacent columns per lane, rows top to bottom:
+//                        Sobel3 by dp4a on funnel-shifted byte windows -> (sx^2, sx*sy, sy^2) as exact int32 -> vertical
+//                        sliding sum through a per-warp shared-memory ring (16-byte accesses) -> horizontal window sum
+//                        by lane shuffles -> lambda_min (OpenCV's float formula) -> running masked maximum and 3x3
+//                        non-maximum test on a three-row register ring.  The response map is never written: a pixel
+//                        above the final threshold is a candidate iff it is a RAW 3x3 maximum (every neighbour above it
+//                        would be above the threshold too), so raw maxima are appended as 64-bit keys
+//                        (response bits << 32 | linear address) and thresholded afterwards; a running lower bound of
+//                        the threshold (quality * maximum seen so far) drops most weak maxima on the spot.
+//                        OpenCV rounds every product to float before its double box sum; the exact integer sums sit in
+//                        the middle of that rounding noise (~1e-7 relative, the size of the wheel's own
+//                        irreproducibility).  REFLECT_101 acts on the product image, as in OpenCV's boxFilter.
+//   K2b  gftt_select_kernel  ONE persistent launch (148 CTAs, software grid barrier) that runs the whole selection with
+//                        device-side control flow: threshold + response histogram -> top-k prefilter (the strongest
+//                        ~4*maxCorners candidates; all of them if culling leaves too few) -> stable LSD radix sort on the
+//                        response bytes (ties by address) -> OpenCV's cell grid as CSR lists -> OpenCV's sequential greedy
+//                        min-distance culling restated as a monotone fixed point over ranks (a candidate is REJECTED once
+//                        a stronger candidate within minDistance in its 3x3 cell neighbourhood is ACCEPTED, ACCEPTED once
+//                        all such candidates are REJECTED; rounds repeat until none is undecided) -> ordered compaction
+//                        -> (x, y) float32 of the first maxCorners, count left in device memory.
+//   ibt_min_eigen_f32    (cornerMinEigenVal test hook) keeps the map-writing eig_kernel.
 #include "common.cuh"
+#include <float.h>
 #include <stddef.h>
 #include <string.h>
 
@@ -125,143 +132,334 @@ static int launch_eig(const uint8_t *gray, int H, int W, int64_t pitch, int bs, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2b
+// K2a/K2b fused: response + raw 3x3 maxima, one warp per (column strip, row chunk)
 enum : uint8_t { ST_UNDECIDED = 0, ST_ACCEPTED = 1, ST_REJECTED = 2 };
 
 struct GfttCounters {
     uint32_t maxbits;        // enc_f32 of the masked maximum, 0 = no allowed pixel
-    uint32_t ncand;          // candidates found (may exceed capacity)
+    uint32_t ncand;          // raw maxima appended by K2a (may exceed capacity)
+    uint32_t nsel;           // candidates selected for ranking
     uint32_t nacc;           // accepted after culling
+    uint32_t nout;           // corners written (min(nacc, limit))
+    int32_t error;           // IBT_E_* raised on the device (capacity)
+    uint32_t bar;            // grid barrier of K2b
     uint32_t pad;
     uint32_t remaining[64];  // undecided candidates left after round k (mod 64)
-    uint32_t hist[4096];     // candidates per top-12-bit bin of the ordered response (top-k prefilter)
+    uint32_t hist[4096];     // candidates above the threshold per top-12-bit bin of the ordered response
 };
 
-__device__ __forceinline__ float tozero(float v, float thr) { return v > thr ? v : 0.f; }
+constexpr int EN_WARPS = 4;               // warps per CTA (independent of each other: no block-level barrier)
+constexpr int EN_COLS = 128;              // support columns per warp (4 per lane)
+constexpr int EN_CB = 192;                // per-warp candidate buffer, flushed to global memory at >= 128 entries
+constexpr int EN_PAD = 32;                // generic blockSize: padding of the shared row buffer on both sides
 
-// one thread per 4 x 4 pixel block: six row loads (float4 + the two neighbouring columns) issued up front
-constexpr int NMS_RY = 4;
+struct EigNmsArgs {
+    const uint8_t *img; int H, W; int64_t pitch;
+    const uint8_t *mask; int64_t mask_pitch;
+    int bs; double s2, s2h, quality;
+    GfttCounters *cnt; unsigned long long *keys; uint32_t cap;
+    int outw, left, nstrips, rows_per_job, njobs, word_ok;
+    int warp_smem_ints;      // per-warp shared memory (ring + candidate buffer + row buffer), in ints
+};
 
-__global__ void __launch_bounds__(256)
-nms_kernel(const float *__restrict__ eig, int H, int W, const uint8_t *__restrict__ mask, int64_t mask_pitch,
-           double quality, GfttCounters *__restrict__ cnt, unsigned long long *__restrict__ keys, uint32_t cap)
+__device__ __forceinline__ int dp4a_uu_(uint32_t a, uint32_t b) { return (int)__dp4a(a, b, 0u); }
+__device__ __forceinline__ int dp4a_us_(uint32_t a, int b)
 {
-    const uint32_t mb = cnt->maxbits;
-    if (!mb) return;
-    __shared__ uint32_t shist[4096];                              // per-CTA response histogram (top-k prefilter)
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x) shist[i] = 0;
-    __syncthreads();
-    const float thr = (float)((double)dec_f32(mb) * quality);
-    const int wq = (W + 3) >> 2;                                  // 4-pixel groups per row
-    const int hq = (H - 2 + NMS_RY - 1) / NMS_RY;                 // row groups over rows 1 .. H-2
-    const int64_t total = (int64_t)hq * wq;
-    const int lane = threadIdx.x & 31;
-    const bool vec = (W & 3) == 0;                                // rows are 16-byte aligned: one float4 + two scalars per row
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t g = base + threadIdx.x;
-        uint32_t flags = 0;                                       // bit (4 * row + col)
-        float r[NMS_RY + 2][6];                                   // rows y0-1 .. y0+RY, columns x0-1 .. x0+4, thresholded
-        int y0 = 0, x0 = 0;
-        if (g < total) {
-            const int gy = (int)(g / wq);
-            y0 = gy * NMS_RY + 1;
-            x0 = (int)(g - (int64_t)gy * wq) * 4;
-#pragma unroll
-            for (int dy = 0; dy < NMS_RY + 2; dy++) {
-                const int yy = min(y0 - 1 + dy, H - 1);
-                const float *row = eig + (int64_t)yy * W;
-                if (vec) {
-                    const float4 m = __ldg(reinterpret_cast<const float4 *>(row + x0));
-                    r[dy][0] = x0 > 0 ? __ldg(row + x0 - 1) : 0.f;
-                    r[dy][1] = m.x; r[dy][2] = m.y; r[dy][3] = m.z; r[dy][4] = m.w;
-                    r[dy][5] = x0 + 4 < W ? __ldg(row + x0 + 4) : 0.f;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 6; c++) {
-                        const int xx = x0 - 1 + c;
-                        r[dy][c] = (xx >= 0 && xx < W) ? __ldg(row + xx) : 0.f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int dy = 0; dy < NMS_RY + 2; dy++)
-#pragma unroll
-                for (int c = 0; c < 6; c++) r[dy][c] = tozero(r[dy][c], thr);
-#pragma unroll
-            for (int ry = 0; ry < NMS_RY; ry++) {
-                const int y = y0 + ry;
-                if (y > H - 2) break;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int xx = x0 + i;
-                    const float v = r[ry + 1][i + 1];
-                    if (xx >= 1 && xx <= W - 2 && v != 0.f) {
-                        float m = v;
-#pragma unroll
-                        for (int dy = 0; dy < 3; dy++)
-                            m = fmaxf(m, fmaxf(r[ry + dy][i], fmaxf(r[ry + dy][i + 1], r[ry + dy][i + 2])));
-                        if (v == m && (!mask || mask[(int64_t)y * mask_pitch + xx])) flags |= 1u << (4 * ry + i);
-                    }
-                }
-            }
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0));
+    return d;
+}
+
+// horizontal taps of one image row for the lane's 4 pixels: hx = I[x+1] - I[x-1], hs = I[x-1] + 2 I[x] + I[x+1]
+template <bool BORDER, bool WANT_HS>
+__device__ __forceinline__ void row_taps(const uint8_t *__restrict__ row, int c0, const int *pc, const int *pm, const int *pp,
+                                         int *hx, int *hs)
+{
+    if (!BORDER) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + c0));
+        const uint32_t L = __shfl_up_sync(0xffffffffu, w, 1), R = __shfl_down_sync(0xffffffffu, w, 1);
+        // byte windows (x-1, x, x+1, .) of the four pixels
+        const uint32_t w0 = __funnelshift_r(L, w, 24), w2 = __funnelshift_r(w, R, 8), w3 = __funnelshift_r(w, R, 16);
+        hx[0] = dp4a_us_(w0, 0x000100FF); hx[1] = dp4a_us_(w, 0x000100FF);
+        hx[2] = dp4a_us_(w2, 0x000100FF); hx[3] = dp4a_us_(w3, 0x000100FF);
+        if (WANT_HS) {
+            hs[0] = dp4a_uu_(w0, 0x00010201u); hs[1] = dp4a_uu_(w, 0x00010201u);
+            hs[2] = dp4a_uu_(w2, 0x00010201u); hs[3] = dp4a_uu_(w3, 0x00010201u);
         }
-        const int n = __popc(flags);
-        // warp-aggregated append
-        int pre = n;
+    } else {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int tmp = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += tmp; }
-        const int wtot = __shfl_sync(0xffffffffu, pre, 31);
-        if (wtot) {
-            uint32_t basepos = 0;
-            if (lane == 31) basepos = atomicAdd(&cnt->ncand, (uint32_t)wtot);
-            basepos = __shfl_sync(0xffffffffu, basepos, 31);
-            uint32_t pos = basepos + pre - n;
-#pragma unroll
-            for (int ry = 0; ry < NMS_RY; ry++)
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (flags & (1u << (4 * ry + i))) {
-                        const uint32_t e = enc_f32(r[ry + 1][i + 1]);
-                        if (pos < cap) keys[pos] = ((unsigned long long)e << 32) | (uint32_t)((y0 + ry) * W + x0 + i);
-                        atomicAdd(&shist[e >> 20], 1u);
-                        pos++;
-                    }
+        for (int k = 0; k < 4; k++) {
+            const int m = __ldg(row + pm[k]), p = __ldg(row + pp[k]);
+            hx[k] = p - m;
+            if (WANT_HS) hs[k] = m + 2 * (int)__ldg(row + pc[k]) + p;
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x)
-        if (shist[i]) atomicAdd(&cnt->hist[i], shist[i]);
+}
+
+// window sum over columns [x + a0, x + a0 + BS) of a plane held as 4 values per lane (compile-time blockSize):
+// the BS + 3 values the lane's four windows touch are gathered from the neighbouring lanes, then three slides.
+template <int BS>
+__device__ __forceinline__ void hbox_shfl(const int *v, int *out, int lane)
+{
+    constexpr int A0 = -(BS / 2);
+    int g[BS + 3];
+#pragma unroll
+    for (int i = 0; i < BS + 3; i++) {
+        const int rel = A0 + i;                              // column offset from the lane's first pixel
+        const int dl = rel >= 0 ? rel / 4 : -((3 - rel) / 4);  // floor(rel / 4)
+        const int comp = rel - 4 * dl;
+        g[i] = dl == 0 ? v[comp] : __shfl_sync(0xffffffffu, v[comp], lane + dl);
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < BS; i++) s += g[i];
+    out[0] = s;
+#pragma unroll
+    for (int k = 1; k < 4; k++) { s += g[k - 1 + BS] - g[k - 1]; out[k] = s; }
+}
+
+// runtime blockSize: the plane goes through a padded shared-memory row, one direct sum + three slides per lane
+__device__ __forceinline__ void hbox_smem(const int *v, int *out, int *rowbuf, int bs, int lane)
+{
+    const int a0 = -(bs / 2);
+    __syncwarp();
+    *reinterpret_cast<int4 *>(rowbuf + EN_PAD + 4 * lane) = make_int4(v[0], v[1], v[2], v[3]);
+    __syncwarp();
+    const int *p = rowbuf + EN_PAD + 4 * lane + a0;
+    int s = 0;
+    for (int j = 0; j < bs; j++) s += p[j];
+    out[0] = s;
+#pragma unroll
+    for (int k = 1; k < 4; k++) { s += p[k - 1 + bs] - p[k - 1]; out[k] = s; }
+}
+
+template <int BS, bool MASK, bool BORDER>
+__device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int chunk, int *wsm, int lane)
+{
+    const int bs = BS ? BS : a.bs;
+    const int a0 = -(bs / 2);
+    const int H = a.H, W = a.W;
+    const int ox0 = strip * a.outw;                       // first output column of the strip
+    const int c0 = ox0 - a.left + 4 * lane;               // support column of this lane's pixel 0 (multiple of 4)
+    const int Y0 = chunk * a.rows_per_job, Y1 = min(H, Y0 + a.rows_per_job);
+    const int ey0 = max(0, Y0 - 1), ey1 = min(H - 1, Y1);         // response rows needed (NMS halo rows included)
+    int *ring = wsm;                                              // [bs][3][128]
+    unsigned long long *cbuf = reinterpret_cast<unsigned long long *>(wsm + bs * 3 * EN_COLS);
+    int *rowbuf = reinterpret_cast<int *>(cbuf + EN_CB);          // generic blockSize only: [EN_PAD + 128 + EN_PAD]
+    unsigned outmask = 0, candmask = 0;                           // pixels this lane owns / may emit
+    int pc[4], pm[4], pp[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int c = c0 + k;
+        const bool own = c >= ox0 && c < ox0 + a.outw && c < W;
+        if (own) outmask |= 1u << k;
+        if (own && c >= 1 && c <= W - 2) candmask |= 1u << k;
+        pc[k] = r101(c, W);                                       // REFLECT_101 on the product image ...
+        pm[k] = r101(pc[k] - 1, W); pp[k] = r101(pc[k] + 1, W);   // ... whose Sobel reflects the source again
+    }
+    int vxx[4] = {0, 0, 0, 0}, vxy[4] = {0, 0, 0, 0}, vyy[4] = {0, 0, 0, 0};
+    float m3a[4], m3b[4], eprev[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { m3a[k] = m3b[k] = -FLT_MAX; eprev[k] = 0.f; }
+    unsigned mprev = 0;                                           // mask bits of the previous response row
+    float lmax = -FLT_MAX;
+    bool have_max = false;
+    float thr_lb = 0.f;
+    {
+        const uint32_t mb = *reinterpret_cast<volatile const uint32_t *>(&a.cnt->maxbits);
+        if (mb) thr_lb = fmaxf(0.f, (float)((double)dec_f32(mb) * a.quality));
+    }
+    int ncb = 0;
+    auto flush = [&]() {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&a.cnt->ncand, (unsigned)ncb);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < ncb; i += 32)
+            if (base + i < a.cap) a.keys[base + i] = cbuf[i];
+        ncb = 0;
+        __syncwarp();
+    };
+    const int p_first = ey0 + a0, p_last = ey1 + a0 + bs - 1;
+    int slot = 0;
+    for (int p = p_first; p <= p_last; p++) {
+        // ---- products of support row p ------------------------------------------------------------------------
+        const int rp = r101(p, H);
+        const uint8_t *rowA = a.img + (int64_t)r101(rp - 1, H) * a.pitch;
+        const uint8_t *rowB = a.img + (int64_t)rp * a.pitch;
+        const uint8_t *rowC = a.img + (int64_t)r101(rp + 1, H) * a.pitch;
+        int hxA[4], hsA[4], hxB[4], hxC[4], hsC[4];
+        row_taps<BORDER, true>(rowA, c0, pc, pm, pp, hxA, hsA);
+        row_taps<BORDER, false>(rowB, c0, pc, pm, pp, hxB, nullptr);
+        row_taps<BORDER, true>(rowC, c0, pc, pm, pp, hxC, hsC);
+        int nxx[4], nxy[4], nyy[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int sx = hxA[k] + 2 * hxB[k] + hxC[k], sy = hsC[k] - hsA[k];
+            nxx[k] = sx * sx; nxy[k] = sx * sy; nyy[k] = sy * sy;
+        }
+        // ---- vertical sliding sums (ring of the last bs product rows) ----------------------------------------------------
+        int4 *rg = reinterpret_cast<int4 *>(ring + slot * 3 * EN_COLS) + lane;
+        if (p - p_first >= bs) {
+            const int4 o0 = rg[0], o1 = rg[EN_COLS / 4], o2 = rg[2 * (EN_COLS / 4)];
+            vxx[0] -= o0.x; vxx[1] -= o0.y; vxx[2] -= o0.z; vxx[3] -= o0.w;
+            vxy[0] -= o1.x; vxy[1] -= o1.y; vxy[2] -= o1.z; vxy[3] -= o1.w;
+            vyy[0] -= o2.x; vyy[1] -= o2.y; vyy[2] -= o2.z; vyy[3] -= o2.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { vxx[k] += nxx[k]; vxy[k] += nxy[k]; vyy[k] += nyy[k]; }
+        rg[0] = make_int4(nxx[0], nxx[1], nxx[2], nxx[3]);
+        rg[EN_COLS / 4] = make_int4(nxy[0], nxy[1], nxy[2], nxy[3]);
+        rg[2 * (EN_COLS / 4)] = make_int4(nyy[0], nyy[1], nyy[2], nyy[3]);
+        slot = slot + 1 == bs ? 0 : slot + 1;
+        const int y = p - a0 - bs + 1;                    // response row completed by this product row
+        if (y < ey0) continue;
+        // ---- horizontal window sums, lambda_min --------------------------------------------------------------------------
+        int bxx[4], bxy[4], byy[4];
+        if (BS) {
+            hbox_shfl<BS ? BS : 1>(vxx, bxx, lane); hbox_shfl<BS ? BS : 1>(vxy, bxy, lane); hbox_shfl<BS ? BS : 1>(vyy, byy, lane);
+        } else {
+            hbox_smem(vxx, bxx, rowbuf, bs, lane); hbox_smem(vxy, bxy, rowbuf, bs, lane); hbox_smem(vyy, byy, rowbuf, bs, lane);
+        }
+        float e[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float fa = (float)((double)bxx[k] * a.s2h), fb = (float)((double)bxy[k] * a.s2);
+            const float fc = (float)((double)byy[k] * a.s2h);
+            const float d = __fsub_rn(fa, fc);
+            e[k] = __fsub_rn(__fadd_rn(fa, fc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(fb, fb))));
+        }
+        // ---- masked maximum over the pixels this lane owns ------------------------------------------------------------------
+        unsigned mcur = 0xfu;
+        if (MASK) {
+            mcur = 0;
+            if (y < H) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((outmask >> k) & 1u) mcur |= (a.mask[(int64_t)y * a.mask_pitch + c0 + k] ? 1u : 0u) << k;
+            }
+        }
+        if (y >= Y0 && y < Y1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (((outmask & mcur) >> k) & 1u) { lmax = fmaxf(lmax, e[k]); have_max = true; }
+        }
+        // ---- 3x3 raw maxima of the previous row -------------------------------------------------------------------------------
+        const float el = __shfl_up_sync(0xffffffffu, e[3], 1), er = __shfl_down_sync(0xffffffffu, e[0], 1);
+        float m3c[4];
+        m3c[0] = fmaxf(fmaxf(el, e[0]), e[1]); m3c[1] = fmaxf(fmaxf(e[0], e[1]), e[2]);
+        m3c[2] = fmaxf(fmaxf(e[1], e[2]), e[3]); m3c[3] = fmaxf(fmaxf(e[2], e[3]), er);
+        const int yc = y - 1;
+        if (yc >= max(Y0, 1) && yc < Y1 && yc <= H - 2) {
+            unsigned flags = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float v = eprev[k];
+                if ((((candmask & mprev) >> k) & 1u) && v > thr_lb && v == fmaxf(fmaxf(m3a[k], m3b[k]), m3c[k])) flags |= 1u << k;
+            }
+            if (__any_sync(0xffffffffu, flags != 0)) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const bool f = (flags >> k) & 1u;
+                    const unsigned ball = __ballot_sync(0xffffffffu, f);
+                    if (f) cbuf[ncb + __popc(ball & ((1u << lane) - 1u))] =
+                        ((unsigned long long)enc_f32(eprev[k]) << 32) | (uint32_t)(yc * W + c0 + k);
+                    ncb += __popc(ball);
+                }
+                __syncwarp();
+                if (ncb >= 128) flush();
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { m3a[k] = m3b[k]; m3b[k] = m3c[k]; eprev[k] = e[k]; }
+        mprev = mcur;
+        if ((y & 31) == 31) {                             // tighten the threshold bound with what this warp has seen
+            float wm = lmax;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+            if (wm > 0.f) thr_lb = fmaxf(thr_lb, (float)((double)wm * a.quality));
+        }
+    }
+    if (ncb) flush();
+    uint32_t lbits = have_max ? enc_f32(lmax) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lbits = max(lbits, __shfl_xor_sync(0xffffffffu, lbits, o));
+    if (lane == 0 && lbits) atomicMax(&a.cnt->maxbits, lbits);
+}
+
+template <int BS, bool MASK>
+__global__ void __launch_bounds__(EN_WARPS * 32)
+eig_nms_kernel(const __grid_constant__ EigNmsArgs a)
+{
+    extern __shared__ __align__(16) int en_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int job = blockIdx.x * EN_WARPS + wib;
+    if (job >= a.njobs) return;
+    const int strip = job % a.nstrips, chunk = job / a.nstrips;
+    int *wsm = en_smem + (size_t)wib * a.warp_smem_ints;
+    // fast path: the warp's 128 support columns are real, 4-byte aligned pixels (no reflection, word loads)
+    const int lx0 = strip * a.outw - a.left;
+    if (a.word_ok && lx0 >= 0 && lx0 + EN_COLS <= a.W) eig_nms_job<BS, MASK, false>(a, strip, chunk, wsm, lane);
+    else eig_nms_job<BS, MASK, true>(a, strip, chunk, wsm, lane);
+}
+
+struct EigNmsGeom { int outw, left, nstrips, rows_per_job, nchunks, warp_smem_ints; };
+static EigNmsGeom eig_nms_geom(int H, int W, int bs)
+{
+    EigNmsGeom g;
+    const int half = bs / 2;                                  // window offsets [-half, bs - 1 - half]
+    g.left = (2 + half + 3) & ~3;                             // Sobel edge + window reach + NMS halo, rounded to words
+    g.outw = (126 - g.left - (bs - 1 - half)) & ~3;           // owned columns per warp
+    g.nstrips = (W + g.outw - 1) / g.outw;
+    g.warp_smem_ints = bs * 3 * EN_COLS + EN_CB * 2 + (EN_PAD + EN_COLS + EN_PAD);
+    // rows per job: one wave of warps over the GPU (warm-up costs bs + 2 rows per job), at least 32 rows
+    int wps = (int)((227 * 1024) / ((size_t)g.warp_smem_ints * 4 * EN_WARPS + 1024)) * EN_WARPS;      // resident warps per SM
+    if (wps < 1) wps = 1;
+    if (wps > 16) wps = 16;
+    int chunks = (kNumSMs * wps) / g.nstrips;
+    if (chunks < 1) chunks = 1;
+    int rows = (H + chunks - 1) / chunks;
+    if (rows < 32) rows = 32;
+    g.rows_per_job = rows;
+    g.nchunks = (H + rows - 1) / rows;
+    return g;
+}
+
+template <int BS>
+static int launch_eig_nms_bs(const EigNmsArgs &a, cudaStream_t st)
+{
+    const size_t smem = (size_t)a.warp_smem_ints * 4 * EN_WARPS;
+    const int blocks = (a.njobs + EN_WARPS - 1) / EN_WARPS;
+    if (a.mask) {
+        if (smem > 48 * 1024) IBT_CUDA_TRY(cudaFuncSetAttribute(eig_nms_kernel<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eig_nms_kernel<BS, true><<<blocks, EN_WARPS * 32, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024) IBT_CUDA_TRY(cudaFuncSetAttribute(eig_nms_kernel<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eig_nms_kernel<BS, false><<<blocks, EN_WARPS * 32, smem, st>>>(a);
+    }
+    return check_launch("eig_nms_kernel");
+}
+
+static int launch_eig_nms(const uint8_t *gray, int H, int W, int64_t pitch, int bs, const uint8_t *mask, int64_t mask_pitch,
+                          double quality, GfttCounters *cnt, unsigned long long *keys, uint32_t cap, cudaStream_t st)
+{
+    if (bs < 1 || bs > MAX_BLOCK) return IBT_E_INVALID;
+    const EigNmsGeom g = eig_nms_geom(H, W, bs);
+    EigNmsArgs a;
+    a.img = gray; a.H = H; a.W = W; a.pitch = pitch; a.mask = mask; a.mask_pitch = mask_pitch; a.bs = bs;
+    const float scale = (float)(1.0 / (4.0 * bs * 255.0));       // OpenCV's Sobel scale for ksize 3
+    a.s2 = (double)scale * (double)scale; a.s2h = a.s2 * 0.5;     // the halving of a and c folded in (exact: power of two)
+    a.quality = quality; a.cnt = cnt; a.keys = keys; a.cap = cap;
+    a.outw = g.outw; a.left = g.left; a.nstrips = g.nstrips; a.rows_per_job = g.rows_per_job;
+    a.njobs = g.nstrips * g.nchunks; a.warp_smem_ints = g.warp_smem_ints;
+    a.word_ok = (reinterpret_cast<uintptr_t>(gray) % 4 == 0) && (pitch % 4 == 0);
+    if (bs == 10) return launch_eig_nms_bs<10>(a, st);
+    if (bs == 3) return launch_eig_nms_bs<3>(a, st);
+    return launch_eig_nms_bs<0>(a, st);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Radix sort (ascending, 64-bit keys, stable LSD, 8-bit digits).
 constexpr int RS_WARPS = 8, RS_STEPS = 16, RS_TILE = RS_WARPS * RS_STEPS * 32;   // 4096 keys per block
-
-__global__ void __launch_bounds__(256)
-complement_kernel(unsigned long long *__restrict__ keys, uint32_t n)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = ~keys[i];                   // ascending sort of ~key = descending (response, address)
-}
-
-// keep the candidates whose response bin is >= min_bin (the strongest ones), complemented for the ascending sort
-__global__ void __launch_bounds__(256)
-select_kernel(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t min_bin, unsigned long long *__restrict__ out,
-              uint32_t *__restrict__ out_count)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long k = 0;
-    bool keep = false;
-    if (i < n) { k = keys[i]; keep = (uint32_t)(k >> 52) >= min_bin; }
-    const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-    if (ballot) {
-        const int lane = threadIdx.x & 31;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(out_count, (uint32_t)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) out[base + __popc(ballot & ((1u << lane) - 1))] = ~k;
-    }
-}
 
 __global__ void __launch_bounds__(256)
 rs_count_kernel(const unsigned long long *__restrict__ keys, uint32_t n, int shift, uint32_t nblocks,
@@ -416,125 +614,390 @@ unsigned long long *radix_sort_u64_bytes(unsigned long long *keys0, unsigned lon
     return src;
 }
 
-// After the stable sort on the response bytes, equal responses keep their arrival order: order each run of equal
-// responses by address (complemented keys ascending = address descending, OpenCV's tie-break).  Runs are rare and short;
-// the first element of a run sorts it.
-__global__ void __launch_bounds__(256)
-tie_fix_kernel(unsigned long long *__restrict__ keys, uint32_t n)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t v = (uint32_t)(keys[i] >> 32);
-    if (i > 0 && (uint32_t)(keys[i - 1] >> 32) == v) return;       // not the first of its run
-    uint32_t e = i + 1;
-    while (e < n && (uint32_t)(keys[e] >> 32) == v) e++;
-    for (uint32_t a = i + 1; a < e; a++) {                          // insertion sort of keys[i..e)
-        const unsigned long long k = keys[a];
-        uint32_t b = a;
-        while (b > i && keys[b - 1] > k) { keys[b] = keys[b - 1]; b--; }
-        keys[b] = k;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// K2c: cell grid + culling rounds.  sorted[r] = ~key of rank r (rank 0 = strongest).
-__global__ void __launch_bounds__(256)
-cell_count_kernel(const unsigned long long *__restrict__ sorted, uint32_t n, int W, int cell, int gw,
-                  uint32_t *__restrict__ pos, uint32_t *__restrict__ cell_count, uint8_t *__restrict__ state)
-{
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const uint32_t idx = (uint32_t)(~sorted[r]);
-    const uint32_t y = idx / W, x = idx - y * W;
-    pos[r] = x | (y << 16);
-    state[r] = ST_UNDECIDED;
-    atomicAdd(&cell_count[(y / cell) * gw + x / cell], 1u);
-}
+// K2b: the whole selection in ONE persistent launch.  sorted[r] = ~key of rank r (rank 0 = strongest).
+constexpr int SEL_THREADS = 256;
 
-__global__ void __launch_bounds__(256)
-cell_fill_kernel(const uint32_t *__restrict__ pos, uint32_t n, int cell, int gw, const uint32_t *__restrict__ cell_start,
-                 uint32_t *__restrict__ cell_fill, uint32_t *__restrict__ items)
-{
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const uint32_t p = pos[r];
-    const uint32_t c = ((p >> 16) / cell) * gw + (p & 0xffffu) / cell;
-    items[cell_start[c] + atomicAdd(&cell_fill[c], 1u)] = r;
-}
+struct SelArgs {
+    GfttCounters *cnt;
+    unsigned long long *keys0, *keys1, *keys2;     // candidates (kept), ping-pong buffers of the sort
+    uint32_t cap;
+    uint32_t *blockhist, *pos, *cell_start, *cell_fill, *items, *blockcnt, *scan_scratch;
+    uint8_t *state;
+    int H, W, maxCorners, cull, cell, gw, gh;
+    uint32_t ncells, limit;
+    double quality;
+    float md2;
+    float *out_xy;
+    int *out_count;                                // device
+};
 
-__global__ void __launch_bounds__(256)
-cull_round_kernel(const uint32_t *__restrict__ pos, uint32_t n, const uint32_t *__restrict__ cell_start,
-                  const uint32_t *__restrict__ items, volatile uint8_t *state, GfttCounters *__restrict__ cnt,
-                  int cell, int gw, int gh, float md2, int round)
+// all CTAs of the launch are resident (grid <= SM count): a monotone counter is a barrier
+__device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target)
 {
-    if (round > 0 && cnt->remaining[(round - 1) & 63] == 0) return;      // already converged
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    bool left = false;
-    if (r < n && state[r] == ST_UNDECIDED) {
-        const uint32_t p = pos[r];
-        const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
-        const int cx = x / cell, cy = y / cell;
-        const int x1 = max(cx - 1, 0), x2 = min(cx + 1, gw - 1), y1 = max(cy - 1, 0), y2 = min(cy + 1, gh - 1);
-        bool blocked = false, killed = false;
-        for (int yy = y1; yy <= y2 && !killed; yy++) {
-            // the cells x1..x2 of one grid row are contiguous in the CSR layout
-            const uint32_t kb = cell_start[yy * gw + x1], ke = cell_start[yy * gw + x2 + 1];
-            for (uint32_t k = kb; k < ke; k++) {
-                const uint32_t q = items[k];
-                if (q >= r) continue;                                    // only stronger candidates matter
-                const uint32_t pq = pos[q];
-                const float dx = (float)(x - (int)(pq & 0xffffu)), dy = (float)(y - (int)(pq >> 16));
-                if (dx * dx + dy * dy < md2) {
-                    const uint8_t s = state[q];
-                    if (s == ST_ACCEPTED) { killed = true; break; }
-                    if (s == ST_UNDECIDED) blocked = true;
-                }
-            }
-        }
-        if (killed) state[r] = ST_REJECTED;
-        else if (!blocked) state[r] = ST_ACCEPTED;
-        else left = true;
-    }
-    const uint32_t ballot = __ballot_sync(0xffffffffu, left);
-    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&cnt->remaining[round & 63], (uint32_t)__popc(ballot));
-}
-
-// accepted candidates in rank order: per-block counts -> scan -> scatter of (x, y)
-__global__ void __launch_bounds__(256)
-accepted_count_kernel(const uint8_t *__restrict__ state, uint32_t n, uint32_t *__restrict__ block_counts)
-{
-    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
-    const int c = __syncthreads_count(r < n && state[r] == ST_ACCEPTED);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
-}
-
-__global__ void __launch_bounds__(256)
-write_corners_kernel(const uint32_t *__restrict__ pos, const uint8_t *__restrict__ state, uint32_t n,
-                     const uint32_t *__restrict__ block_off, uint32_t limit, float *__restrict__ out_xy)
-{
-    __shared__ uint32_t wbase[8];
-    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool a = r < n && (!state || state[r] == ST_ACCEPTED);
-    const uint32_t ballot = __ballot_sync(0xffffffffu, a);
-    if (lane == 0) wbase[wid] = __popc(ballot);
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t run = block_off ? block_off[blockIdx.x] : blockIdx.x * 256;
-        for (int w = 0; w < 8; w++) { const uint32_t c = wbase[w]; wbase[w] = run; run += c; }
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*reinterpret_cast<volatile uint32_t *>(bar) < target) { }
+        __threadfence();
     }
     __syncthreads();
-    if (!a) return;
-    const uint32_t m = wbase[wid] + __popc(ballot & ((1u << lane) - 1));
-    if (m >= limit) return;
-    const uint32_t p = pos[r];
-    out_xy[2 * m] = (float)(p & 0xffffu);
-    out_xy[2 * m + 1] = (float)(p >> 16);
+}
+
+// exclusive scan of v[0..len) (shared memory, len <= 4096) by the 256 threads of the CTA; returns the total
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t *v, int len, uint32_t *wtot /* [9] shared */)
+{
+    const int per = (len + SEL_THREADS - 1) / SEL_THREADS;
+    const int i0 = threadIdx.x * per;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t sum = 0;
+    for (int i = i0; i < min(len, i0 + per); i++) sum += v[i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) wtot[wid] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int w = 0; w < 8; w++) { const uint32_t c = wtot[w]; wtot[w] = run; run += c; } wtot[8] = run; }
+    __syncthreads();
+    uint32_t run = wtot[wid] + inc - sum;
+    for (int i = i0; i < min(len, i0 + per); i++) { const uint32_t c = v[i]; v[i] = run; run += c; }
+    __syncthreads();
+    return wtot[8];
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+gftt_select_kernel(const __grid_constant__ SelArgs a)
+{
+    __shared__ uint32_t sh[4096];
+    __shared__ uint32_t wcount[RS_WARPS][256];
+    __shared__ uint32_t wtot[9];
+    __shared__ uint32_t s_misc[8];
+    GfttCounters *cnt = a.cnt;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t gtid = blockIdx.x * SEL_THREADS + tid, gsize = gridDim.x * SEL_THREADS;
+    uint32_t bar_target = 0;
+    const uint32_t mb = __ldcg(&cnt->maxbits);
+    const uint32_t ncand = __ldcg(&cnt->ncand);
+    if (!mb || !ncand || ncand > a.cap) {                 // uniform over the grid: nothing to select (or overflow)
+        if (gtid == 0) {
+            if (ncand > a.cap) cnt->error = IBT_E_CAPACITY;
+            cnt->nout = 0; *a.out_count = 0;
+        }
+        return;
+    }
+    const float thr = (float)((double)dec_f32(mb) * a.quality);
+    const uint32_t thrbits = enc_f32(thr);                // enc is order preserving: v > thr  <=>  enc(v) > thrbits
+
+    // ---- phase 1: response histogram of the candidates above the threshold; zero the cell grid ------------------------------
+    for (int i = tid; i < 4096; i += SEL_THREADS) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t i = gtid; i < ncand; i += gsize) {
+        const uint32_t e = (uint32_t)(a.keys0[i] >> 32);
+        if (e > thrbits) atomicAdd(&sh[e >> 20], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < 4096; i += SEL_THREADS) if (sh[i]) atomicAdd(&cnt->hist[i], sh[i]);
+    grid_barrier(&cnt->bar, bar_target);
+
+    // ---- phase 2 (every CTA, redundantly): the response bin that keeps the strongest ~4 * maxCorners candidates ------------
+    for (int i = tid; i < 4096; i += SEL_THREADS) sh[i] = __ldcg(&cnt->hist[i]);
+    __syncthreads();
+    {
+        // bins in DESCENDING order so that an exclusive scan gives "candidates stronger than this bin"
+        uint32_t lo = 4096, hi = 0;
+        for (int i = tid; i < 4096; i += SEL_THREADS) if (sh[i]) { lo = min(lo, (uint32_t)i); hi = max(hi, (uint32_t)i); }
+        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if (tid == 0) { s_misc[0] = 4096; s_misc[1] = 0; }
+        __syncthreads();
+        if (lane == 0) { atomicMin(&s_misc[0], lo); atomicMax(&s_misc[1], hi); }
+        __syncthreads();
+    }
+    const uint32_t lo_bin_all = s_misc[0], hi_bin = s_misc[1];
+    // reverse in place (pairs) then scan
+    for (int i = tid; i < 2048; i += SEL_THREADS) { const uint32_t t = sh[i]; sh[i] = sh[4095 - i]; sh[4095 - i] = t; }
+    __syncthreads();
+    const uint32_t total = block_scan_excl(sh, 4096, wtot);       // sh[j] = candidates in bins > 4095 - j
+    if (total == 0) {                                            // nothing above the threshold (cannot happen: the max is)
+        if (gtid == 0) { cnt->nout = 0; *a.out_count = 0; }
+        return;
+    }
+    const uint64_t want = a.maxCorners > 0 ? (uint64_t)a.maxCorners * 4 + 1024 : 0;
+    uint32_t min_bin = 0;
+    bool subset = false;
+    if (a.maxCorners > 0 && a.cull && (uint64_t)total > 2 * want) {
+        // smallest j with (candidates in bins >= 4095 - j) >= want, i.e. sh[j + 1] >= want (sh[4096] = total)
+        if (tid == 0) s_misc[2] = 4095;
+        __syncthreads();
+        for (int j = tid; j < 4096; j += SEL_THREADS) {
+            const uint32_t incl = j == 4095 ? total : sh[j + 1];
+            if (incl >= want) atomicMin(&s_misc[2], (uint32_t)j);
+        }
+        __syncthreads();
+        const uint32_t j = s_misc[2];
+        const uint32_t b = 4095 - j;
+        const uint32_t cum = j == 4095 ? total : sh[j + 1];
+        if (b > 0 && cum < total) { min_bin = b; subset = true; }
+    }
+    __syncthreads();
+
+    uint32_t nacc = 0, n = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        // attempt 0 may rank the strongest candidates only; if culling leaves fewer than maxCorners of them, attempt 1 repeats
+        // with every candidate.  The greedy order makes the prefix exact either way: whether a candidate is accepted depends
+        // on stronger candidates only.
+        if (attempt == 1) { min_bin = 0; subset = false; }
+        const uint32_t lo_bin = max(lo_bin_all, min_bin);
+        // ---- select (complemented keys: the ascending sort of ~key is the descending (response, address) order) ----------------
+        for (uint32_t i0 = blockIdx.x * SEL_THREADS; i0 < ncand; i0 += gsize) {
+            const uint32_t i = i0 + tid;
+            unsigned long long k = 0;
+            bool keep = false;
+            if (i < ncand) { k = a.keys0[i]; const uint32_t e = (uint32_t)(k >> 32); keep = e > thrbits && (e >> 20) >= min_bin; }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+            if (ballot) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cnt->nsel, (uint32_t)__popc(ballot));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) a.keys1[base + __popc(ballot & ((1u << lane) - 1u))] = ~k;
+            }
+        }
+        // zero the cell grid and the round counters while we are at it
+        if (a.cull) for (uint32_t i = gtid; i < a.ncells + 1; i += gsize) { a.cell_start[i] = 0; if (i < a.ncells) a.cell_fill[i] = 0; }
+        if (gtid < 64) cnt->remaining[gtid] = 0;
+        grid_barrier(&cnt->bar, bar_target);
+        n = __ldcg(&cnt->nsel);
+        unsigned long long *src = a.keys1, *dst = a.keys2;
+
+        // ---- stable LSD radix sort on the response bytes (the top byte is usually the same for every candidate) -------------
+        if (n > 1) {
+            const uint32_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+            const int last_pass = (lo_bin >> 4) == (hi_bin >> 4) ? 6 : 7;
+            for (int p = 4; p <= last_pass; p++) {
+                const int shift = 8 * p;
+                for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // digit counts per tile
+                    __syncthreads();
+                    sh[tid] = 0;
+                    __syncthreads();
+                    const uint32_t base = tile * RS_TILE;
+                    for (uint32_t i = tid; i < RS_TILE; i += SEL_THREADS) {
+                        const uint32_t g = base + i;
+                        if (g < n) atomicAdd(&sh[(uint32_t)((src[g] >> shift) & 0xff)], 1u);
+                    }
+                    __syncthreads();
+                    a.blockhist[tid * ntiles + tile] = sh[tid];
+                }
+                grid_barrier(&cnt->bar, bar_target);
+                // digit bases: thread d sums its digit over all tiles, exclusive scan over the 256 digits
+                {
+                    uint32_t rs = 0;
+                    for (uint32_t t = 0; t < ntiles; t++) rs += __ldcg(&a.blockhist[tid * ntiles + t]);
+                    __syncthreads();
+                    sh[tid] = rs;
+                    __syncthreads();
+                    block_scan_excl(sh, 256, wtot);
+                }
+                const uint32_t digit_base = sh[tid];
+                __syncthreads();
+                for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // scatter
+                    uint32_t before = 0;
+                    for (uint32_t t = 0; t < tile; t++) before += __ldcg(&a.blockhist[tid * ntiles + t]);
+                    for (int i = tid; i < RS_WARPS * 256; i += SEL_THREADS) (&wcount[0][0])[i] = 0;
+                    __syncthreads();
+                    const uint32_t wbase = tile * RS_TILE + wid * (RS_STEPS * 32);
+                    unsigned long long k[RS_STEPS];
+                    uint32_t rank[RS_STEPS];
+#pragma unroll
+                    for (int s = 0; s < RS_STEPS; s++) {
+                        const uint32_t g = wbase + s * 32 + lane;
+                        const bool valid = g < n;
+                        k[s] = valid ? src[g] : 0ull;
+                        const uint32_t d = (uint32_t)((k[s] >> shift) & 0xff);
+                        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                        uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane) & vmask;
+                        if (!valid) peers = 0;
+                        const uint32_t bef = __popc(peers & ((1u << lane) - 1u));
+                        uint32_t prev = 0;
+                        if (valid) prev = wcount[wid][d];          // all peers read the same value before the leader updates
+                        __syncwarp();
+                        if (valid && bef == 0) wcount[wid][d] = prev + __popc(peers);
+                        __syncwarp();
+                        rank[s] = prev + bef;                      // rank within this warp's chunk for digit d
+                    }
+                    __syncthreads();
+                    {
+                        uint32_t run = digit_base + before;        // thread d: exclusive prefix over warps + global offset of (digit, tile)
+#pragma unroll
+                        for (int w = 0; w < RS_WARPS; w++) { const uint32_t c = wcount[w][tid]; wcount[w][tid] = run; run += c; }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int s = 0; s < RS_STEPS; s++) {
+                        const uint32_t g = wbase + s * 32 + lane;
+                        if (g < n) {
+                            const uint32_t d = (uint32_t)((k[s] >> shift) & 0xff);
+                            dst[wcount[wid][d] + rank[s]] = k[s];
+                        }
+                    }
+                    __syncthreads();
+                }
+                grid_barrier(&cnt->bar, bar_target);
+                unsigned long long *t = src; src = dst; dst = t;
+            }
+            // equal responses keep their arrival order after the stable sort: order each run of equal responses by address
+            // (complemented keys ascending = address descending, OpenCV's tie-break).  Runs are rare and short.
+            for (uint32_t i = gtid; i < n; i += gsize) {
+                const uint32_t v = (uint32_t)(src[i] >> 32);
+                if (i > 0 && (uint32_t)(src[i - 1] >> 32) == v) continue;       // not the first of its run
+                uint32_t e = i + 1;
+                while (e < n && (uint32_t)(src[e] >> 32) == v) e++;
+                for (uint32_t x = i + 1; x < e; x++) {                          // insertion sort of src[i..e)
+                    const unsigned long long kk = src[x];
+                    uint32_t b = x;
+                    while (b > i && src[b - 1] > kk) { src[b] = src[b - 1]; b--; }
+                    src[b] = kk;
+                }
+            }
+            grid_barrier(&cnt->bar, bar_target);
+        }
+
+        // ---- positions of all ranks; OpenCV's cell grid as CSR lists ---------------------------------------------------------
+        for (uint32_t r = gtid; r < n; r += gsize) {
+            const uint32_t idx = (uint32_t)(~src[r]);
+            const uint32_t y = idx / a.W, x = idx - y * a.W;
+            a.pos[r] = x | (y << 16);
+            a.state[r] = ST_UNDECIDED;
+            if (a.cull) atomicAdd(&a.cell_start[(y / a.cell) * a.gw + x / a.cell], 1u);
+        }
+        grid_barrier(&cnt->bar, bar_target);
+        if (a.cull) {
+            // exclusive scan of cell_start[0 .. ncells]: 4096-entry chunks per CTA, chunk totals, offsets
+            const uint32_t len = a.ncells + 1, nchunks = (len + 4095) / 4096;
+            for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+                __syncthreads();
+                for (int i = tid; i < 4096; i += SEL_THREADS) { const uint32_t g = c * 4096 + i; sh[i] = g < len ? __ldcg(&a.cell_start[g]) : 0; }
+                __syncthreads();
+                const uint32_t tot = block_scan_excl(sh, 4096, wtot);
+                for (int i = tid; i < 4096; i += SEL_THREADS) { const uint32_t g = c * 4096 + i; if (g < len) a.cell_start[g] = sh[i]; }
+                if (tid == 0) a.scan_scratch[c] = tot;
+            }
+            grid_barrier(&cnt->bar, bar_target);
+            for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+                if (c == 0) continue;
+                // offset of chunk c = sum of the totals of the chunks before it
+                uint32_t part = 0;
+                for (uint32_t t = tid; t < c; t += SEL_THREADS) part += __ldcg(&a.scan_scratch[t]);
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                __syncthreads();
+                if (lane == 0) wtot[wid] = part;
+                __syncthreads();
+                uint32_t off = 0;
+                for (int w = 0; w < 8; w++) off += wtot[w];
+                for (int i = tid; i < 4096; i += SEL_THREADS) { const uint32_t g = c * 4096 + i; if (g < len) a.cell_start[g] += off; }
+            }
+            grid_barrier(&cnt->bar, bar_target);
+            for (uint32_t r = gtid; r < n; r += gsize) {
+                const uint32_t p = __ldcg(&a.pos[r]);
+                const uint32_t c = ((p >> 16) / a.cell) * a.gw + (p & 0xffffu) / a.cell;
+                a.items[__ldcg(&a.cell_start[c]) + atomicAdd(&a.cell_fill[c], 1u)] = r;
+            }
+            grid_barrier(&cnt->bar, bar_target);
+            // ---- culling rounds until no candidate is undecided --------------------------------------------------------------
+            volatile uint8_t *state = a.state;
+            for (int round = 0;; round++) {
+                uint32_t left_cnt = 0;
+                for (uint32_t r = gtid; r < n; r += gsize) {
+                    if (state[r] != ST_UNDECIDED) continue;
+                    const uint32_t p = __ldcg(&a.pos[r]);
+                    const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
+                    const int cx = x / a.cell, cy = y / a.cell;
+                    const int x1 = max(cx - 1, 0), x2 = min(cx + 1, a.gw - 1), y1 = max(cy - 1, 0), y2 = min(cy + 1, a.gh - 1);
+                    bool blocked = false, killed = false;
+                    for (int yy = y1; yy <= y2 && !killed; yy++) {
+                        // the cells x1..x2 of one grid row are contiguous in the CSR layout
+                        const uint32_t kb = __ldcg(&a.cell_start[yy * a.gw + x1]), ke = __ldcg(&a.cell_start[yy * a.gw + x2 + 1]);
+                        for (uint32_t k = kb; k < ke; k++) {
+                            const uint32_t q = __ldcg(&a.items[k]);
+                            if (q >= r) continue;                                    // only stronger candidates matter
+                            const uint32_t pq = __ldcg(&a.pos[q]);
+                            const float dx = (float)(x - (int)(pq & 0xffffu)), dy = (float)(y - (int)(pq >> 16));
+                            if (dx * dx + dy * dy < a.md2) {
+                                const uint8_t s = state[q];
+                                if (s == ST_ACCEPTED) { killed = true; break; }
+                                if (s == ST_UNDECIDED) blocked = true;
+                            }
+                        }
+                    }
+                    if (killed) state[r] = ST_REJECTED;
+                    else if (!blocked) state[r] = ST_ACCEPTED;
+                    else left_cnt++;
+                }
+                for (int o = 16; o > 0; o >>= 1) left_cnt += __shfl_xor_sync(0xffffffffu, left_cnt, o);
+                if (lane == 0 && left_cnt) atomicAdd(&cnt->remaining[round & 63], left_cnt);
+                if (gtid == 0) cnt->remaining[(round + 32) & 63] = 0;          // recycled long before it is used again
+                grid_barrier(&cnt->bar, bar_target);
+                if (__ldcg(&cnt->remaining[round & 63]) == 0) break;
+            }
+        }
+        // ---- accepted candidates in rank order -> (x, y), first `limit` -------------------------------------------------------
+        const uint32_t nchunk = (n + SEL_THREADS - 1) / SEL_THREADS;
+        for (uint32_t c = blockIdx.x; c < nchunk; c += gridDim.x) {
+            const uint32_t r = c * SEL_THREADS + tid;
+            const int cacc = __syncthreads_count(r < n && (!a.cull || __ldcg(&a.state[r]) == ST_ACCEPTED));
+            if (tid == 0) a.blockcnt[c] = (uint32_t)cacc;
+        }
+        grid_barrier(&cnt->bar, bar_target);
+        for (uint32_t c = blockIdx.x; c < nchunk; c += gridDim.x) {
+            uint32_t part = 0;
+            for (uint32_t t = tid; t < c; t += SEL_THREADS) part += __ldcg(&a.blockcnt[t]);
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            __syncthreads();
+            if (lane == 0) wtot[wid] = part;
+            __syncthreads();
+            uint32_t off = 0;
+            for (int w = 0; w < 8; w++) off += wtot[w];
+            const uint32_t r = c * SEL_THREADS + tid;
+            const bool acc = r < n && (!a.cull || __ldcg(&a.state[r]) == ST_ACCEPTED);
+            const uint32_t ballot = __ballot_sync(0xffffffffu, acc);
+            __syncthreads();
+            if (lane == 0) wtot[wid] = __popc(ballot);
+            __syncthreads();
+            uint32_t wb = off;
+            for (int w = 0; w < wid; w++) wb += wtot[w];
+            if (acc) {
+                const uint32_t m = wb + __popc(ballot & ((1u << lane) - 1u));
+                if (m < a.limit) {
+                    const uint32_t p = __ldcg(&a.pos[r]);
+                    a.out_xy[2 * m] = (float)(p & 0xffffu);
+                    a.out_xy[2 * m + 1] = (float)(p >> 16);
+                }
+            }
+            if (c == nchunk - 1 && tid == SEL_THREADS - 1) {      // grand total = offset of the last chunk + its own count
+                uint32_t tot = off;
+                for (int w = 0; w < 8; w++) tot += wtot[w];
+                cnt->nacc = tot;
+            }
+        }
+        grid_barrier(&cnt->bar, bar_target);
+        nacc = __ldcg(&cnt->nacc);
+        if (!subset || nacc >= (uint32_t)a.maxCorners) break;          // done (the subset produced a full prefix)
+        if (gtid == 0) { cnt->nsel = 0; cnt->nacc = 0; }
+        grid_barrier(&cnt->bar, bar_target);
+    }
+    if (gtid == 0) {
+        uint32_t nout = nacc;
+        if (a.maxCorners > 0 && nout > (uint32_t)a.maxCorners) nout = (uint32_t)a.maxCorners;
+        if (nout > a.limit) { cnt->error = IBT_E_CAPACITY; }
+        cnt->nout = nout;
+        *a.out_count = (int)nout;
+    }
 }
 
 // workspace layout
 struct GfttLayout {
-    size_t off_cnt, off_eig, off_keys0, off_keys1, off_blockhist, off_pos, off_state, off_cells, off_fill, off_items,
+    size_t off_cnt, off_keys0, off_keys1, off_keys2, off_blockhist, off_pos, off_state, off_cells, off_fill, off_items,
         off_blockcnt, off_scan, total;
     uint32_t cap, max_sort_blocks, max_cells;
 };
@@ -543,14 +1006,14 @@ static GfttLayout gftt_layout(int H, int W)
     GfttLayout L;
     const size_t np = (size_t)H * W;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    L.cap = (uint32_t)(np / 4 + 4096);                 // 3x3 NMS maxima cannot be denser than 1 in 4 pixels
+    L.cap = (uint32_t)(np / 4 + 4096);                 // isolated 3x3 maxima cannot be denser than 1 in 4 pixels (plateaus can: IBT_E_CAPACITY)
     L.max_sort_blocks = (L.cap + RS_TILE - 1) / RS_TILE;
     L.max_cells = (uint32_t)np + 1;                    // cell >= 1 pixel
     size_t o = 0;
     L.off_cnt = o; o = up(o + sizeof(GfttCounters));
-    L.off_eig = o; o = up(o + np * 4);
     L.off_keys0 = o; o = up(o + (size_t)L.cap * 8);
     L.off_keys1 = o; o = up(o + (size_t)L.cap * 8);
+    L.off_keys2 = o; o = up(o + (size_t)L.cap * 8);
     L.off_blockhist = o; o = up(o + (size_t)256 * L.max_sort_blocks * 4);
     L.off_pos = o; o = up(o + (size_t)L.cap * 4);
     L.off_state = o; o = up(o + (size_t)L.cap);
@@ -558,9 +1021,55 @@ static GfttLayout gftt_layout(int H, int W)
     L.off_fill = o; o = up(o + (size_t)L.max_cells * 4);
     L.off_items = o; o = up(o + (size_t)L.cap * 4);
     L.off_blockcnt = o; o = up(o + ((size_t)L.cap / 256 + 2) * 4);
-    L.off_scan = o; o = up(o + ((size_t)L.max_cells / SCAN_TILE + 4) * 4);
+    L.off_scan = o; o = up(o + ((size_t)L.max_cells / 4096 + 4) * 4);
     L.total = o;
     return L;
+}
+
+// Both launches of goodFeaturesToTrack on `st`; nothing is read back.  count_dev (device int) receives the corner count.
+static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch, int H, int W,
+                        int maxCorners, double qualityLevel, double minDistance, int blockSize, void *workspace,
+                        size_t workspace_bytes, float *out_xy, int cap, int *count_dev, cudaStream_t st)
+{
+    if (!gray || !workspace || H < 3 || W < 3 || H > 65535 || W > 65535 || (int64_t)H * W > 0x7fffffffLL ||
+        cap < 0 || (cap > 0 && !out_xy) || (mask && mask_pitch < W) || qualityLevel < 0 || minDistance < 0 || minDistance > 1024 ||
+        pitch < W)
+        return IBT_E_INVALID;
+    const GfttLayout L = gftt_layout(H, W);
+    if (workspace_bytes < L.total) return IBT_E_WORKSPACE;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    GfttCounters *cnt = reinterpret_cast<GfttCounters *>(ws + L.off_cnt);
+    IBT_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(GfttCounters), st));
+    unsigned long long *keys0 = reinterpret_cast<unsigned long long *>(ws + L.off_keys0);
+    int rc = launch_eig_nms(gray, H, W, pitch, blockSize, mask, mask_pitch, qualityLevel, cnt, keys0, L.cap, st);
+    if (rc) return rc;
+    SelArgs a;
+    a.cnt = cnt; a.keys0 = keys0;
+    a.keys1 = reinterpret_cast<unsigned long long *>(ws + L.off_keys1);
+    a.keys2 = reinterpret_cast<unsigned long long *>(ws + L.off_keys2);
+    a.cap = L.cap;
+    a.blockhist = reinterpret_cast<uint32_t *>(ws + L.off_blockhist);
+    a.pos = reinterpret_cast<uint32_t *>(ws + L.off_pos);
+    a.state = ws + L.off_state;
+    a.cell_start = reinterpret_cast<uint32_t *>(ws + L.off_cells);
+    a.cell_fill = reinterpret_cast<uint32_t *>(ws + L.off_fill);
+    a.items = reinterpret_cast<uint32_t *>(ws + L.off_items);
+    a.blockcnt = reinterpret_cast<uint32_t *>(ws + L.off_blockcnt);
+    a.scan_scratch = reinterpret_cast<uint32_t *>(ws + L.off_scan);
+    a.H = H; a.W = W; a.maxCorners = maxCorners;
+    a.cull = minDistance >= 1.0 ? 1 : 0;
+    a.cell = a.cull ? (int)lrint(minDistance) : 65536;        // no culling: only positions are needed
+    a.gw = (W + a.cell - 1) / a.cell; a.gh = (H + a.cell - 1) / a.cell;
+    a.ncells = (uint32_t)a.gw * a.gh;
+    uint32_t limit = (maxCorners > 0) ? (uint32_t)maxCorners : 0xffffffffu;
+    if (limit > (uint32_t)cap) limit = (uint32_t)cap;
+    a.limit = limit;
+    a.quality = qualityLevel;
+    a.md2 = (float)(minDistance * minDistance);
+    a.out_xy = out_xy;
+    a.out_count = count_dev ? count_dev : reinterpret_cast<int *>(&cnt->pad);
+    gftt_select_kernel<<<kNumSMs, SEL_THREADS, 0, st>>>(a);        // every CTA resident: the kernel synchronises its grid itself
+    return check_launch("gftt_select_kernel");
 }
 
 } // namespace ibt
@@ -577,131 +1086,30 @@ IBT_API size_t ibt_gftt_workspace_bytes(int H, int W)
     return ibt::gftt_layout(H, W).total;
 }
 
+IBT_API int ibt_gftt_async(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch, int H, int W,
+                           int maxCorners, double qualityLevel, double minDistance, int blockSize, void *workspace,
+                           size_t workspace_bytes, float *out_xy, int cap, int *count_dev, void *stream)
+{
+    if (!count_dev) return IBT_E_INVALID;
+    return ibt::gftt_enqueue(gray, pitch, mask, mask_pitch, H, W, maxCorners, qualityLevel, minDistance, blockSize, workspace,
+                             workspace_bytes, out_xy, cap, count_dev, static_cast<cudaStream_t>(stream));
+}
+
 IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch, int H, int W,
                      int maxCorners, double qualityLevel, double minDistance, int blockSize, void *workspace,
                      size_t workspace_bytes, float *out_xy, int cap, int *out_count, void *stream)
 {
     using namespace ibt;
-    if (!gray || !workspace || !out_count || H < 3 || W < 3 || H > 65535 || W > 65535 || (int64_t)H * W > 0x7fffffffLL ||
-        cap < 0 || (cap > 0 && !out_xy) || (mask && mask_pitch < W) || qualityLevel < 0 || minDistance < 0 || minDistance > 1024)
-        return IBT_E_INVALID;
-    const GfttLayout L = gftt_layout(H, W);
-    if (workspace_bytes < L.total) return IBT_E_WORKSPACE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
-    GfttCounters *cnt = reinterpret_cast<GfttCounters *>(ws + L.off_cnt);
-    float *eig = reinterpret_cast<float *>(ws + L.off_eig);
-    unsigned long long *keys0 = reinterpret_cast<unsigned long long *>(ws + L.off_keys0);
-    unsigned long long *keys1 = reinterpret_cast<unsigned long long *>(ws + L.off_keys1);
-    uint32_t *blockhist = reinterpret_cast<uint32_t *>(ws + L.off_blockhist);
-    uint32_t *pos = reinterpret_cast<uint32_t *>(ws + L.off_pos);
-    uint8_t *state = ws + L.off_state;
-    uint32_t *cell_start = reinterpret_cast<uint32_t *>(ws + L.off_cells);
-    uint32_t *cell_fill = reinterpret_cast<uint32_t *>(ws + L.off_fill);
-    uint32_t *items = reinterpret_cast<uint32_t *>(ws + L.off_items);
-    uint32_t *blockcnt = reinterpret_cast<uint32_t *>(ws + L.off_blockcnt);
-    uint32_t *scan_scratch = reinterpret_cast<uint32_t *>(ws + L.off_scan);
+    if (!out_count) return IBT_E_INVALID;
     *out_count = 0;
-
-    IBT_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(GfttCounters), st));
-    int rc = launch_eig(gray, H, W, pitch, blockSize, eig, (int64_t)W * 4, mask, mask_pitch, &cnt->maxbits, st);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = gftt_enqueue(gray, pitch, mask, mask_pitch, H, W, maxCorners, qualityLevel, minDistance, blockSize, workspace,
+                          workspace_bytes, out_xy, cap, nullptr, st);
     if (rc) return rc;
-    const int nblk = kNumSMs * 8;
-    const bool cull = minDistance >= 1.0;
-    const int cell = cull ? (int)lrint(minDistance) : 65536;        // no culling: one cell, only positions are needed
-    const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
-    const uint32_t ncells = (uint32_t)gw * gh;
-    uint32_t limit = (maxCorners > 0) ? (uint32_t)maxCorners : 0xffffffffu;
-    if (limit > (uint32_t)cap) limit = (uint32_t)cap;
-    static thread_local GfttCounters hc;                           // 17 KB: keep it off the stack
-    uint32_t nout = 0;
-
-    // attempt 0 may work on the strongest candidates only (top-k prefilter); if culling leaves fewer than maxCorners of
-    // them, attempt 1 repeats with every candidate.  The greedy order makes the prefix exact either way: whether a
-    // candidate is accepted depends on stronger candidates only.
-    for (int attempt = 0; attempt < 2; attempt++) {
-        if (attempt == 1) {
-            IBT_CUDA_TRY(cudaMemsetAsync(&cnt->ncand, 0, sizeof(GfttCounters) - offsetof(GfttCounters, ncand), st));
-        }
-        nms_kernel<<<nblk, 256, 0, st>>>(eig, H, W, mask, mask_pitch, qualityLevel, cnt, keys0, L.cap);
-        if ((rc = check_launch("nms_kernel"))) return rc;
-        IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
-        IBT_CUDA_TRY(cudaStreamSynchronize(st));
-        if (hc.ncand > L.cap) return IBT_E_CAPACITY;
-        uint32_t n = hc.ncand;
-        if (n == 0) return IBT_OK;
-
-        // ---- order the candidates by (response desc, address desc): rank ------------------------------------
-        unsigned long long *src = keys0, *dst = keys1;
-        bool subset = false;
-        const uint64_t want = maxCorners > 0 ? (uint64_t)maxCorners * 4 + 1024 : 0;
-        if (attempt == 0 && maxCorners > 0 && cull && n > 2 * want) {
-            uint32_t cum = 0;
-            int b = 4095;
-            for (; b >= 0; b--) { cum += hc.hist[b]; if (cum >= want) break; }
-            if (b > 0 && cum < n) {
-                IBT_CUDA_TRY(cudaMemsetAsync(&cnt->nacc, 0, 4, st));            // reused as the selection counter
-                select_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys0, n, (uint32_t)b, keys1, &cnt->nacc);
-                src = keys1; dst = keys0;
-                n = cum;
-                subset = true;
-            }
-        }
-        if (!subset) complement_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, n);
-        if (n > 1) {
-            const uint32_t nblocks = (n + RS_TILE - 1) / RS_TILE;
-            // the top response byte (sign + 7 exponent bits) is usually the same for every candidate: the histogram tells
-            int lo_bin = 4096, hi_bin = -1;
-            for (int b = 0; b < 4096; b++) if (hc.hist[b]) { if (b < lo_bin) lo_bin = b; hi_bin = b; }
-            const int last_pass = (lo_bin >> 4) == (hi_bin >> 4) ? 6 : 7;
-            for (int p = 4; p <= last_pass; p++) {                      // response bytes only; ties are fixed below
-                rs_count_kernel<<<nblocks, 256, 0, st>>>(src, n, 8 * p, nblocks, blockhist);
-                scan_u32(blockhist, 256u * nblocks, nullptr, scan_scratch, st);
-                rs_scatter_kernel<<<nblocks, 256, 0, st>>>(src, dst, n, 8 * p, nblocks, blockhist);
-                unsigned long long *t = src; src = dst; dst = t;
-            }
-            tie_fix_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, n);
-            if ((rc = check_launch("radix sort"))) return rc;
-        }
-        const uint32_t nb = (n + 255) / 256;
-
-        // positions of all ranks (+ cell histogram when culling)
-        IBT_CUDA_TRY(cudaMemsetAsync(cell_start, 0, ((size_t)ncells + 1) * 4, st));
-        cell_count_kernel<<<nb, 256, 0, st>>>(src, n, W, cell, gw, pos, cell_start, state);
-        if ((rc = check_launch("cell_count_kernel"))) return rc;
-        nout = n;
-        if (cull) {
-            IBT_CUDA_TRY(cudaMemsetAsync(cell_fill, 0, (size_t)ncells * 4, st));
-            scan_u32(cell_start, ncells + 1, nullptr, scan_scratch, st);
-            cell_fill_kernel<<<nb, 256, 0, st>>>(pos, n, cell, gw, cell_start, cell_fill, items);
-            const float md2 = (float)(minDistance * minDistance);
-            int round = 0;
-            for (;;) {
-                const int batch = round == 0 ? 12 : 4;
-                for (int b = 0; b < batch; b++, round++) {
-                    if (round >= 64) IBT_CUDA_TRY(cudaMemsetAsync(&cnt->remaining[round & 63], 0, 4, st));
-                    cull_round_kernel<<<nb, 256, 0, st>>>(pos, n, cell_start, items, state, cnt, cell, gw, gh, md2, round);
-                }
-                if ((rc = check_launch("cull_round_kernel"))) return rc;
-                IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, offsetof(GfttCounters, hist), cudaMemcpyDeviceToHost, st));
-                IBT_CUDA_TRY(cudaStreamSynchronize(st));
-                if (hc.remaining[(round - 1) & 63] == 0) break;
-                if (round > (1 << 20)) return IBT_E_CUDA;
-            }
-            accepted_count_kernel<<<nb, 256, 0, st>>>(state, n, blockcnt);
-            scan_u32(blockcnt, nb, &cnt->nacc, scan_scratch, st);
-            write_corners_kernel<<<nb, 256, 0, st>>>(pos, state, n, blockcnt, limit, out_xy);
-            if ((rc = check_launch("write_corners_kernel"))) return rc;
-            IBT_CUDA_TRY(cudaMemcpyAsync(&hc, cnt, offsetof(GfttCounters, hist), cudaMemcpyDeviceToHost, st));
-            IBT_CUDA_TRY(cudaStreamSynchronize(st));
-            nout = hc.nacc;
-        } else {
-            write_corners_kernel<<<nb, 256, 0, st>>>(pos, nullptr, n, nullptr, limit, out_xy);
-            if ((rc = check_launch("write_corners_kernel"))) return rc;
-        }
-        if (!subset || nout >= (uint32_t)maxCorners) break;          // done (the subset produced a full prefix)
-    }
-    if (maxCorners > 0 && nout > (uint32_t)maxCorners) nout = (uint32_t)maxCorners;
-    *out_count = (int)nout;
-    return nout > (uint32_t)cap ? IBT_E_CAPACITY : IBT_OK;
+    // the one host round trip of the synchronous form: the corner count decides the shapes the caller allocates next
+    struct { uint32_t maxbits, ncand, nsel, nacc, nout; int32_t error; } hc;
+    IBT_CUDA_TRY(cudaMemcpyAsync(&hc, workspace, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    IBT_CUDA_TRY(cudaStreamSynchronize(st));
+    *out_count = (int)hc.nout;
+    return hc.error ? hc.error : IBT_OK;
 }

@@ -129,6 +129,13 @@ int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t ma
              int H, int W, int maxCorners, double qualityLevel, double minDistance, int blockSize,
              void *workspace, size_t workspace_bytes,
              float *out_xy, int cap, int *out_count, void *stream);
+/* Same two launches, nothing read back: count_dev (DEVICE int*) receives the corner count when the stream reaches it, out_xy
+ * the corners.  The frame loop (s1:437-448) seeds the next group with it while earlier work is still in flight; the count
+ * travels to ibt_lk_fb as n_dev.  A capacity overflow is reported by the next synchronous call on the workspace. */
+int ibt_gftt_async(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
+                   int H, int W, int maxCorners, double qualityLevel, double minDistance, int blockSize,
+                   void *workspace, size_t workspace_bytes,
+                   float *out_xy, int cap, int *count_dev, void *stream);
 
 /* ---- track bookkeeping at a group boundary (s1:362-395): stable compaction of the live
  * tracks.  tracks_tm (T+1, N, 2) f32 time-major, quality_tm (T, N) f32, alive (N) u8 ->
