@@ -144,21 +144,33 @@ struct GfttCounters {
     int32_t error;           // IBT_E_* raised on the device (capacity)
     uint32_t bar;            // grid barrier of K2b
     uint32_t pad;
-    uint32_t remaining[64];  // undecided candidates left after round k (mod 64)
+    uint32_t remaining[64];  // undecided ranks left after culling round k (mod 64)
     uint32_t hist[4096];     // candidates above the threshold per top-12-bit bin of the ordered response
+    unsigned long long tstamp[16];   // %globaltimer at the phase boundaries of K2b (CTA 0; tools/prof_gftt.py prints them)
 };
+__device__ __forceinline__ void stamp(GfttCounters *cnt, int i)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        cnt->tstamp[i] = t;
+    }
+}
 
 constexpr int EN_WARPS = 4;               // warps per CTA (independent of each other: no block-level barrier)
 constexpr int EN_COLS = 128;              // support columns per warp (4 per lane)
-constexpr int EN_CB = 192;                // per-warp candidate buffer, flushed to global memory at >= 128 entries
+constexpr int EN_CB = 192;                // per-warp candidate buffer (flushed every 8 rows once it holds >= 96 entries)
 constexpr int EN_PAD = 32;                // generic blockSize: padding of the shared row buffer on both sides
+constexpr int EN_BORDER_SPLIT = 4;        // border strips (byte gathers, ~4x slower per row) get 4x shorter jobs
 
 struct EigNmsArgs {
     const uint8_t *img; int H, W; int64_t pitch;
     const uint8_t *mask; int64_t mask_pitch;
     int bs; double s2, s2h, quality;
     GfttCounters *cnt; unsigned long long *keys; uint32_t cap;
-    int outw, left, nstrips, rows_per_job, njobs, word_ok;
+    int outw, left, nstrips, word_ok;
+    int first_right;          // strips >= first_right (and strip 0) reach outside the image: border variant
+    int nborder, rows_border, chunks_border, rows_fast, njobs;
     int warp_smem_ints;      // per-warp shared memory (ring + candidate buffer + row buffer), in ints
 };
 
@@ -171,28 +183,23 @@ __device__ __forceinline__ int dp4a_us_(uint32_t a, int b)
 }
 
 // horizontal taps of one image row for the lane's 4 pixels: hx = I[x+1] - I[x-1], hs = I[x-1] + 2 I[x] + I[x+1]
-template <bool BORDER, bool WANT_HS>
-__device__ __forceinline__ void row_taps(const uint8_t *__restrict__ row, int c0, const int *pc, const int *pm, const int *pp,
-                                         int *hx, int *hs)
+__device__ __forceinline__ void taps_word(uint32_t w, int *hx, int *hs)
 {
-    if (!BORDER) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + c0));
-        const uint32_t L = __shfl_up_sync(0xffffffffu, w, 1), R = __shfl_down_sync(0xffffffffu, w, 1);
-        // byte windows (x-1, x, x+1, .) of the four pixels
-        const uint32_t w0 = __funnelshift_r(L, w, 24), w2 = __funnelshift_r(w, R, 8), w3 = __funnelshift_r(w, R, 16);
-        hx[0] = dp4a_us_(w0, 0x000100FF); hx[1] = dp4a_us_(w, 0x000100FF);
-        hx[2] = dp4a_us_(w2, 0x000100FF); hx[3] = dp4a_us_(w3, 0x000100FF);
-        if (WANT_HS) {
-            hs[0] = dp4a_uu_(w0, 0x00010201u); hs[1] = dp4a_uu_(w, 0x00010201u);
-            hs[2] = dp4a_uu_(w2, 0x00010201u); hs[3] = dp4a_uu_(w3, 0x00010201u);
-        }
-    } else {
+    const uint32_t L = __shfl_up_sync(0xffffffffu, w, 1), R = __shfl_down_sync(0xffffffffu, w, 1);
+    // byte windows (x-1, x, x+1, .) of the four pixels
+    const uint32_t w0 = __funnelshift_r(L, w, 24), w2 = __funnelshift_r(w, R, 8), w3 = __funnelshift_r(w, R, 16);
+    hx[0] = dp4a_us_(w0, 0x000100FF); hx[1] = dp4a_us_(w, 0x000100FF);
+    hx[2] = dp4a_us_(w2, 0x000100FF); hx[3] = dp4a_us_(w3, 0x000100FF);
+    hs[0] = dp4a_uu_(w0, 0x00010201u); hs[1] = dp4a_uu_(w, 0x00010201u);
+    hs[2] = dp4a_uu_(w2, 0x00010201u); hs[3] = dp4a_uu_(w3, 0x00010201u);
+}
+__device__ __forceinline__ void taps_bytes(const uint8_t *__restrict__ row, const int *pc, const int *pm, const int *pp, int *hx, int *hs)
+{
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int m = __ldg(row + pm[k]), p = __ldg(row + pp[k]);
-            hx[k] = p - m;
-            if (WANT_HS) hs[k] = m + 2 * (int)__ldg(row + pc[k]) + p;
-        }
+    for (int k = 0; k < 4; k++) {
+        const int m = __ldg(row + pm[k]), c = __ldg(row + pc[k]), p = __ldg(row + pp[k]);
+        hx[k] = p - m;
+        hs[k] = m + 2 * c + p;
     }
 }
 
@@ -234,18 +241,18 @@ __device__ __forceinline__ void hbox_smem(const int *v, int *out, int *rowbuf, i
 }
 
 template <int BS, bool MASK, bool BORDER>
-__device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int chunk, int *wsm, int lane)
+__device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int Y0, int Y1, int *wsm, int lane)
 {
     const int bs = BS ? BS : a.bs;
     const int a0 = -(bs / 2);
     const int H = a.H, W = a.W;
     const int ox0 = strip * a.outw;                       // first output column of the strip
     const int c0 = ox0 - a.left + 4 * lane;               // support column of this lane's pixel 0 (multiple of 4)
-    const int Y0 = chunk * a.rows_per_job, Y1 = min(H, Y0 + a.rows_per_job);
     const int ey0 = max(0, Y0 - 1), ey1 = min(H - 1, Y1);         // response rows needed (NMS halo rows included)
-    int *ring = wsm;                                              // [bs][3][128]
-    unsigned long long *cbuf = reinterpret_cast<unsigned long long *>(wsm + bs * 3 * EN_COLS);
-    int *rowbuf = reinterpret_cast<int *>(cbuf + EN_CB);          // generic blockSize only: [EN_PAD + 128 + EN_PAD]
+    uint32_t *ring = reinterpret_cast<uint32_t *>(wsm);           // [bs][128]: (sx & 0xffff) | (sy << 16) of the last bs product rows
+    unsigned long long *cbuf = reinterpret_cast<unsigned long long *>(wsm + bs * EN_COLS);
+    int *scount = reinterpret_cast<int *>(cbuf + EN_CB);          // entries in cbuf (may run past EN_CB: those went straight to global)
+    int *rowbuf = scount + 4;                                     // generic blockSize only: [EN_PAD + 128 + EN_PAD]
     unsigned outmask = 0, candmask = 0;                           // pixels this lane owns / may emit
     int pc[4], pm[4], pp[4];
 #pragma unroll
@@ -257,6 +264,8 @@ __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int 
         pc[k] = r101(c, W);                                       // REFLECT_101 on the product image ...
         pm[k] = r101(pc[k] - 1, W); pp[k] = r101(pc[k] + 1, W);   // ... whose Sobel reflects the source again
     }
+    if (lane == 0) *scount = 0;
+    __syncwarp();
     int vxx[4] = {0, 0, 0, 0}, vxy[4] = {0, 0, 0, 0}, vyy[4] = {0, 0, 0, 0};
     float m3a[4], m3b[4], eprev[4];
 #pragma unroll
@@ -269,47 +278,72 @@ __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int 
         const uint32_t mb = *reinterpret_cast<volatile const uint32_t *>(&a.cnt->maxbits);
         if (mb) thr_lb = fmaxf(0.f, (float)((double)dec_f32(mb) * a.quality));
     }
-    int ncb = 0;
     auto flush = [&]() {
+        __syncwarp();
+        const int ncb = min(*reinterpret_cast<volatile int *>(scount), EN_CB);
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&a.cnt->ncand, (unsigned)ncb);
+        if (lane == 0 && ncb) base = atomicAdd(&a.cnt->ncand, (unsigned)ncb);
         base = __shfl_sync(0xffffffffu, base, 0);
         for (int i = lane; i < ncb; i += 32)
             if (base + i < a.cap) a.keys[base + i] = cbuf[i];
-        ncb = 0;
+        __syncwarp();
+        if (lane == 0) *scount = 0;
         __syncwarp();
     };
     const int p_first = ey0 + a0, p_last = ey1 + a0 + bs - 1;
     int slot = 0;
+    // taps of the image rows (rp-1, rp, rp+1) of product row p; rolled while the rows advance one by one
+    int hxA[4], hsA[4], hxB[4], hsB[4], hxC[4], hsC[4];
+    bool have = false;
+    uint32_t wnext = 0;
+    bool wnext_ok = false;
     for (int p = p_first; p <= p_last; p++) {
-        // ---- products of support row p ------------------------------------------------------------------------
-        const int rp = r101(p, H);
-        const uint8_t *rowA = a.img + (int64_t)r101(rp - 1, H) * a.pitch;
-        const uint8_t *rowB = a.img + (int64_t)rp * a.pitch;
-        const uint8_t *rowC = a.img + (int64_t)r101(rp + 1, H) * a.pitch;
-        int hxA[4], hsA[4], hxB[4], hxC[4], hsC[4];
-        row_taps<BORDER, true>(rowA, c0, pc, pm, pp, hxA, hsA);
-        row_taps<BORDER, false>(rowB, c0, pc, pm, pp, hxB, nullptr);
-        row_taps<BORDER, true>(rowC, c0, pc, pm, pp, hxC, hsC);
-        int nxx[4], nxy[4], nyy[4];
+        // ---- taps of the three image rows under support row p ---------------------------------------------------------
+        if (have && p >= 1 && p <= H - 2) {               // rows p-1, p are held: only row p+1 is new
+#pragma unroll
+            for (int k = 0; k < 4; k++) { hxA[k] = hxB[k]; hsA[k] = hsB[k]; hxB[k] = hxC[k]; hsB[k] = hsC[k]; }
+            const uint8_t *rowC = a.img + (int64_t)(p + 1) * a.pitch;
+            if (BORDER) taps_bytes(rowC, pc, pm, pp, hxC, hsC);
+            else taps_word(wnext_ok ? wnext : __ldg(reinterpret_cast<const uint32_t *>(rowC + c0)), hxC, hsC);
+        } else {
+            const int rp = r101(p, H);
+            const uint8_t *rowA = a.img + (int64_t)r101(rp - 1, H) * a.pitch;
+            const uint8_t *rowB = a.img + (int64_t)rp * a.pitch;
+            const uint8_t *rowC = a.img + (int64_t)r101(rp + 1, H) * a.pitch;
+            if (BORDER) {
+                taps_bytes(rowA, pc, pm, pp, hxA, hsA); taps_bytes(rowB, pc, pm, pp, hxB, hsB); taps_bytes(rowC, pc, pm, pp, hxC, hsC);
+            } else {
+                const uint32_t wa = __ldg(reinterpret_cast<const uint32_t *>(rowA + c0));
+                const uint32_t wb = __ldg(reinterpret_cast<const uint32_t *>(rowB + c0));
+                const uint32_t wc = __ldg(reinterpret_cast<const uint32_t *>(rowC + c0));
+                taps_word(wa, hxA, hsA); taps_word(wb, hxB, hsB); taps_word(wc, hxC, hsC);
+            }
+        }
+        have = p >= 0;                                    // (for p >= 0 the held rows B, C are the image rows p, p+1)
+        wnext_ok = false;
+        if (!BORDER && p >= 0 && p + 1 <= H - 2) {        // the next iteration rolls: fetch its new row (p + 2) now
+            wnext = __ldg(reinterpret_cast<const uint32_t *>(a.img + (int64_t)(p + 2) * a.pitch + c0));
+            wnext_ok = true;
+        }
+        // ---- vertical sliding sums of the products; the ring keeps (sx, sy) of the last bs rows -------------------------
+        uint4 *rg = reinterpret_cast<uint4 *>(ring + slot * EN_COLS) + lane;
+        if (p - p_first >= bs) {
+            const uint4 o = *rg;
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int ox = (int)(short)(ow[k] & 0xffffu), oy = (int)ow[k] >> 16;
+                vxx[k] -= ox * ox; vxy[k] -= ox * oy; vyy[k] -= oy * oy;
+            }
+        }
+        uint32_t nw[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int sx = hxA[k] + 2 * hxB[k] + hxC[k], sy = hsC[k] - hsA[k];
-            nxx[k] = sx * sx; nxy[k] = sx * sy; nyy[k] = sy * sy;
+            vxx[k] += sx * sx; vxy[k] += sx * sy; vyy[k] += sy * sy;
+            nw[k] = ((uint32_t)sx & 0xffffu) | ((uint32_t)sy << 16);
         }
-        // ---- vertical sliding sums (ring of the last bs product rows) ----------------------------------------------------
-        int4 *rg = reinterpret_cast<int4 *>(ring + slot * 3 * EN_COLS) + lane;
-        if (p - p_first >= bs) {
-            const int4 o0 = rg[0], o1 = rg[EN_COLS / 4], o2 = rg[2 * (EN_COLS / 4)];
-            vxx[0] -= o0.x; vxx[1] -= o0.y; vxx[2] -= o0.z; vxx[3] -= o0.w;
-            vxy[0] -= o1.x; vxy[1] -= o1.y; vxy[2] -= o1.z; vxy[3] -= o1.w;
-            vyy[0] -= o2.x; vyy[1] -= o2.y; vyy[2] -= o2.z; vyy[3] -= o2.w;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) { vxx[k] += nxx[k]; vxy[k] += nxy[k]; vyy[k] += nyy[k]; }
-        rg[0] = make_int4(nxx[0], nxx[1], nxx[2], nxx[3]);
-        rg[EN_COLS / 4] = make_int4(nxy[0], nxy[1], nxy[2], nxy[3]);
-        rg[2 * (EN_COLS / 4)] = make_int4(nyy[0], nyy[1], nyy[2], nyy[3]);
+        *rg = make_uint4(nw[0], nw[1], nw[2], nw[3]);
         slot = slot + 1 == bs ? 0 : slot + 1;
         const int y = p - a0 - bs + 1;                    // response row completed by this product row
         if (y < ey0) continue;
@@ -332,11 +366,9 @@ __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int 
         unsigned mcur = 0xfu;
         if (MASK) {
             mcur = 0;
-            if (y < H) {
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if ((outmask >> k) & 1u) mcur |= (a.mask[(int64_t)y * a.mask_pitch + c0 + k] ? 1u : 0u) << k;
-            }
+            for (int k = 0; k < 4; k++)
+                if ((outmask >> k) & 1u) mcur |= (a.mask[(int64_t)y * a.mask_pitch + c0 + k] ? 1u : 0u) << k;
         }
         if (y >= Y0 && y < Y1) {
 #pragma unroll
@@ -350,36 +382,35 @@ __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int 
         m3c[2] = fmaxf(fmaxf(e[1], e[2]), e[3]); m3c[3] = fmaxf(fmaxf(e[2], e[3]), er);
         const int yc = y - 1;
         if (yc >= max(Y0, 1) && yc < Y1 && yc <= H - 2) {
-            unsigned flags = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const float v = eprev[k];
-                if ((((candmask & mprev) >> k) & 1u) && v > thr_lb && v == fmaxf(fmaxf(m3a[k], m3b[k]), m3c[k])) flags |= 1u << k;
-            }
-            if (__any_sync(0xffffffffu, flags != 0)) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const bool f = (flags >> k) & 1u;
-                    const unsigned ball = __ballot_sync(0xffffffffu, f);
-                    if (f) cbuf[ncb + __popc(ball & ((1u << lane) - 1u))] =
-                        ((unsigned long long)enc_f32(eprev[k]) << 32) | (uint32_t)(yc * W + c0 + k);
-                    ncb += __popc(ball);
+                if ((((candmask & mprev) >> k) & 1u) && v > thr_lb && v == fmaxf(fmaxf(m3a[k], m3b[k]), m3c[k])) {
+                    const unsigned long long key = ((unsigned long long)enc_f32(v) << 32) | (uint32_t)(yc * W + c0 + k);
+                    const int pos = atomicAdd(scount, 1);
+                    if (pos < EN_CB) cbuf[pos] = key;
+                    else {                                              // buffer full (plateaus): straight to the global list
+                        const unsigned g = atomicAdd(&a.cnt->ncand, 1u);
+                        if (g < a.cap) a.keys[g] = key;
+                    }
                 }
-                __syncwarp();
-                if (ncb >= 128) flush();
             }
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) { m3a[k] = m3b[k]; m3b[k] = m3c[k]; eprev[k] = e[k]; }
         mprev = mcur;
-        if ((y & 31) == 31) {                             // tighten the threshold bound with what this warp has seen
-            float wm = lmax;
+        if ((y & 7) == 7) {
+            __syncwarp();
+            if (*reinterpret_cast<volatile int *>(scount) >= EN_CB / 2) flush();
+            if ((y & 31) == 31) {                         // tighten the threshold bound with what this warp has seen
+                float wm = lmax;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-            if (wm > 0.f) thr_lb = fmaxf(thr_lb, (float)((double)wm * a.quality));
+                for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+                if (wm > 0.f) thr_lb = fmaxf(thr_lb, (float)((double)wm * a.quality));
+            }
         }
     }
-    if (ncb) flush();
+    flush();
     uint32_t lbits = have_max ? enc_f32(lmax) : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lbits = max(lbits, __shfl_xor_sync(0xffffffffu, lbits, o));
@@ -387,41 +418,28 @@ __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int 
 }
 
 template <int BS, bool MASK>
-__global__ void __launch_bounds__(EN_WARPS * 32)
+__global__ void __launch_bounds__(EN_WARPS * 32, 4)
 eig_nms_kernel(const __grid_constant__ EigNmsArgs a)
 {
     extern __shared__ __align__(16) int en_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int job = blockIdx.x * EN_WARPS + wib;
     if (job >= a.njobs) return;
-    const int strip = job % a.nstrips, chunk = job / a.nstrips;
     int *wsm = en_smem + (size_t)wib * a.warp_smem_ints;
-    // fast path: the warp's 128 support columns are real, 4-byte aligned pixels (no reflection, word loads)
-    const int lx0 = strip * a.outw - a.left;
-    if (a.word_ok && lx0 >= 0 && lx0 + EN_COLS <= a.W) eig_nms_job<BS, MASK, false>(a, strip, chunk, wsm, lane);
-    else eig_nms_job<BS, MASK, true>(a, strip, chunk, wsm, lane);
-}
-
-struct EigNmsGeom { int outw, left, nstrips, rows_per_job, nchunks, warp_smem_ints; };
-static EigNmsGeom eig_nms_geom(int H, int W, int bs)
-{
-    EigNmsGeom g;
-    const int half = bs / 2;                                  // window offsets [-half, bs - 1 - half]
-    g.left = (2 + half + 3) & ~3;                             // Sobel edge + window reach + NMS halo, rounded to words
-    g.outw = (126 - g.left - (bs - 1 - half)) & ~3;           // owned columns per warp
-    g.nstrips = (W + g.outw - 1) / g.outw;
-    g.warp_smem_ints = bs * 3 * EN_COLS + EN_CB * 2 + (EN_PAD + EN_COLS + EN_PAD);
-    // rows per job: one wave of warps over the GPU (warm-up costs bs + 2 rows per job), at least 32 rows
-    int wps = (int)((227 * 1024) / ((size_t)g.warp_smem_ints * 4 * EN_WARPS + 1024)) * EN_WARPS;      // resident warps per SM
-    if (wps < 1) wps = 1;
-    if (wps > 16) wps = 16;
-    int chunks = (kNumSMs * wps) / g.nstrips;
-    if (chunks < 1) chunks = 1;
-    int rows = (H + chunks - 1) / chunks;
-    if (rows < 32) rows = 32;
-    g.rows_per_job = rows;
-    g.nchunks = (H + rows - 1) / rows;
-    return g;
+    // jobs [0, nborder * chunks_border): strips that reach outside the image (or every strip of an unaligned image), in
+    // short row chunks: their byte gathers make a row ~4x slower, and the launch is one wave -- the longest job sets its time
+    const int nbj = a.nborder * a.chunks_border;
+    if (job < nbj) {
+        const int sb = job % a.nborder, chunk = job / a.nborder;
+        const int strip = a.nborder == a.nstrips ? sb : (sb == 0 ? 0 : a.first_right + sb - 1);
+        const int Y0 = chunk * a.rows_border;
+        eig_nms_job<BS, MASK, true>(a, strip, Y0, min(a.H, Y0 + a.rows_border), wsm, lane);
+    } else {
+        const int j = job - nbj, nfast = a.nstrips - a.nborder;
+        const int strip = 1 + j % nfast, chunk = j / nfast;
+        const int Y0 = chunk * a.rows_fast;
+        eig_nms_job<BS, MASK, false>(a, strip, Y0, min(a.H, Y0 + a.rows_fast), wsm, lane);
+    }
 }
 
 template <int BS>
@@ -443,15 +461,40 @@ static int launch_eig_nms(const uint8_t *gray, int H, int W, int64_t pitch, int 
                           double quality, GfttCounters *cnt, unsigned long long *keys, uint32_t cap, cudaStream_t st)
 {
     if (bs < 1 || bs > MAX_BLOCK) return IBT_E_INVALID;
-    const EigNmsGeom g = eig_nms_geom(H, W, bs);
     EigNmsArgs a;
     a.img = gray; a.H = H; a.W = W; a.pitch = pitch; a.mask = mask; a.mask_pitch = mask_pitch; a.bs = bs;
     const float scale = (float)(1.0 / (4.0 * bs * 255.0));       // OpenCV's Sobel scale for ksize 3
     a.s2 = (double)scale * (double)scale; a.s2h = a.s2 * 0.5;     // the halving of a and c folded in (exact: power of two)
     a.quality = quality; a.cnt = cnt; a.keys = keys; a.cap = cap;
-    a.outw = g.outw; a.left = g.left; a.nstrips = g.nstrips; a.rows_per_job = g.rows_per_job;
-    a.njobs = g.nstrips * g.nchunks; a.warp_smem_ints = g.warp_smem_ints;
+    // strip geometry: lane 0's first column is `left` columns before the strip (Sobel edge + window reach + NMS halo, rounded
+    // to words); a warp owns `outw` of its 128 support columns
+    const int half = bs / 2;                                      // window offsets [-half, bs - 1 - half]
+    a.left = (2 + half + 3) & ~3;
+    a.outw = (126 - a.left - (bs - 1 - half)) & ~3;
+    a.nstrips = (W + a.outw - 1) / a.outw;
     a.word_ok = (reinterpret_cast<uintptr_t>(gray) % 4 == 0) && (pitch % 4 == 0);
+    // strips whose 128 support columns are all real pixels take the word-load path: 1 <= strip < first_right
+    int first_right = a.nstrips;
+    while (first_right > 1 && (first_right - 1) * a.outw - a.left + EN_COLS > W) first_right--;
+    if (!a.word_ok || first_right <= 1) { a.nborder = a.nstrips; first_right = a.nstrips; }
+    else a.nborder = 1 + (a.nstrips - first_right);
+    a.first_right = first_right;
+    a.warp_smem_ints = bs * EN_COLS + EN_CB * 2 + 4 + (EN_PAD + EN_COLS + EN_PAD);
+    // rows per job: one wave of warps over the GPU (warm-up costs bs + 2 rows per job), at least 32 rows (8 for border strips)
+    int wps = (int)((227 * 1024) / ((size_t)a.warp_smem_ints * 4 * EN_WARPS + 1024)) * EN_WARPS;       // resident warps per SM
+    if (wps < 1) wps = 1;
+    if (wps > 16) wps = 16;                                       // 128 registers per thread
+    const int nfast = a.nstrips - a.nborder;
+    const int weight = nfast + EN_BORDER_SPLIT * a.nborder;       // jobs per row chunk, border strips count EN_BORDER_SPLIT times
+    int chunks = (kNumSMs * wps) / weight;
+    if (chunks < 1) chunks = 1;
+    int rows = (H + chunks - 1) / chunks;
+    if (rows < 32) rows = 32;
+    a.rows_fast = rows;
+    a.rows_border = (rows + EN_BORDER_SPLIT - 1) / EN_BORDER_SPLIT;
+    if (a.rows_border < 8) a.rows_border = 8;
+    a.chunks_border = (H + a.rows_border - 1) / a.rows_border;
+    a.njobs = a.nborder * a.chunks_border + nfast * ((H + rows - 1) / rows);
     if (bs == 10) return launch_eig_nms_bs<10>(a, st);
     if (bs == 3) return launch_eig_nms_bs<3>(a, st);
     return launch_eig_nms_bs<0>(a, st);
@@ -617,12 +660,16 @@ unsigned long long *radix_sort_u64_bytes(unsigned long long *keys0, unsigned lon
 // ---------------------------------------------------------------------------------------------
 // K2b: the whole selection in ONE persistent launch.  sorted[r] = ~key of rank r (rank 0 = strongest).
 constexpr int SEL_THREADS = 256;
+constexpr int SEL_CTAS_PER_SM = 2;                   // 2 x 256 threads x 128 registers fill an SM: the grid is kNumSMs * 2, all resident
+constexpr int SEL_STEPS = 4, SEL_TILE = RS_WARPS * SEL_STEPS * 32, SEL_TILE_SHIFT = 10;   // 1024 keys per sort tile: ~80 tiles for 81 k keys
+constexpr uint32_t CELL_END = 0xffffffffu;
 
 struct SelArgs {
     GfttCounters *cnt;
     unsigned long long *keys0, *keys1, *keys2;     // candidates (kept), ping-pong buffers of the sort
     uint32_t cap;
-    uint32_t *blockhist, *pos, *cell_start, *cell_fill, *items, *blockcnt, *scan_scratch;
+    uint32_t *hist3;                               // 3 x [256][ntu] digit counts per destination tile (sort passes, rotating)
+    uint32_t *pos, *head, *next, *blockcnt;        // positions by rank; cell lists (head per cell, next per rank); accepted per 256 ranks
     uint8_t *state;
     int H, W, maxCorners, cull, cell, gw, gh;
     uint32_t ncells, limit;
@@ -668,7 +715,73 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t *v, int len, uint32
     return wtot[8];
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
+// sum of g[0..len) over the CTA (every thread gets it)
+__device__ __forceinline__ uint32_t block_sum_global(const uint32_t *g, uint32_t len, uint32_t *wtot)
+{
+    uint32_t part = 0;
+    for (uint32_t t = threadIdx.x; t < len; t += SEL_THREADS) part += __ldcg(&g[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = part;
+    __syncthreads();
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) tot += wtot[w];
+    __syncthreads();
+    return tot;
+}
+
+// digit tables of the sort: [tile / 4][digit][tile % 4] -- one 16-byte load brings four tiles of a digit, a warp's loads coalesce
+__device__ __forceinline__ uint32_t hidx(uint32_t digit, uint32_t tile) { return (((tile >> 2) << 8) + digit) * 4 + (tile & 3u); }
+
+// one evaluation of OpenCV's greedy rule for rank r by walking its 3x3 cell neighbourhood: 0 = still blocked, else the state.
+// Breadth first: the nine list heads are fetched together, then all nine lists advance one element per step with their
+// loads in flight together -- a warp pays one latency chain per list DEPTH, not one per (cell, element) of its 32 lanes.
+__device__ __forceinline__ uint8_t cull_walk(const SelArgs &a, volatile const uint8_t *state, uint32_t r, int x, int y,
+                                             uint32_t *nb, int &nnb, bool &over, bool gather)
+{
+    const int cx = x / a.cell, cy = y / a.cell;
+    uint32_t q[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const int xx = cx + (i % 3) - 1, yy = cy + (i / 3) - 1;
+        q[i] = (xx >= 0 && xx < a.gw && yy >= 0 && yy < a.gh) ? __ldcg(&a.head[yy * a.gw + xx]) : CELL_END;
+    }
+    bool blocked = false, killed = false;
+    for (;;) {
+        bool any = false;
+        uint32_t qn[9], pq[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            qn[i] = CELL_END; pq[i] = 0;
+            if (q[i] != CELL_END) { any = true; qn[i] = __ldcg(&a.next[q[i]]); if (q[i] < r) pq[i] = __ldcg(&a.pos[q[i]]); }
+        }
+        if (!any) break;
+        uint8_t sq[9];
+        bool hit[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            hit[i] = false; sq[i] = ST_REJECTED;
+            if (q[i] != CELL_END && q[i] < r) {                               // only stronger candidates matter
+                const float dx = (float)(x - (int)(pq[i] & 0xffffu)), dy = (float)(y - (int)(pq[i] >> 16));
+                if (dx * dx + dy * dy < a.md2) { hit[i] = true; sq[i] = state[q[i]]; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            if (hit[i]) {
+                if (gather) { if (nnb < 8) nb[nnb++] = q[i]; else over = true; }
+                if (sq[i] == ST_ACCEPTED) killed = true;
+                else if (sq[i] == ST_UNDECIDED) blocked = true;
+            }
+            q[i] = qn[i];
+        }
+    }
+    return killed ? ST_REJECTED : (blocked ? ST_UNDECIDED : ST_ACCEPTED);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS, SEL_CTAS_PER_SM)
 gftt_select_kernel(const __grid_constant__ SelArgs a)
 {
     __shared__ uint32_t sh[4096];
@@ -679,6 +792,7 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t gtid = blockIdx.x * SEL_THREADS + tid, gsize = gridDim.x * SEL_THREADS;
     uint32_t bar_target = 0;
+    stamp(cnt, 0);
     const uint32_t mb = __ldcg(&cnt->maxbits);
     const uint32_t ncand = __ldcg(&cnt->ncand);
     if (!mb || !ncand || ncand > a.cap) {                 // uniform over the grid: nothing to select (or overflow)
@@ -690,23 +804,28 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
     }
     const float thr = (float)((double)dec_f32(mb) * a.quality);
     const uint32_t thrbits = enc_f32(thr);                // enc is order preserving: v > thr  <=>  enc(v) > thrbits
+    const uint32_t ntu = (((ncand + SEL_TILE - 1) / SEL_TILE) + 3) & ~3u; // tiles of the sort at most, in whole groups of four
+    const uint32_t nchunk_u = (ncand + SEL_THREADS - 1) / SEL_THREADS;
 
-    // ---- phase 1: response histogram of the candidates above the threshold; zero the cell grid ------------------------------
+    // ---- phase 1: response histogram of the candidates above the threshold; clear the tables of the later phases ---------
     for (int i = tid; i < 4096; i += SEL_THREADS) sh[i] = 0;
     __syncthreads();
     for (uint32_t i = gtid; i < ncand; i += gsize) {
-        const uint32_t e = (uint32_t)(a.keys0[i] >> 32);
+        const uint32_t e = (uint32_t)(__ldcg(&a.keys0[i]) >> 32);
         if (e > thrbits) atomicAdd(&sh[e >> 20], 1u);
     }
     __syncthreads();
     for (int i = tid; i < 4096; i += SEL_THREADS) if (sh[i]) atomicAdd(&cnt->hist[i], sh[i]);
+    for (uint32_t i = gtid; i < 3u * 256u * ntu; i += gsize) a.hist3[i] = 0;
+    for (uint32_t i = gtid; i < nchunk_u + 1; i += gsize) a.blockcnt[i] = 0;
+    if (a.cull) for (uint32_t i = gtid; i < a.ncells; i += gsize) a.head[i] = CELL_END;
     grid_barrier(&cnt->bar, bar_target);
+    stamp(cnt, 1);
 
     // ---- phase 2 (every CTA, redundantly): the response bin that keeps the strongest ~4 * maxCorners candidates ------------
     for (int i = tid; i < 4096; i += SEL_THREADS) sh[i] = __ldcg(&cnt->hist[i]);
     __syncthreads();
     {
-        // bins in DESCENDING order so that an exclusive scan gives "candidates stronger than this bin"
         uint32_t lo = 4096, hi = 0;
         for (int i = tid; i < 4096; i += SEL_THREADS) if (sh[i]) { lo = min(lo, (uint32_t)i); hi = max(hi, (uint32_t)i); }
         for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
@@ -716,11 +835,11 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
         __syncthreads();
     }
     const uint32_t lo_bin_all = s_misc[0], hi_bin = s_misc[1];
-    // reverse in place (pairs) then scan
+    // bins in DESCENDING order, so that the exclusive scan gives "candidates in stronger bins"
     for (int i = tid; i < 2048; i += SEL_THREADS) { const uint32_t t = sh[i]; sh[i] = sh[4095 - i]; sh[4095 - i] = t; }
     __syncthreads();
     const uint32_t total = block_scan_excl(sh, 4096, wtot);       // sh[j] = candidates in bins > 4095 - j
-    if (total == 0) {                                            // nothing above the threshold (cannot happen: the max is)
+    if (total == 0) {                                            // nothing above the threshold (cannot happen: the maximum is)
         if (gtid == 0) { cnt->nout = 0; *a.out_count = 0; }
         return;
     }
@@ -728,13 +847,16 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
     uint32_t min_bin = 0;
     bool subset = false;
     if (a.maxCorners > 0 && a.cull && (uint64_t)total > 2 * want) {
-        // smallest j with (candidates in bins >= 4095 - j) >= want, i.e. sh[j + 1] >= want (sh[4096] = total)
+        // smallest j with (candidates in bins >= 4095 - j) >= want
         if (tid == 0) s_misc[2] = 4095;
         __syncthreads();
+        uint32_t jm = 4095;
         for (int j = tid; j < 4096; j += SEL_THREADS) {
             const uint32_t incl = j == 4095 ? total : sh[j + 1];
-            if (incl >= want) atomicMin(&s_misc[2], (uint32_t)j);
+            if (incl >= want) jm = min(jm, (uint32_t)j);
         }
+        for (int o = 16; o > 0; o >>= 1) jm = min(jm, __shfl_xor_sync(0xffffffffu, jm, o));
+        if (lane == 0) atomicMin(&s_misc[2], jm);
         __syncthreads();
         const uint32_t j = s_misc[2];
         const uint32_t b = 4095 - j;
@@ -743,77 +865,85 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
     }
     __syncthreads();
 
-    uint32_t nacc = 0, n = 0;
+    uint32_t nacc = 0;
+    stamp(cnt, 2);
     for (int attempt = 0; attempt < 2; attempt++) {
         // attempt 0 may rank the strongest candidates only; if culling leaves fewer than maxCorners of them, attempt 1 repeats
         // with every candidate.  The greedy order makes the prefix exact either way: whether a candidate is accepted depends
         // on stronger candidates only.
-        if (attempt == 1) { min_bin = 0; subset = false; }
         const uint32_t lo_bin = max(lo_bin_all, min_bin);
-        // ---- select (complemented keys: the ascending sort of ~key is the descending (response, address) order) ----------------
+        // sort key = (hi_bound - response bits) << 32 | ~address: ascending order = (response desc, address desc), and only the
+        // bytes the selected response range can differ in are sorted
+        const uint32_t hi_bound = (hi_bin << 20) | 0xfffffu;
+        const uint32_t range = ((hi_bin - lo_bin + 1) << 20) - 1;            // largest possible hi_bound - e
+        const int last_pass = range < (1u << 8) ? 4 : range < (1u << 16) ? 5 : range < (1u << 24) ? 6 : 7;
+        // ---- select; every kept key also counts its first sort digit for the tile it lands in ------------------------------------
         for (uint32_t i0 = blockIdx.x * SEL_THREADS; i0 < ncand; i0 += gsize) {
             const uint32_t i = i0 + tid;
             unsigned long long k = 0;
             bool keep = false;
-            if (i < ncand) { k = a.keys0[i]; const uint32_t e = (uint32_t)(k >> 32); keep = e > thrbits && (e >> 20) >= min_bin; }
+            if (i < ncand) { k = __ldcg(&a.keys0[i]); const uint32_t e = (uint32_t)(k >> 32); keep = e > thrbits && (e >> 20) >= min_bin; }
             const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
             if (ballot) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&cnt->nsel, (uint32_t)__popc(ballot));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (keep) a.keys1[base + __popc(ballot & ((1u << lane) - 1u))] = ~k;
+                if (keep) {
+                    const uint32_t j = base + __popc(ballot & ((1u << lane) - 1u));
+                    const unsigned long long ck = ((unsigned long long)(hi_bound - (uint32_t)(k >> 32)) << 32) | (uint32_t)(~(uint32_t)k);
+                    a.keys1[j] = ck;
+                    atomicAdd(&a.hist3[hidx((uint32_t)((ck >> 32) & 0xff), j >> SEL_TILE_SHIFT)], 1u);
+                }
             }
         }
-        // zero the cell grid and the round counters while we are at it
-        if (a.cull) for (uint32_t i = gtid; i < a.ncells + 1; i += gsize) { a.cell_start[i] = 0; if (i < a.ncells) a.cell_fill[i] = 0; }
-        if (gtid < 64) cnt->remaining[gtid] = 0;
         grid_barrier(&cnt->bar, bar_target);
-        n = __ldcg(&cnt->nsel);
-        unsigned long long *src = a.keys1, *dst = a.keys2;
+        stamp(cnt, 3);
+        const uint32_t n = __ldcg(&cnt->nsel);
+        const unsigned long long *src = a.keys1;
+        unsigned long long *dst = a.keys2;
 
-        // ---- stable LSD radix sort on the response bytes (the top byte is usually the same for every candidate) -------------
+        // ---- stable LSD radix sort on the response bytes; each pass counts the next pass's digits while it scatters --------
         if (n > 1) {
-            const uint32_t ntiles = (n + RS_TILE - 1) / RS_TILE;
-            const int last_pass = (lo_bin >> 4) == (hi_bin >> 4) ? 6 : 7;
+            const uint32_t ntiles = (n + SEL_TILE - 1) / SEL_TILE;
             for (int p = 4; p <= last_pass; p++) {
                 const int shift = 8 * p;
-                for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // digit counts per tile
-                    __syncthreads();
-                    sh[tid] = 0;
-                    __syncthreads();
-                    const uint32_t base = tile * RS_TILE;
-                    for (uint32_t i = tid; i < RS_TILE; i += SEL_THREADS) {
-                        const uint32_t g = base + i;
-                        if (g < n) atomicAdd(&sh[(uint32_t)((src[g] >> shift) & 0xff)], 1u);
-                    }
-                    __syncthreads();
-                    a.blockhist[tid * ntiles + tile] = sh[tid];
+                const uint32_t *hcur = a.hist3 + (size_t)((p - 4) % 3) * 256 * ntu;
+                uint32_t *hnext = a.hist3 + (size_t)((p - 3) % 3) * 256 * ntu;
+                if (p + 2 <= last_pass) {                                       // the table of pass p+2 was used by pass p-1
+                    uint32_t *hz = a.hist3 + (size_t)((p - 2) % 3) * 256 * ntu;
+                    for (uint32_t i = gtid; i < 256u * ntu; i += gsize) hz[i] = 0;
                 }
-                grid_barrier(&cnt->bar, bar_target);
-                // digit bases: thread d sums its digit over all tiles, exclusive scan over the 256 digits
-                {
-                    uint32_t rs = 0;
-                    for (uint32_t t = 0; t < ntiles; t++) rs += __ldcg(&a.blockhist[tid * ntiles + t]);
+                for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                    // thread d: its digit summed over all tiles (-> digit base by an exclusive scan) and over the tiles before this one
+                    uint32_t rs = 0, before = 0;
+                    const uint4 *hq = reinterpret_cast<const uint4 *>(hcur) + tid;
+#pragma unroll 4
+                    for (uint32_t g = 0; g < (ntiles + 3) / 4; g++) {
+                        const uint4 c = __ldcg(hq + (size_t)g * 256);
+                        const uint32_t t0 = 4 * g;
+                        rs += c.x + c.y + c.z + c.w;
+                        before += (t0 < tile ? c.x : 0) + (t0 + 1 < tile ? c.y : 0) + (t0 + 2 < tile ? c.z : 0) + (t0 + 3 < tile ? c.w : 0);
+                    }
                     __syncthreads();
                     sh[tid] = rs;
                     __syncthreads();
                     block_scan_excl(sh, 256, wtot);
-                }
-                const uint32_t digit_base = sh[tid];
-                __syncthreads();
-                for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {             // scatter
-                    uint32_t before = 0;
-                    for (uint32_t t = 0; t < tile; t++) before += __ldcg(&a.blockhist[tid * ntiles + t]);
+                    const uint32_t digit_base = sh[tid];
+                    __syncthreads();
                     for (int i = tid; i < RS_WARPS * 256; i += SEL_THREADS) (&wcount[0][0])[i] = 0;
                     __syncthreads();
-                    const uint32_t wbase = tile * RS_TILE + wid * (RS_STEPS * 32);
-                    unsigned long long k[RS_STEPS];
-                    uint32_t rank[RS_STEPS];
+                    const uint32_t wbase = tile * SEL_TILE + wid * (SEL_STEPS * 32);
+                    unsigned long long k[SEL_STEPS];
+                    uint32_t rank[SEL_STEPS];
 #pragma unroll
-                    for (int s = 0; s < RS_STEPS; s++) {
+                    for (int s = 0; s < SEL_STEPS; s++) {                       // all loads of the tile in flight together
+                        const uint32_t g = wbase + s * 32 + lane;
+                        k[s] = g < n ? __ldcg(&src[g]) : 0ull;
+                    }
+#pragma unroll
+                    for (int s = 0; s < SEL_STEPS; s++) {
                         const uint32_t g = wbase + s * 32 + lane;
                         const bool valid = g < n;
-                        k[s] = valid ? src[g] : 0ull;
                         const uint32_t d = (uint32_t)((k[s] >> shift) & 0xff);
                         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                         uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane) & vmask;
@@ -834,130 +964,119 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
                     }
                     __syncthreads();
 #pragma unroll
-                    for (int s = 0; s < RS_STEPS; s++) {
+                    for (int s = 0; s < SEL_STEPS; s++) {
                         const uint32_t g = wbase + s * 32 + lane;
                         if (g < n) {
                             const uint32_t d = (uint32_t)((k[s] >> shift) & 0xff);
-                            dst[wcount[wid][d] + rank[s]] = k[s];
+                            const uint32_t j = wcount[wid][d] + rank[s];
+                            dst[j] = k[s];
+                            if (p < last_pass) atomicAdd(&hnext[hidx((uint32_t)((k[s] >> (shift + 8)) & 0xff), j >> SEL_TILE_SHIFT)], 1u);
                         }
                     }
                     __syncthreads();
                 }
                 grid_barrier(&cnt->bar, bar_target);
-                unsigned long long *t = src; src = dst; dst = t;
+                stamp(cnt, p);
+                const unsigned long long *t = src; src = dst; dst = const_cast<unsigned long long *>(t);
             }
-            // equal responses keep their arrival order after the stable sort: order each run of equal responses by address
-            // (complemented keys ascending = address descending, OpenCV's tie-break).  Runs are rare and short.
+        }
+        // ---- positions by rank, cell lists.  Equal responses kept their arrival order: the first element of a run of equal
+        // responses orders the run by address (complemented keys ascending = address descending, OpenCV's tie-break) ------
+        {
+            unsigned long long *srt = const_cast<unsigned long long *>(src);
             for (uint32_t i = gtid; i < n; i += gsize) {
-                const uint32_t v = (uint32_t)(src[i] >> 32);
-                if (i > 0 && (uint32_t)(src[i - 1] >> 32) == v) continue;       // not the first of its run
+                const uint32_t v = (uint32_t)(__ldcg(&srt[i]) >> 32);
+                if (i > 0 && (uint32_t)(__ldcg(&srt[i - 1]) >> 32) == v) continue;
                 uint32_t e = i + 1;
-                while (e < n && (uint32_t)(src[e] >> 32) == v) e++;
-                for (uint32_t x = i + 1; x < e; x++) {                          // insertion sort of src[i..e)
-                    const unsigned long long kk = src[x];
+                while (e < n && (uint32_t)(__ldcg(&srt[e]) >> 32) == v) e++;
+                for (uint32_t x = i + 1; x < e; x++) {                          // insertion sort of srt[i..e): runs are rare and short
+                    const unsigned long long kk = srt[x];
                     uint32_t b = x;
-                    while (b > i && src[b - 1] > kk) { src[b] = src[b - 1]; b--; }
-                    src[b] = kk;
+                    while (b > i && srt[b - 1] > kk) { srt[b] = srt[b - 1]; b--; }
+                    srt[b] = kk;
+                }
+                for (uint32_t x = i; x < e; x++) {
+                    const uint32_t idx = ~(uint32_t)srt[x];
+                    const uint32_t y = idx / a.W, xc = idx - y * a.W;
+                    a.pos[x] = xc | (y << 16);
+                    a.state[x] = ST_UNDECIDED;
+                    if (a.cull) a.next[x] = atomicExch(&a.head[(y / a.cell) * a.gw + xc / a.cell], x);
                 }
             }
-            grid_barrier(&cnt->bar, bar_target);
-        }
-
-        // ---- positions of all ranks; OpenCV's cell grid as CSR lists ---------------------------------------------------------
-        for (uint32_t r = gtid; r < n; r += gsize) {
-            const uint32_t idx = (uint32_t)(~src[r]);
-            const uint32_t y = idx / a.W, x = idx - y * a.W;
-            a.pos[r] = x | (y << 16);
-            a.state[r] = ST_UNDECIDED;
-            if (a.cull) atomicAdd(&a.cell_start[(y / a.cell) * a.gw + x / a.cell], 1u);
         }
         grid_barrier(&cnt->bar, bar_target);
+        stamp(cnt, 8);
+        // ---- culling: decisions are final and monotone, so a thread may read fresh or stale states.  Every thread first collects
+        // the stronger conflicting candidates of its ranks (walk of the 3x3 cell lists, once), then polls their states a few
+        // times per grid barrier until no rank of the grid is undecided.  Ranks are handed out in rank-ordered batches of two per
+        // thread: dependencies point to stronger ranks only, so a batch never waits for a later one -----------------------------
         if (a.cull) {
-            // exclusive scan of cell_start[0 .. ncells]: 4096-entry chunks per CTA, chunk totals, offsets
-            const uint32_t len = a.ncells + 1, nchunks = (len + 4095) / 4096;
-            for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-                __syncthreads();
-                for (int i = tid; i < 4096; i += SEL_THREADS) { const uint32_t g = c * 4096 + i; sh[i] = g < len ? __ldcg(&a.cell_start[g]) : 0; }
-                __syncthreads();
-                const uint32_t tot = block_scan_excl(sh, 4096, wtot);
-                for (int i = tid; i < 4096; i += SEL_THREADS) { const uint32_t g = c * 4096 + i; if (g < len) a.cell_start[g] = sh[i]; }
-                if (tid == 0) a.scan_scratch[c] = tot;
-            }
-            grid_barrier(&cnt->bar, bar_target);
-            for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-                if (c == 0) continue;
-                // offset of chunk c = sum of the totals of the chunks before it
-                uint32_t part = 0;
-                for (uint32_t t = tid; t < c; t += SEL_THREADS) part += __ldcg(&a.scan_scratch[t]);
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                __syncthreads();
-                if (lane == 0) wtot[wid] = part;
-                __syncthreads();
-                uint32_t off = 0;
-                for (int w = 0; w < 8; w++) off += wtot[w];
-                for (int i = tid; i < 4096; i += SEL_THREADS) { const uint32_t g = c * 4096 + i; if (g < len) a.cell_start[g] += off; }
-            }
-            grid_barrier(&cnt->bar, bar_target);
-            for (uint32_t r = gtid; r < n; r += gsize) {
-                const uint32_t p = __ldcg(&a.pos[r]);
-                const uint32_t c = ((p >> 16) / a.cell) * a.gw + (p & 0xffffu) / a.cell;
-                a.items[__ldcg(&a.cell_start[c]) + atomicAdd(&a.cell_fill[c], 1u)] = r;
-            }
-            grid_barrier(&cnt->bar, bar_target);
-            // ---- culling rounds until no candidate is undecided --------------------------------------------------------------
             volatile uint8_t *state = a.state;
-            for (int round = 0;; round++) {
-                uint32_t left_cnt = 0;
-                for (uint32_t r = gtid; r < n; r += gsize) {
-                    if (state[r] != ST_UNDECIDED) continue;
-                    const uint32_t p = __ldcg(&a.pos[r]);
-                    const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
-                    const int cx = x / a.cell, cy = y / a.cell;
-                    const int x1 = max(cx - 1, 0), x2 = min(cx + 1, a.gw - 1), y1 = max(cy - 1, 0), y2 = min(cy + 1, a.gh - 1);
-                    bool blocked = false, killed = false;
-                    for (int yy = y1; yy <= y2 && !killed; yy++) {
-                        // the cells x1..x2 of one grid row are contiguous in the CSR layout
-                        const uint32_t kb = __ldcg(&a.cell_start[yy * a.gw + x1]), ke = __ldcg(&a.cell_start[yy * a.gw + x2 + 1]);
-                        for (uint32_t k = kb; k < ke; k++) {
-                            const uint32_t q = __ldcg(&a.items[k]);
-                            if (q >= r) continue;                                    // only stronger candidates matter
-                            const uint32_t pq = __ldcg(&a.pos[q]);
-                            const float dx = (float)(x - (int)(pq & 0xffffu)), dy = (float)(y - (int)(pq >> 16));
-                            if (dx * dx + dy * dy < a.md2) {
-                                const uint8_t s = state[q];
-                                if (s == ST_ACCEPTED) { killed = true; break; }
-                                if (s == ST_UNDECIDED) blocked = true;
+            uint32_t round_no = 0;
+            for (uint32_t b0 = 0; b0 < n; b0 += 2 * gsize) {
+                uint32_t r[2], nb[2][8];
+                int xs[2], ys[2], nnb[2];
+                bool over[2], open[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    r[j] = b0 + j * gsize + gtid;
+                    open[j] = r[j] < n;
+                    nnb[j] = 0; over[j] = false; xs[j] = ys[j] = 0;
+                    if (open[j]) {
+                        const uint32_t p = __ldcg(&a.pos[r[j]]);
+                        xs[j] = (int)(p & 0xffffu); ys[j] = (int)(p >> 16);
+                        const uint8_t s = cull_walk(a, state, r[j], xs[j], ys[j], nb[j], nnb[j], over[j], true);
+                        if (s != ST_UNDECIDED) {
+                            state[r[j]] = s; open[j] = false;
+                            if (s == ST_ACCEPTED) atomicAdd(&a.blockcnt[r[j] >> 8], 1u);
+                        }
+                    }
+                }
+                for (;;) {
+                    for (int it = 0; it < 4 && (open[0] || open[1]); it++) {
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            if (!open[j]) continue;
+                            uint8_t s = ST_ACCEPTED;
+                            if (over[j]) {
+                                int dummy = 8; bool od = false;
+                                s = cull_walk(a, state, r[j], xs[j], ys[j], nb[j], dummy, od, false);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) {
+                                    if (i < nnb[j]) {
+                                        const uint8_t sq = state[nb[j][i]];
+                                        if (sq == ST_ACCEPTED) s = ST_REJECTED;
+                                        else if (sq == ST_UNDECIDED && s != ST_REJECTED) s = ST_UNDECIDED;
+                                    }
+                                }
+                            }
+                            if (s != ST_UNDECIDED) {
+                                state[r[j]] = s; open[j] = false;
+                                if (s == ST_ACCEPTED) atomicAdd(&a.blockcnt[r[j] >> 8], 1u);
                             }
                         }
                     }
-                    if (killed) state[r] = ST_REJECTED;
-                    else if (!blocked) state[r] = ST_ACCEPTED;
-                    else left_cnt++;
+                    // anyone still undecided in this batch?  (one counter per round, recycled after 32 rounds)
+                    const int left = __syncthreads_count(open[0] || open[1]);
+                    if (tid == 0) {
+                        if (left) atomicAdd(&cnt->remaining[round_no & 63], (uint32_t)left);
+                        if (blockIdx.x == 0) cnt->remaining[(round_no + 32) & 63] = 0;
+                    }
+                    grid_barrier(&cnt->bar, bar_target);
+                    const uint32_t rem = __ldcg(&cnt->remaining[round_no & 63]);
+                    round_no++;
+                    if (rem == 0) break;
                 }
-                for (int o = 16; o > 0; o >>= 1) left_cnt += __shfl_xor_sync(0xffffffffu, left_cnt, o);
-                if (lane == 0 && left_cnt) atomicAdd(&cnt->remaining[round & 63], left_cnt);
-                if (gtid == 0) cnt->remaining[(round + 32) & 63] = 0;          // recycled long before it is used again
-                grid_barrier(&cnt->bar, bar_target);
-                if (__ldcg(&cnt->remaining[round & 63]) == 0) break;
             }
         }
+        stamp(cnt, 9);
         // ---- accepted candidates in rank order -> (x, y), first `limit` -------------------------------------------------------
         const uint32_t nchunk = (n + SEL_THREADS - 1) / SEL_THREADS;
+        nacc = a.cull ? block_sum_global(a.blockcnt, nchunk, wtot) : n;
         for (uint32_t c = blockIdx.x; c < nchunk; c += gridDim.x) {
-            const uint32_t r = c * SEL_THREADS + tid;
-            const int cacc = __syncthreads_count(r < n && (!a.cull || __ldcg(&a.state[r]) == ST_ACCEPTED));
-            if (tid == 0) a.blockcnt[c] = (uint32_t)cacc;
-        }
-        grid_barrier(&cnt->bar, bar_target);
-        for (uint32_t c = blockIdx.x; c < nchunk; c += gridDim.x) {
-            uint32_t part = 0;
-            for (uint32_t t = tid; t < c; t += SEL_THREADS) part += __ldcg(&a.blockcnt[t]);
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            __syncthreads();
-            if (lane == 0) wtot[wid] = part;
-            __syncthreads();
-            uint32_t off = 0;
-            for (int w = 0; w < 8; w++) off += wtot[w];
+            const uint32_t off = a.cull ? block_sum_global(a.blockcnt, c, wtot) : c * SEL_THREADS;
+            if (off >= a.limit) continue;                                   // block-uniform
             const uint32_t r = c * SEL_THREADS + tid;
             const bool acc = r < n && (!a.cull || __ldcg(&a.state[r]) == ST_ACCEPTED);
             const uint32_t ballot = __ballot_sync(0xffffffffu, acc);
@@ -974,22 +1093,24 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
                     a.out_xy[2 * m + 1] = (float)(p >> 16);
                 }
             }
-            if (c == nchunk - 1 && tid == SEL_THREADS - 1) {      // grand total = offset of the last chunk + its own count
-                uint32_t tot = off;
-                for (int w = 0; w < 8; w++) tot += wtot[w];
-                cnt->nacc = tot;
-            }
+            __syncthreads();
         }
-        grid_barrier(&cnt->bar, bar_target);
-        nacc = __ldcg(&cnt->nacc);
         if (!subset || nacc >= (uint32_t)a.maxCorners) break;          // done (the subset produced a full prefix)
-        if (gtid == 0) { cnt->nsel = 0; cnt->nacc = 0; }
+        // ---- too few survivors among the strongest: once more with every candidate above the threshold ---------------------------
+        grid_barrier(&cnt->bar, bar_target);                            // everyone has read blockcnt / state
+        min_bin = 0; subset = false;
+        if (gtid == 0) cnt->nsel = 0;
+        for (uint32_t i = gtid; i < 3u * 256u * ntu; i += gsize) a.hist3[i] = 0;
+        for (uint32_t i = gtid; i < nchunk_u + 1; i += gsize) a.blockcnt[i] = 0;
+        for (uint32_t i = gtid; i < a.ncells; i += gsize) a.head[i] = CELL_END;
         grid_barrier(&cnt->bar, bar_target);
     }
+    stamp(cnt, 10);
     if (gtid == 0) {
         uint32_t nout = nacc;
         if (a.maxCorners > 0 && nout > (uint32_t)a.maxCorners) nout = (uint32_t)a.maxCorners;
         if (nout > a.limit) { cnt->error = IBT_E_CAPACITY; }
+        cnt->nacc = nacc;
         cnt->nout = nout;
         *a.out_count = (int)nout;
     }
@@ -997,8 +1118,7 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
 
 // workspace layout
 struct GfttLayout {
-    size_t off_cnt, off_keys0, off_keys1, off_keys2, off_blockhist, off_pos, off_state, off_cells, off_fill, off_items,
-        off_blockcnt, off_scan, total;
+    size_t off_cnt, off_keys0, off_keys1, off_keys2, off_hist3, off_pos, off_state, off_head, off_next, off_blockcnt, total;
     uint32_t cap, max_sort_blocks, max_cells;
 };
 static GfttLayout gftt_layout(int H, int W)
@@ -1007,21 +1127,19 @@ static GfttLayout gftt_layout(int H, int W)
     const size_t np = (size_t)H * W;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     L.cap = (uint32_t)(np / 4 + 4096);                 // isolated 3x3 maxima cannot be denser than 1 in 4 pixels (plateaus can: IBT_E_CAPACITY)
-    L.max_sort_blocks = (L.cap + RS_TILE - 1) / RS_TILE;
+    L.max_sort_blocks = (L.cap + 1024 - 1) / 1024;          // SEL_TILE
     L.max_cells = (uint32_t)np + 1;                    // cell >= 1 pixel
     size_t o = 0;
     L.off_cnt = o; o = up(o + sizeof(GfttCounters));
     L.off_keys0 = o; o = up(o + (size_t)L.cap * 8);
     L.off_keys1 = o; o = up(o + (size_t)L.cap * 8);
     L.off_keys2 = o; o = up(o + (size_t)L.cap * 8);
-    L.off_blockhist = o; o = up(o + (size_t)256 * L.max_sort_blocks * 4);
+    L.off_hist3 = o; o = up(o + (size_t)3 * 256 * (L.max_sort_blocks + 4) * 4);
     L.off_pos = o; o = up(o + (size_t)L.cap * 4);
     L.off_state = o; o = up(o + (size_t)L.cap);
-    L.off_cells = o; o = up(o + ((size_t)L.max_cells + 1) * 4);
-    L.off_fill = o; o = up(o + (size_t)L.max_cells * 4);
-    L.off_items = o; o = up(o + (size_t)L.cap * 4);
-    L.off_blockcnt = o; o = up(o + ((size_t)L.cap / 256 + 2) * 4);
-    L.off_scan = o; o = up(o + ((size_t)L.max_cells / 4096 + 4) * 4);
+    L.off_head = o; o = up(o + (size_t)L.max_cells * 4);
+    L.off_next = o; o = up(o + (size_t)L.cap * 4);
+    L.off_blockcnt = o; o = up(o + ((size_t)L.cap / 256 + 4) * 4);
     L.total = o;
     return L;
 }
@@ -1048,14 +1166,12 @@ static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask,
     a.keys1 = reinterpret_cast<unsigned long long *>(ws + L.off_keys1);
     a.keys2 = reinterpret_cast<unsigned long long *>(ws + L.off_keys2);
     a.cap = L.cap;
-    a.blockhist = reinterpret_cast<uint32_t *>(ws + L.off_blockhist);
+    a.hist3 = reinterpret_cast<uint32_t *>(ws + L.off_hist3);
     a.pos = reinterpret_cast<uint32_t *>(ws + L.off_pos);
     a.state = ws + L.off_state;
-    a.cell_start = reinterpret_cast<uint32_t *>(ws + L.off_cells);
-    a.cell_fill = reinterpret_cast<uint32_t *>(ws + L.off_fill);
-    a.items = reinterpret_cast<uint32_t *>(ws + L.off_items);
+    a.head = reinterpret_cast<uint32_t *>(ws + L.off_head);
+    a.next = reinterpret_cast<uint32_t *>(ws + L.off_next);
     a.blockcnt = reinterpret_cast<uint32_t *>(ws + L.off_blockcnt);
-    a.scan_scratch = reinterpret_cast<uint32_t *>(ws + L.off_scan);
     a.H = H; a.W = W; a.maxCorners = maxCorners;
     a.cull = minDistance >= 1.0 ? 1 : 0;
     a.cell = a.cull ? (int)lrint(minDistance) : 65536;        // no culling: only positions are needed
@@ -1068,7 +1184,7 @@ static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask,
     a.md2 = (float)(minDistance * minDistance);
     a.out_xy = out_xy;
     a.out_count = count_dev ? count_dev : reinterpret_cast<int *>(&cnt->pad);
-    gftt_select_kernel<<<kNumSMs, SEL_THREADS, 0, st>>>(a);        // every CTA resident: the kernel synchronises its grid itself
+    gftt_select_kernel<<<kNumSMs * SEL_CTAS_PER_SM, SEL_THREADS, 0, st>>>(a);        // every CTA resident: the kernel synchronises its grid itself
     return check_launch("gftt_select_kernel");
 }
 
