@@ -65,6 +65,7 @@ SIGNATURES = {
     "ibt_gftt": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _d, _d, _i, _vp, _sz, _vp, _i, C.POINTER(C.c_int), _vp]),
     "ibt_gftt_async": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _d, _d, _i, _vp, _sz, _vp, _i, _vp, _vp]),
     "ibt_tracks_compact": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(C.c_int), _vp]),
+    "ibt_tracks_compact_async": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ibt_photo_to_utm": (_i, [_vp, _i64, C.POINTER(C.c_double), _vp, _vp]),
     "ibt_track_velocities": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "ibt_polygon_mask": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp]),

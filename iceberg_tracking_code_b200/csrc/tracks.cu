@@ -81,6 +81,21 @@ tracks_scatter_kernel(const float2 *__restrict__ tracks_tm, const float *__restr
 
 } // namespace ibt
 
+static int tracks_compact_enqueue(const float *tracks_tm, const float *quality_tm, const uint8_t *alive, int N, int T,
+                                  int32_t *scratch, float *out_tracks, float *out_quality, cudaStream_t st)
+{
+    using namespace ibt;
+    if (!tracks_tm || !quality_tm || !alive || !scratch || !out_tracks || !out_quality ||
+        reinterpret_cast<uintptr_t>(tracks_tm) % 8 != 0 || reinterpret_cast<uintptr_t>(out_tracks) % 8 != 0)
+        return IBT_E_INVALID;
+    const int nb = (N + CB - 1) / CB;
+    alive_count_kernel<<<nb, CB, 0, st>>>(alive, N, scratch);
+    block_scan_kernel<<<1, 1024, 0, st>>>(scratch, nb, scratch + N);
+    tracks_scatter_kernel<<<nb, CB, 0, st>>>(reinterpret_cast<const float2 *>(tracks_tm), quality_tm, alive, N, T, scratch,
+                                             reinterpret_cast<float2 *>(out_tracks), out_quality);
+    return check_launch("ibt_tracks_compact");
+}
+
 IBT_API int ibt_tracks_compact(const float *tracks_tm, const float *quality_tm, const uint8_t *alive, int N, int T,
                                int32_t *scratch, float *out_tracks, float *out_quality, int *out_count, void *stream)
 {
@@ -88,20 +103,20 @@ IBT_API int ibt_tracks_compact(const float *tracks_tm, const float *quality_tm, 
     if (N < 0 || T < 1 || !out_count) return IBT_E_INVALID;
     *out_count = 0;
     if (N == 0) return IBT_OK;
-    if (!tracks_tm || !quality_tm || !alive || !scratch || !out_tracks || !out_quality ||
-        reinterpret_cast<uintptr_t>(tracks_tm) % 8 != 0 || reinterpret_cast<uintptr_t>(out_tracks) % 8 != 0)
-        return IBT_E_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int nb = (N + CB - 1) / CB;
-    alive_count_kernel<<<nb, CB, 0, st>>>(alive, N, scratch);
-    block_scan_kernel<<<1, 1024, 0, st>>>(scratch, nb, scratch + N);
-    tracks_scatter_kernel<<<nb, CB, 0, st>>>(reinterpret_cast<const float2 *>(tracks_tm), quality_tm, alive, N, T, scratch,
-                                             reinterpret_cast<float2 *>(out_tracks), out_quality);
-    int rc = check_launch("ibt_tracks_compact");
+    int rc = tracks_compact_enqueue(tracks_tm, quality_tm, alive, N, T, scratch, out_tracks, out_quality, st);
     if (rc) return rc;
     int32_t total = 0;
     IBT_CUDA_TRY(cudaMemcpyAsync(&total, scratch + N, sizeof(total), cudaMemcpyDeviceToHost, st));
     IBT_CUDA_TRY(cudaStreamSynchronize(st));
     *out_count = total;
     return IBT_OK;
+}
+
+IBT_API int ibt_tracks_compact_async(const float *tracks_tm, const float *quality_tm, const uint8_t *alive, int N, int T,
+                                     int32_t *scratch, float *out_tracks, float *out_quality, void *stream)
+{
+    if (N < 1 || T < 1) return IBT_E_INVALID;
+    return tracks_compact_enqueue(tracks_tm, quality_tm, alive, N, T, scratch, out_tracks, out_quality,
+                                  static_cast<cudaStream_t>(stream));
 }

@@ -68,9 +68,9 @@ def gather_results(results, track_len, device=None, to_host=True):
     to_host="rank0" is the single-writer mode: rank 0 copies the gathered arrays to the host once (one D2H per array),
     the other ranks keep device views."""
     import torch.distributed as dist
-    meta, tracks, quality = pack_results(results, track_len)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return unpack_results(meta, tracks, quality)
+        return [(int(seed), tracks, quality) for seed, _path, tracks, quality in results]      # one rank: nothing to move
+    meta, tracks, quality = pack_results(results, track_len)
     world = dist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")

@@ -131,6 +131,11 @@ class SequenceTracker:
         self.steps = 0             # pairs tracked in the current group
         self.T = 0
         self._tracks = self._quality = self._alive = None
+        # prepare + goodFeaturesToTrack of upcoming frames (track_sequence); high priority: its CTAs take the SM slots that the
+        # persistent LK launch frees while its last warps finish, ahead of the next LK launch
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self._pinned = {}          # free pinned host buffers by size (results travel D2H asynchronously)
+        self._ws = None            # private goodFeaturesToTrack workspace (one call in flight per tracker)
 
     # -- frames ---------------------------------------------------------------------------------------
     def upload(self, frame):
@@ -169,9 +174,66 @@ class SequenceTracker:
             return pyr
 
     # -- group life cycle -----------------------------------------------------------------------------
-    def seed(self, pyr, mask=None, track_len=2, points=None):
-        """Re-seed (s1:437-448): Shi-Tomasi corners of the frame (or the given (N,1,2) points) start a new group."""
-        if points is None:
+    def _pin(self, shape, dtype):
+        """pinned host tensor from the tracker's pool (give it back with _unpin)"""
+        key = (tuple(shape), dtype)
+        lst = self._pinned.get(key)
+        if lst:
+            return lst.pop()
+        return torch.empty(shape, dtype=dtype).pin_memory()
+
+    def _unpin(self, t):
+        self._pinned.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+    def gftt_prefetch(self, pyr, mask=None):
+        """Enqueue cv2.goodFeaturesToTrack(frame_gray, mask=mask, **feature_params) (s1:437) of a frame that will seed a
+        group, on the CURRENT stream, without waiting for it (ibt_gftt_async): returns the handle seed(prefetched=) takes.
+        track_sequence issues it on the side stream one frame ahead, so the corners are ready when the group starts."""
+        fp = self.feature_params
+        if fp.get("useHarrisDetector", False):
+            raise cv.error("goodFeaturesToTrack: useHarrisDetector=True is not implemented (the reference never sets it)")
+        q, md, bs = float(fp["qualityLevel"]), float(fp["minDistance"]), int(fp.get("blockSize", 3))
+        if not (q > 0) or md < 0:
+            raise cv.error("goodFeaturesToTrack: qualityLevel must be > 0 and minDistance >= 0")
+        img = pyr.levels[0]
+        H, W = img.shape
+        if H < 3 or W < 3:
+            return None
+        m = None
+        if mask is not None:
+            m = cv._to_dev(mask, np.uint8, "goodFeaturesToTrack mask")
+            if tuple(m.shape) != (H, W):
+                raise cv.error("goodFeaturesToTrack: mask must be (H,W) u8 of the image size")
+        nbytes = N.lib().ibt_gftt_workspace_bytes(H, W)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        maxc = int(fp["maxCorners"])
+        cap = H * W // 4 + 4096
+        if 0 < maxc < cap:
+            cap = maxc
+        out = torch.empty((cap, 2), dtype=torch.float32, device=self.device)
+        cnt = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        p = cv._ptr
+        N.check(N.lib().ibt_gftt_async(p(img), img.stride(0), p(m), W, H, W, maxc, q, md, bs, p(self._ws), self._ws.numel(),
+                                       p(out), cap, p(cnt), cv._stream()), "ibt_gftt_async")
+        h = self._pin((1,), torch.int32)
+        h.copy_(cnt, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return out, cnt, h, ev
+
+    def seed(self, pyr, mask=None, track_len=2, points=None, prefetched=None):
+        """Re-seed (s1:437-448): Shi-Tomasi corners of the frame (or the given (N,1,2) points) start a new group.
+        prefetched: handle of gftt_prefetch() for this frame (the corners were computed ahead on another stream)."""
+        if prefetched is not None:
+            out, _cnt, h, ev = prefetched
+            ev.synchronize()                              # (issued a frame ago: normally long finished)
+            n = int(h[0])
+            self._unpin(h)
+            torch.cuda.current_stream().wait_event(ev)
+            out.record_stream(torch.cuda.current_stream())
+            p = out[:n] if n else None
+        elif points is None:
             p = cv.goodFeaturesToTrack(pyr.levels[0], mask=mask, **self.feature_params)
         else:
             p = cv._to_dev(points, np.float32, "seed points")
@@ -228,6 +290,39 @@ class SequenceTracker:
         if to_host:
             return out_t[:m].cpu().numpy(), out_q[:m].cpu().numpy()
         return out_t[:m], out_q[:m]
+
+    def harvest_async(self):
+        """harvest() without waiting: compaction and the device->host copies of the current group are enqueued on the
+        current stream; finalize(handle) returns the arrays later (track_sequence finalises a group while the next one
+        is being tracked)."""
+        if self.n == 0 or self.steps == 0:
+            return ("done", self.harvest())
+        n, k = self.n, self.steps
+        scratch = torch.empty((n + 1,), dtype=torch.int32, device=self.device)
+        out_t = torch.empty((n, k + 1, 2), dtype=torch.float32, device=self.device)
+        out_q = torch.empty((n, k), dtype=torch.float32, device=self.device)
+        p = cv._ptr
+        N.check(N.lib().ibt_tracks_compact_async(p(self._tracks), p(self._quality), p(self._alive), n, k, p(scratch), p(out_t),
+                                                 p(out_q), cv._stream()), "ibt_tracks_compact_async")
+        h_t, h_q, h_m = self._pin((n, k + 1, 2), torch.float32), self._pin((n, k), torch.float32), self._pin((1,), torch.int32)
+        h_t.copy_(out_t, non_blocking=True); h_q.copy_(out_q, non_blocking=True); h_m.copy_(scratch[n:], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ("pending", h_t, h_q, h_m, ev)
+
+    def finalize(self, handle):
+        """-> (tracks (M, steps+1, 2) f32, trackquality (M, steps) f32) of a harvest_async() handle (M == 0: two (0,) f64)."""
+        if handle[0] == "done":
+            return handle[1]
+        _tag, h_t, h_q, h_m, ev = handle
+        ev.synchronize()
+        m = int(h_m[0])
+        if m == 0:
+            res = (np.zeros((0,), np.float64), np.zeros((0,), np.float64))
+        else:
+            res = (h_t[:m].numpy().copy(), h_q[:m].numpy().copy())
+        self._unpin(h_t); self._unpin(h_q); self._unpin(h_m)
+        return res
 
     def alive_count(self):
         return 0 if self.n == 0 else int(self._alive.sum().item())
@@ -288,54 +383,110 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         prev = None
         seed_idx = None
         counters = range(g0 * T, g1 * T + 1)
-        pool, pending = None, {}
+        pool, futures = None, {}
         # (the "gpu" loader reads the few MB of a file in the calling thread: a pool only adds GIL contention there)
         if host_loader is not None and gpu is None and decode_workers and decode_workers > 1:
             from concurrent.futures import ThreadPoolExecutor
             pool = ThreadPoolExecutor(max_workers=int(decode_workers))
             for c in counters[:decode_workers]:
-                pending[c] = pool.submit(host_loader, frames[c])
+                futures[c] = pool.submit(host_loader, frames[c])
 
         def fetch(c):
             """frame c as prepare() takes it (host array, device tensor, or (device tensor, event) from the GPU decoder)"""
             if pool is not None:
                 nxt = c + decode_workers
                 if nxt <= counters[-1]:
-                    pending[nxt] = pool.submit(host_loader, frames[nxt])
-                data = pending.pop(c).result()
+                    futures[nxt] = pool.submit(host_loader, frames[nxt])
+                data = futures.pop(c).result()
             elif gpu is not None:
                 return gpu(frames[c])             # file -> pinned staging -> device -> gray plane, on the decoder's stream
             else:
                 data = host_loader(frames[c]) if host_loader is not None else frames[c]
             return data
 
-        upcoming = fetch(counters[0])
-        for counter in counters:
-            cur = trk.prepare(upcoming)
-            if prev is not None and trk.n > 0:
-                trk.track(prev, cur)
-            # the next frame is fetched now: a GPU decode (side stream, one host wait) overlaps this frame's kernels
-            upcoming = fetch(counter + 1) if counter < counters[-1] else None
-            if (counter - g0 * T) % T == 0:
-                if seed_idx is not None:
-                    tracks, quality = trk.harvest()
-                    path = None
-                    ok = True
-                    if check_time and loader is not None:
-                        ok = group_time_ok(frames[counter - T: counter + 1], track_len_sec)
-                    if ok and save and loader is not None:
-                        path = npz_name(frames[seed_idx], T, track_len_sec)
-                        np.savez(path, tracks=tracks, trackquality=quality)
-                    if ok:
-                        results.append((start + seed_idx, path, tracks, quality))
-                        if on_group is not None:
-                            on_group(start + seed_idx, tracks, quality)
-                if counter < g1 * T:
-                    trk.seed(cur, mask, T)
-                    seed_idx = counter
-            prev = cur
-        if pool is not None:
-            pool.shutdown(wait=False)
+        # ---- pipelined loop.  Side stream: gray + pyramid of frame c+1 (and goodFeaturesToTrack if it seeds a group) are
+        # issued BEFORE the LK launch of frame c on the main stream, so they fill the SMs that a persistent LK launch leaves
+        # idle while its last warps finish.  Four pyramid slots: slot (c+1) % 4 was last read by the LK launch of frame c-2.
+        # A finished group is compacted and copied to pinned host memory asynchronously and finalised (np.savez, callbacks)
+        # one group later.  The order of all arithmetic is that of the reference loop.
+        NSLOT = 4
+        main = torch.cuda.current_stream()
+        side = trk.side
+        slots = getattr(trk, "_slots", None)
+        if slots is None:
+            slots = trk._slots = [None] * NSLOT
+        lk_done = [None] * NSLOT
+        side.wait_stream(main)
+
+        def is_seed(c):
+            return (c - g0 * T) % T == 0 and c < g1 * T
+
+        def prepare_ahead(c):
+            data = fetch(c)
+            k = c % NSLOT
+            with torch.cuda.stream(side):
+                if lk_done[k] is not None:
+                    side.wait_event(lk_done[k])
+                reuse = slots[k]
+                pyr = None
+                if reuse is not None:
+                    try:
+                        pyr = trk.prepare(data, reuse=reuse)
+                    except cv.error:                      # frame size changed: build a fresh pyramid
+                        pyr = None
+                if pyr is None:
+                    pyr = trk.prepare(data)
+                slots[k] = pyr
+                pyr.levels[0].record_stream(main)         # (a decoder-owned gray plane is read by the LK launches on `main`)
+                pf = trk.gftt_prefetch(pyr, mask) if is_seed(c) else None
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return pyr, ev, pf
+
+        pending = []                                      # (seed_idx, ok, path, harvest handle) of groups not finalised yet
+
+        def finalize_oldest():
+            sidx, ok, path, handle = pending.pop(0)
+            tracks, quality = trk.finalize(handle)
+            if ok and path is not None:
+                np.savez(path, tracks=tracks, trackquality=quality)
+            if ok:
+                results.append((start + sidx, path, tracks, quality))
+                if on_group is not None:
+                    on_group(start + sidx, tracks, quality)
+
+        try:
+            ahead = prepare_ahead(counters[0])
+            for counter in counters:
+                cur, ev_cur, pf_cur = ahead
+                # the next frame is fetched and prepared now: a GPU decode / upload / pyramid build overlaps this frame's kernels
+                ahead = prepare_ahead(counter + 1) if counter < counters[-1] else None
+                main.wait_event(ev_cur)
+                if prev is not None and trk.n > 0:
+                    trk.track(prev, cur)
+                if prev is not None:
+                    e = torch.cuda.Event()
+                    e.record(main)
+                    lk_done[(counter - 1) % NSLOT] = e        # frame counter-1 has been read for the last time
+                if (counter - g0 * T) % T == 0:
+                    if seed_idx is not None:
+                        ok = True
+                        if check_time and loader is not None:
+                            ok = group_time_ok(frames[counter - T: counter + 1], track_len_sec)
+                        path = npz_name(frames[seed_idx], T, track_len_sec) if (ok and save and loader is not None) else None
+                        pending.append((seed_idx, ok, path, trk.harvest_async()))
+                        if len(pending) > 1:
+                            finalize_oldest()
+                    if counter < g1 * T:
+                        trk.seed(cur, mask, T, prefetched=pf_cur)
+                        seed_idx = counter
+                prev = cur
+            while pending:
+                finalize_oldest()
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=False)
+            main.wait_stream(side)
     return results
 
 

@@ -144,6 +144,10 @@ int ibt_gftt_async(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int6
 int ibt_tracks_compact(const float *tracks_tm, const float *quality_tm, const uint8_t *alive,
                        int N, int T, int32_t *scratch, float *out_tracks, float *out_quality,
                        int *out_count, void *stream);
+/* Same launches, nothing read back: the survivor count stays in scratch[N] (device) -- the frame loop copies it to pinned host
+ * memory together with the arrays and finalises the group one group later, while the next group's kernels run. */
+int ibt_tracks_compact_async(const float *tracks_tm, const float *quality_tm, const uint8_t *alive,
+                             int N, int T, int32_t *scratch, float *out_tracks, float *out_quality, void *stream);
 
 /* ---- K4: Camera.photocords_cropped_to_uncropped + Camera.photo_to_utm
  *      imports/camtools.py:414-421, 286-332, called per vertex at s2_cam_to_utm.py:247-254.
