@@ -319,18 +319,21 @@ def run_sharded_sequence(dev, rank, world, dist):
     imagelist = list(range(SEQ_FRAMES))
     tracker = trk.SequenceTracker(GFTT, LK)
     kw = dict(loader=lambda t: frames[t], tracker=tracker, save=False, check_time=False, decode_workers=0)
-    # warm-up (allocator, kernels, NCCL channels) on this rank's first group
-    res = trk.track_sequence(imagelist, None, SEQ_T, 60, first_group=g0, n_groups=1, **kw)
-    sh.gather_results(res, SEQ_T, to_host="rank0")
+    # warm-up: the whole job once, untimed (allocator pools, pinned staging buffers, NCCL channels, kernels)
+    dev_res = {}
+    res = trk.track_sequence(imagelist, None, SEQ_T, 60, first_group=g0, n_groups=n, device_results=dev_res, **kw)
+    sh.gather_results(res, SEQ_T, to_host="rank0", device_results=dev_res)
+    del res, dev_res
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = trk.track_sequence(imagelist, None, SEQ_T, 60, first_group=g0, n_groups=n, **kw)
+    dev_res = {}
+    res = trk.track_sequence(imagelist, None, SEQ_T, 60, first_group=g0, n_groups=n, device_results=dev_res, **kw)
     torch.cuda.synchronize()
     t_track = time.perf_counter() - t0
-    allres = sh.gather_results(res, SEQ_T, to_host="rank0")
+    allres = sh.gather_results(res, SEQ_T, to_host="rank0", device_results=dev_res)
     torch.cuda.synchronize()
     t_all = time.perf_counter() - t0
     if dist is not None:

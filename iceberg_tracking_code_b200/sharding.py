@@ -59,23 +59,52 @@ def unpack_results(meta, tracks, quality):
     return out
 
 
-def gather_results(results, track_len, device=None, to_host=True):
+_pinned_cache = {}
+
+
+def _pinned(shape, dtype):
+    """pinned host buffers reused between gathers (cudaHostAlloc of ~100 MB costs tens of ms); one per (trailing shape,
+    dtype), grown when a gather needs more rows"""
+    key = (tuple(shape[1:]), dtype)
+    t = _pinned_cache.get(key)
+    if t is None or t.shape[0] < shape[0]:
+        t = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        _pinned_cache[key] = t
+    return t[:shape[0]]
+
+
+def gather_results(results, track_len, device=None, to_host=True, device_results=None):
     """The single collective of the path: every rank contributes its groups' track arrays; returns, on EVERY rank,
     the list [(seed_index, tracks, trackquality)] of all ranks in time order (all_gather of sizes, then all_gather of
     the padded payloads).  Without an initialised process group this is the identity.
     to_host=False leaves the gathered payloads on the device (the groups are views into one CUDA tensor per array):
     copying 8 ranks' worth of a day (0.6 GB) into fresh host memory costs more than tracking the day.
-    to_host="rank0" is the single-writer mode: rank 0 copies the gathered arrays to the host once (one D2H per array),
-    the other ranks keep device views."""
+    to_host="rank0" is the single-writer mode: rank 0 copies the gathered arrays to (reused, pinned) host memory once, the
+    other ranks keep device views.
+    device_results: {seed_index: (tracks, trackquality) CUDA tensors} as track_sequence(device_results=) leaves them: the
+    payload is then assembled on the device instead of being uploaded from the host arrays again."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return [(int(seed), tracks, quality) for seed, _path, tracks, quality in results]      # one rank: nothing to move
-    meta, tracks, quality = pack_results(results, track_len)
     world = dist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     host = bool(to_host) if to_host != "rank0" else dist.get_rank() == 0
     T = int(track_len)
+    use_dev = device_results is not None and device.type == "cuda"
+    if use_dev:
+        meta = np.zeros((len(results), 2), np.int64)
+        tr, qu = [], []
+        for i, (seed, _path, tracks_h, _q) in enumerate(results):
+            m = 0 if tracks_h.ndim != 3 else tracks_h.shape[0]
+            meta[i] = (seed, m)
+            if m:
+                t_d, q_d = device_results[seed]
+                tr.append(t_d.reshape(m, T + 1, 2)); qu.append(q_d.reshape(m, T))
+        tracks = torch.cat(tr, 0) if tr else torch.zeros((0, T + 1, 2), dtype=torch.float32, device=device)
+        quality = torch.cat(qu, 0) if qu else torch.zeros((0, T), dtype=torch.float32, device=device)
+    else:
+        meta, tracks, quality = pack_results(results, track_len)
     sizes = torch.tensor([meta.shape[0], tracks.shape[0]], dtype=torch.int64, device=device)
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
@@ -83,9 +112,12 @@ def gather_results(results, track_len, device=None, to_host=True):
     gmax, mmax = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
 
     def padded(a, n, dtype):
-        t = torch.zeros((n,) + a.shape[1:], dtype=dtype, device=device)
-        if a.shape[0]:
-            t[:a.shape[0]] = torch.from_numpy(a).to(device, non_blocking=True)
+        t = torch.empty((n,) + tuple(a.shape[1:]), dtype=dtype, device=device)
+        k = a.shape[0]
+        if k:
+            t[:k] = a if isinstance(a, torch.Tensor) else torch.from_numpy(a).to(device, non_blocking=True)
+        if k < n:
+            t[k:].zero_()
         return t
 
     def allg(t, host=True):
@@ -96,10 +128,16 @@ def gather_results(results, track_len, device=None, to_host=True):
         out = torch.empty((world * n,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
         dist.all_gather_into_tensor(out, t)
         if host:
-            out = out.cpu().numpy()
+            if out.is_cuda:
+                h = _pinned(out.shape, out.dtype)
+                h.copy_(out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                out = h.numpy()
+            else:
+                out = out.numpy()
         return [out[r * n:(r + 1) * n] for r in range(world)]
 
-    metas = allg(padded(meta, gmax, torch.int64))
+    metas = allg(padded(meta, gmax, torch.int64), True) if gmax else [np.zeros((0, 2), np.int64)] * world
     trs = allg(padded(tracks, mmax, torch.float32), host) if mmax else [np.zeros((0, T + 1, 2), np.float32)] * world
     qus = allg(padded(quality, mmax, torch.float32), host) if mmax else [np.zeros((0, T), np.float32)] * world
     out = []
@@ -121,7 +159,9 @@ def track_sequence_sharded(imagelist, mask, track_len, track_len_sec, start=0, r
         world = dist.get_world_size() if dist.is_initialized() else 1
     total = n_groups(len(imagelist), track_len, start)
     g0, n = shard_groups(total, rank, world)
-    res = track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(start,), first_group=g0, n_groups=n, **kw) if n else []
+    dev_res = {} if (gather and torch.cuda.is_available() and dist.is_initialized() and dist.get_backend() == "nccl") else None
+    res = track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(start,), first_group=g0, n_groups=n,
+                         device_results=dev_res, **kw) if n else []
     if not gather:
         return [(s, t, q) for s, _p, t, q in res]
-    return gather_results(res, track_len)
+    return gather_results(res, track_len, device_results=dev_res)

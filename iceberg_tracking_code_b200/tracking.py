@@ -308,21 +308,25 @@ class SequenceTracker:
         h_t.copy_(out_t, non_blocking=True); h_q.copy_(out_q, non_blocking=True); h_m.copy_(scratch[n:], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        return ("pending", h_t, h_q, h_m, ev)
+        return ("pending", h_t, h_q, h_m, ev, out_t, out_q)
 
-    def finalize(self, handle):
-        """-> (tracks (M, steps+1, 2) f32, trackquality (M, steps) f32) of a harvest_async() handle (M == 0: two (0,) f64)."""
+    def finalize(self, handle, with_device=False):
+        """-> (tracks (M, steps+1, 2) f32, trackquality (M, steps) f32) of a harvest_async() handle (M == 0: two (0,) f64).
+        with_device=True appends the device-resident copies (tracks, quality) -- or None for an empty group -- which the
+        multi-GPU gather sends without going through the host again."""
         if handle[0] == "done":
-            return handle[1]
-        _tag, h_t, h_q, h_m, ev = handle
+            return handle[1] + ((None,) if with_device else ())
+        _tag, h_t, h_q, h_m, ev, out_t, out_q = handle
         ev.synchronize()
         m = int(h_m[0])
         if m == 0:
             res = (np.zeros((0,), np.float64), np.zeros((0,), np.float64))
+            dev = None
         else:
             res = (h_t[:m].numpy().copy(), h_q[:m].numpy().copy())
+            dev = (out_t[:m], out_q[:m])
         self._unpin(h_t); self._unpin(h_q); self._unpin(h_m)
-        return res
+        return res + ((dev,) if with_device else ())
 
     def alive_count(self):
         return 0 if self.n == 0 else int(self._alive.sum().item())
@@ -346,7 +350,7 @@ def group_time_ok(paths, track_len_sec):
 
 def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), feature_params=None, lk_params=None,
                    save=True, loader=load_image, tracker=None, check_time=True, on_group=None, first_group=0,
-                   n_groups=None, decode_workers=4):
+                   n_groups=None, decode_workers=4, device_results=None):
     """The loop of s1:296-450 over `imagelist` (paths, or in-memory frames when loader is None).
     Returns the list of (seed_index, npz_path_or_None, tracks, trackquality) of every completed group.
 
@@ -356,6 +360,9 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
     loader: callable path -> (H,W,3) u8 RGB host array (default: Pillow, as the reference, s1:310), None for in-memory
     frames, or the string "gpu": the file bytes go to the GPU compressed and csrc/jpeg.cu decodes them (bit-exact with
     Pillow) straight into the gray plane; files it does not handle raise jpeg.Unsupported.
+
+    device_results: a dict; if given, {seed_index: (tracks, trackquality) CUDA tensors} of every non-empty group is left
+    in it (sharding.gather_results sends those instead of re-uploading the host arrays).
 
     decode_workers: a host loader (PIL JPEG decode, ~0.25 s per 24 MP frame, far slower than the GPU step) runs in a
     thread pool that keeps `decode_workers` frames ahead of the tracker; the order of processing is unchanged.  Ignored
@@ -447,7 +454,9 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
 
         def finalize_oldest():
             sidx, ok, path, handle = pending.pop(0)
-            tracks, quality = trk.finalize(handle)
+            tracks, quality, dev = trk.finalize(handle, with_device=True)
+            if ok and device_results is not None and dev is not None:
+                device_results[start + sidx] = dev
             if ok and path is not None:
                 np.savez(path, tracks=tracks, trackquality=quality)
             if ok:
