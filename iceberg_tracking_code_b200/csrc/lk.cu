@@ -210,18 +210,26 @@ __device__ __noinline__ void patch_reflect(uint8_t *patch, int pitch, int x0a, i
 {
     __syncwarp();
     const int pw = pitch >> 2;
-    for (int r = 0; r < nrows; r++) {                           // rows first (whole staged width)
+    const int ntop = min(nrows, max(0, -y0));                     // patch rows above the image
+    const int rbot = max(0, rows - y0);                           // first patch row below the image
+    for (int i = lane; i < (ntop + max(0, nrows - rbot)) * pw; i += 32) {       // rows first (whole staged width)
+        int r = i / pw;
+        const int c = i - r * pw;
+        if (r >= ntop) r = rbot + (r - ntop);
         const int y = y0 + r;
-        if (y >= 0 && y < rows) continue;
         const int rs = (y < 0 ? -y : 2 * (rows - 1) - y) - y0;
-        for (int c = lane; c < pw; c += 32)
-            reinterpret_cast<uint32_t *>(patch + r * pitch)[c] = reinterpret_cast<const uint32_t *>(patch + rs * pitch)[c];
+        reinterpret_cast<uint32_t *>(patch + r * pitch)[c] = reinterpret_cast<const uint32_t *>(patch + rs * pitch)[c];
     }
     __syncwarp();
-    for (int x = nx0; x <= nx1; x++) {                          // then the needed columns outside the image
-        if (x >= 0 && x < cols) { if (x >= 0 && nx1 < cols) break; continue; }
+    const int nleft = min(nx1 - nx0 + 1, max(0, -nx0));           // needed columns left of the image
+    const int xright = max(nx0, cols);                            // first needed column right of the image
+    const int ncol = nleft + max(0, nx1 - xright + 1);
+    for (int i = lane; i < ncol * nrows; i += 32) {               // then the needed columns outside the image
+        int k = i / nrows;
+        const int r = i - k * nrows;
+        const int x = k < nleft ? nx0 + k : xright + (k - nleft);
         const int xs = (x < 0 ? -x : 2 * (cols - 1) - x) - x0a, xd = x - x0a;
-        for (int r = lane; r < nrows; r += 32) patch[r * pitch + xd] = patch[r * pitch + xs];
+        patch[r * pitch + xd] = patch[r * pitch + xs];
     }
     __syncwarp();
 }
@@ -282,10 +290,17 @@ __device__ __forceinline__ void build_template(const LKArgs &a, const uint8_t *i
     int a11[NS], a12[NS], a22[NS], c1[NS], c2[NS];
     uint32_t ipair[NS];
     int d00x[NS], d00y[NS], d01x[NS], d01y[NS];
+    // lanes beyond the window take all-zero weights: Iw = Ix = Iy = 0 there without a per-row select, which is exactly what the
+    // template must hold outside the window
+    uint32_t mtop[NS], mbot[NS];
+    int m00[NS], m01[NS], m10[NS], m11[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         a11[s] = a12[s] = a22[s] = c1[s] = c2[s] = 0;
         ipair[s] = 0; d00x[s] = d00y[s] = d01x[s] = d01y[s] = 0;
+        const bool active = s < nstrips && lane < SC && s * SC + lane < winW;
+        mtop[s] = active ? wtop : 0u; mbot[s] = active ? wbot : 0u;
+        m00[s] = active ? iw00 : 0; m01[s] = active ? iw01 : 0; m10[s] = active ? iw10 : 0; m11[s] = active ? iw11 : 0;
         if (s < nstrips) {
             const uint8_t *ip = ip0 + s * SC + lane;
             const uint32_t *dp = dp0 + s * SC + lane;
@@ -301,20 +316,20 @@ __device__ __forceinline__ void build_template(const LKArgs &a, const uint8_t *i
         for (int s = 0; s < NS; s++) {
             if (s < nstrips) {
                 const int col = s * SC + lane;
-                const bool active = lane < SC && col < winW;
                 const uint8_t *ip = ip0 + (r + 1) * IP + col;
                 const uint32_t *dp = dp0 + (r + 1) * DP + col;
                 const uint32_t cpair = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
                 const uint32_t dc = dp[0], dcr = dp[1];
                 const int d10x = (int)(short)(dc & 0xffffu), d10y = (int)dc >> 16;
                 const int d11x = (int)(short)(dcr & 0xffffu), d11y = (int)dcr >> 16;
-                uint32_t v = dp2a_lo(wtop, ipair[s], 256u);
-                v = dp2a_lo(wbot, cpair, v);                           // v = taps + 256; Iw = v >> 9
+                uint32_t v = dp2a_lo(mtop[s], ipair[s], 256u);
+                v = dp2a_lo(mbot[s], cpair, v);                        // v = taps + 256; Iw = v >> 9
                 const int Iw = (int)(v >> 9);
-                int Ix = (d00x[s] * iw00 + d01x[s] * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
-                int Iy = (d00y[s] * iw00 + d01y[s] * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
-                if (!active) { Ix = 0; Iy = 0; }                       // template columns beyond the window hold zeros
-                if (lane < SC && col < TC) tmpl[r * TC + col] = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
+                const int Ix = (d00x[s] * m00[s] + d01x[s] * m01[s] + d10x * m10[s] + d11x * m11[s] + 8192) >> 14;
+                const int Iy = (d00y[s] * m00[s] + d01y[s] * m01[s] + d10y * m10[s] + d11y * m11[s] + 8192) >> 14;
+                // (compile-time window sizes fold these guards away where every lane owns a template column)
+                if ((SC >= 32 || lane < SC) && (NS * SC <= TC || col < TC))
+                    tmpl[r * TC + col] = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
                 a11[s] += Ix * Ix; a12[s] += Ix * Iy; a22[s] += Iy * Iy;
                 c1[s] += Iw * Ix; c2[s] += Iw * Iy;
                 ipair[s] = cpair; d00x[s] = d10x; d00y[s] = d10y; d01x[s] = d11x; d01y[s] = d11y;
