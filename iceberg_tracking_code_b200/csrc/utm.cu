@@ -31,7 +31,8 @@ photo_to_utm_kernel(const float2 *__restrict__ xy, int64_t n, const __grid_const
 
 // s2_cam_to_utm.py:243-343 for one track per thread: project every vertex (fp64), segment velocities u, v (m/s) and speed,
 // then the three plausibility criteria.  Python's max() over a list is restated literally (m = first; if x > m: m = x),
-// which also reproduces its NaN behaviour (0/0 speeds ratios of motionless tracks).
+// which also reproduces its NaN behaviour (0/0 speeds ratios of motionless tracks).  One divergence, documented: for T == 1
+// with max speed above speed_threshold the reference raises (max() of the empty ratio list, s2:337); here the track is kept.
 struct VelArgs {
     UtmCam cam;
     const float2 *tracks; int M, T;
@@ -48,6 +49,35 @@ __device__ __forceinline__ double2 project(const UtmCam &c, float2 p)
                         c.Hc * (c.sX1 + xi * c.U1 + yi * c.V1) / den + c.N0);
 }
 
+// np.mean(speedsublist) (s2:310) sums with numpy's pairwise scheme (loops_utils.h.src @TYPE@_pairwise_sum): sequential below 8
+// elements, 8 accumulators up to 128, recursive halving above.  A borderline mean < min_speed decision follows numpy's bits.
+__device__ double np_sum_block(const double *v, int n)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; i++) res = res + v[i];
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = v[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = r[j] + v[i + j];
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res = res + v[i];
+    return res;
+}
+__device__ double np_sum(const double *v, int n)
+{
+    if (n <= 128) return np_sum_block(v, n);
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_sum(v, n2) + np_sum(v + n2, n - n2);      // depth log2(n / 128): a track has at most a few hundred vertices
+}
+
 __global__ void __launch_bounds__(128)
 track_velocities_kernel(const __grid_constant__ VelArgs a)
 {
@@ -60,7 +90,7 @@ track_velocities_kernel(const __grid_constant__ VelArgs a)
     double *sp = a.speed + (int64_t)m * T;
     double2 prev = project(a.cam, tr[0]);
     en[0] = prev;
-    double ssum = 0.0, smax = 0.0;
+    double smax = 0.0;
     for (int i = 1; i <= T; i++) {
         const double2 cur = project(a.cam, tr[i]);
         en[i] = cur;
@@ -68,12 +98,11 @@ track_velocities_kernel(const __grid_constant__ VelArgs a)
         const double s = hypot(u, v);                                                           // s2:286
         uv[i - 1] = make_double2(u, v);
         sp[i - 1] = s;
-        ssum += s;
         if (i == 1 || s > smax) smax = s;
         prev = cur;
     }
     bool keep = true;
-    if ((ssum / (double)T < a.min_speed) || (smax > a.max_speed)) keep = false;                // criterion 1, s2:310
+    if ((np_sum(sp, T) / (double)T < a.min_speed) || (smax > a.max_speed)) keep = false;       // criterion 1, s2:310
     if (keep && smax > a.speed_threshold && T >= 2) {                                           // s2:314
         double rmax = 0.0, amax = 0.0;
         for (int c1 = 0; c1 + 1 < T; c1++) {
@@ -129,7 +158,7 @@ IBT_API int ibt_track_velocities(const float *tracks, int M, int T, const double
                                  double *EN, double *uv, double *speed, uint8_t *keep, void *stream)
 {
     using namespace ibt;
-    if (M < 0 || T < 1 || T > 64 || !cam || !(interval_s > 0)) return IBT_E_INVALID;
+    if (M < 0 || T < 1 || !cam || !(interval_s > 0)) return IBT_E_INVALID;
     if (M == 0) return IBT_OK;
     if (!tracks || !EN || !uv || !speed || !keep || reinterpret_cast<uintptr_t>(tracks) % 8 != 0 ||
         reinterpret_cast<uintptr_t>(EN) % 16 != 0 || reinterpret_cast<uintptr_t>(uv) % 16 != 0)

@@ -362,17 +362,20 @@ def cornerMinEigenVal(src, blockSize, ksize=3):
 
 
 _gftt_ws = {}
+_gftt_lock = __import__("threading").Lock()
 
 
 def _gftt_workspace(dev, H, W):
-    key = (dev.index, H, W)
-    ws = _gftt_ws.get(key)
-    if ws is None:
-        _gftt_ws.clear()                     # one frame size at a time: do not hoard HBM
-        nbytes = N.lib().ibt_gftt_workspace_bytes(H, W)
-        cap = H * W // 4 + 4096
-        ws = (torch.empty((nbytes,), dtype=torch.uint8, device=dev), torch.empty((cap, 2), dtype=torch.float32, device=dev))
-        _gftt_ws[key] = ws
+    """One workspace per device for the cv2-style call, regrown when a larger frame arrives (a SequenceTracker keeps its own:
+    tracking.SequenceTracker.gftt_prefetch).  Calls from several host threads on one device must not overlap on a workspace:
+    the lock covers the lookup, callers serialise on the stream like any cv2 call."""
+    nbytes = N.lib().ibt_gftt_workspace_bytes(H, W)
+    cap = H * W // 4 + 4096
+    with _gftt_lock:
+        ws = _gftt_ws.get(dev.index)
+        if ws is None or ws[0].numel() < nbytes or ws[1].shape[0] < cap:
+            ws = (torch.empty((nbytes,), dtype=torch.uint8, device=dev), torch.empty((cap, 2), dtype=torch.float32, device=dev))
+            _gftt_ws[dev.index] = ws
     return ws
 
 

@@ -81,6 +81,36 @@ class GpuJpegLoader:
         return gray, ev
 
 
+class ViewLoader:
+    """lucaskanade_tracking(crop="view"): source file -> cropped gray plane decoded on the GPU.  Files the GPU decoder must not
+    or cannot take -- a scan that ends early (no EOI marker), a crop box that leaves the frame (PIL pads with zeros), a
+    progressive / CMYK / 12-bit file -- are read with Pillow exactly as camtools.crop_image_standalone reads them (truncated
+    scans logged to logfile_image_cropping.log, re-read with LOAD_TRUNCATED_IMAGES, announced) and uploaded as pixels."""
+
+    def __init__(self, gpu_loader, crop_box, sources):
+        self.gpu = gpu_loader
+        self.box = tuple(int(v) for v in crop_box)
+        self.sources = sources                            # {name in ws_target: source path}
+        self.fallbacks = 0
+
+    def __call__(self, name):
+        from . import jpeg as _jpeg
+        path = self.sources[name]
+        data = read_file(path)
+        ok = False
+        try:
+            info = _jpeg.parse(data)
+            l, u, r, b = self.box
+            ok = data.rstrip(b'\x00')[-2:] == b'\xff\xd9' and 0 <= l < r <= info.width and 0 <= u < b <= info.height
+        except (_jpeg.Unsupported, RuntimeError):
+            ok = False
+        if ok:
+            return self.gpu.decode(data)
+        from ._crop import open_cropped
+        self.fallbacks += 1
+        return np.array(open_cropped(path, name, self.box).convert("RGB"))
+
+
 class FrameStager:
     """Pinned double buffer + copy stream: the host->device copy of frame t+1 overlaps the kernels of frame t."""
 
@@ -260,6 +290,9 @@ class SequenceTracker:
         cnt, eps = cv._criteria(self.lk_params["criteria"])
         w = self.lk_params["winSize"]
         p = cv._ptr
+        if torch.cuda.current_device() != self.device.index:
+            raise RuntimeError("SequenceTracker was created for %s but cuda:%d is current (wrap the loop in torch.cuda.device)"
+                               % (self.device, torch.cuda.current_device()))
         N.check(N.lib().ibt_lk_fb(C.byref(prev_pyr.c), C.byref(cur_pyr.c), p(self._tracks[t]), self.n, int(w[0]), int(w[1]),
                                   cnt, eps, float(self.lk_params.get("minEigThreshold", 1e-4)), self.fb_threshold,
                                   p(self._tracks[t + 1]), None, None, None, None, None, p(self._quality[t]),
@@ -503,7 +536,8 @@ def lucaskanade_tracking(file_path, ws_source, ws_target, camname, track_len, tr
                          plot_switch, movie_switch, delete_jpgs_switch, paramfile_path, n_proc, camera=None, crop="reencode"):
     """Same positional signature as s1_lucaskanade_tracking.py:234-236; side effect = the .npz files of SURVEY A.8.
     `camera` (keyword, optional) injects a ready camera.Camera instead of reading `paramfile_path`.
-    plot_switch / movie_switch / delete_jpgs_switch are accepted and ignored (matplotlib / mencoder work, out of scope).
+    plot_switch / movie_switch are accepted and ignored (matplotlib / mencoder work, out of scope); delete_jpgs_switch == 1
+    removes the cropped copies after tracking like the reference (s1:475-479).
 
     crop="reencode" (default) is the reference: every source frame is decoded, cropped and re-saved as a JPEG by Pillow
     (camtools.py:237-258, ~0.3 s of host time per 24 MP frame) and the tracker reads those files -- the lossy re-encode is
@@ -532,8 +566,8 @@ def lucaskanade_tracking(file_path, ws_source, ws_target, camname, track_len, tr
         sources = {osp.join(ws_target, osp.basename(p)): p for p in imagelist}
         gpu = GpuJpegLoader(tracker.device, crop_box=(l, u, r, b))
         track_sequence(sorted(sources), mask, track_len, track_len_sec, startlist, tracker=tracker,
-                       loader=lambda name: gpu(sources[name]), decode_workers=0)
-        return
+                       loader=ViewLoader(gpu, (l, u, r, b), sources), decode_workers=0)
+        return                                                         # (no cropped copies were written: nothing to delete)
     if crop != "reencode":
         raise ValueError("crop must be 'reencode' or 'view'")
     cam.crop_image_parallel(imagelist, ws_target, n_proc)              # s1:272
@@ -546,6 +580,9 @@ def lucaskanade_tracking(file_path, ws_source, ws_target, camname, track_len, tr
         mask = np.full((h, w), 255, np.uint8)
     # the cropping step above re-saved every frame with Pillow (baseline JPEG): the GPU decoder handles all of them
     track_sequence(imagelist, mask, track_len, track_len_sec, startlist, loader="gpu")
+    if delete_jpgs_switch == 1:                                        # s1:475-479: delete the cropped .jpgs to open up space
+        for img in imagelist:
+            os.remove(img)
 
 
 class LucasKanade:

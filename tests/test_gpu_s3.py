@@ -93,3 +93,27 @@ def test_grid_bin_vs_oracle(grd, oracle, n, spacing):
     for (i, j), (c, a, b) in zip(idx, ref):
         q = i * rows + j
         assert cnt[q] == c and su[q] == a and sv[q] == b, (i, j, cnt[q], c, su[q], a)
+
+
+def test_polygon_rule_gpu(ibt):
+    """mask.cu (per pixel) and grid.cu (per point) against the literal transcription of matplotlib's point_in_path_impl on the
+    degenerate cases of tests/test_polygon_rule.py: points on edges, vertices, edge extensions, collinear / repeated vertices,
+    a concave vertex on the scan line.  (Parity against matplotlib itself is unpinned: it is not installable here.)"""
+    import ctypes as C
+    import torch
+    from iceberg_tracking_code_b200 import _native as N, cv, gridding
+    from test_polygon_rule import CASES, COLLINEAR, NOTCH, RECT, crossings_literal
+    for poly, pt, want in CASES:
+        assert bool(gridding.points_in_polygon(np.asarray(poly), np.asarray([pt]))[0]) == want, (poly, pt)
+    for poly in (RECT, NOTCH, COLLINEAR, [(1.0, 1.0), (7.0, 2.0), (5.0, 6.0), (4.0, 3.0), (2.0, 6.0)]):
+        xs, ys = np.meshgrid(np.arange(-2, 9, 0.5), np.arange(-2, 7, 0.5))
+        pts = np.stack([xs.ravel(), ys.ravel()], 1)
+        ref = np.array([crossings_literal(poly, x, y) for x, y in pts])
+        assert np.array_equal(gridding.points_in_polygon(np.asarray(poly), pts).astype(bool), ref)
+        # the mask kernel tests pixel (x, y) = integer coordinates against the polygon in pixel units
+        h, w = 8, 10
+        pd_ = torch.tensor(np.asarray(poly, np.float64), device="cuda")
+        out = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+        N.check(N.lib().ibt_polygon_mask(cv._ptr(pd_), len(poly), h, w, cv._ptr(out), w, 255, cv._stream()), "ibt_polygon_mask")
+        refm = np.array([[255 if crossings_literal(poly, float(x), float(y)) else 0 for x in range(w)] for y in range(h)], np.uint8)
+        assert np.array_equal(out.cpu().numpy(), refm), poly

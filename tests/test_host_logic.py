@@ -152,3 +152,38 @@ def test_crop_image_parallel_matches_pillow(tmp_path):
         ref = tmp_path / ("ref_" + n)
         Image.open(src / n).crop((16, 10, w - 8, h - 20)).save(ref)          # crop_image_standalone, camtools.py:76-80
         assert (tgt / n).read_bytes() == ref.read_bytes()
+
+
+def test_view_loader_fallbacks(tmp_path, capsys, caplog):
+    """crop="view" host logic: a sound baseline JPEG goes to the GPU decoder; a truncated scan, a crop box that leaves the frame
+    and a progressive file are read with Pillow the way camtools.crop_image_standalone reads them (log entry + TRUNCATED)."""
+    import io
+    from PIL import Image
+    from iceberg_tracking_code_b200.tracking import ViewLoader
+
+    class StubGpu:                                       # stands in for GpuJpegLoader (no GPU in this test)
+        def decode(self, data):
+            return "gpu"
+    rng = np.random.default_rng(0)
+    img = Image.fromarray(rng.integers(0, 255, (64, 96, 3), dtype=np.uint8))
+    tgt = tmp_path / "cam1" / "oblique" / "20190724"
+    tgt.mkdir(parents=True)
+    good = tmp_path / "good.jpg"; img.save(good)
+    bio = io.BytesIO(); img.save(bio, "JPEG")
+    trunc = tmp_path / "trunc.jpg"; trunc.write_bytes(bio.getvalue()[: len(bio.getvalue()) * 2 // 3])
+    prog = tmp_path / "prog.jpg"; img.save(prog, progressive=True)
+    names = {str(tgt / "good.jpg"): str(good), str(tgt / "trunc.jpg"): str(trunc), str(tgt / "prog.jpg"): str(prog)}
+    vl = ViewLoader(StubGpu(), (8, 4, 88, 60), names)
+    assert vl(str(tgt / "good.jpg")) == "gpu" and vl.fallbacks == 0
+    import logging
+    with caplog.at_level(logging.INFO):
+        a = vl(str(tgt / "trunc.jpg"))
+    assert isinstance(a, np.ndarray) and a.shape == (56, 80, 3) and vl.fallbacks == 1
+    assert "TRUNCATED" in capsys.readouterr().out
+    # the reference's log entry (camtools.py:84-92; logging.basicConfig is a no-op under pytest's own handlers, the records are not)
+    assert any(str(trunc) in r.getMessage() for r in caplog.records)
+    p = vl(str(tgt / "prog.jpg"))
+    assert isinstance(p, np.ndarray) and p.shape == (56, 80, 3)
+    assert np.array_equal(p, np.array(Image.open(prog).crop((8, 4, 88, 60))))
+    big = ViewLoader(StubGpu(), (8, 4, 120, 60), names)(str(tgt / "good.jpg"))         # box wider than the 96 px frame
+    assert isinstance(big, np.ndarray) and big.shape == (56, 112, 3) and not big[:, 96 - 8:].any()   # PIL pads with zeros
