@@ -247,7 +247,10 @@ def timed_steps(pipe, frames, pts, first, n, iter_total=None, probes=None):
 def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
     """Same step, but the new frame arrives as the JPEG FILE the reference opens with Pillow (s1:310): the bytes are
     copied host->device compressed and csrc/jpeg.cu decodes them straight to the gray plane (bit-exact with Pillow +
-    cv2.cvtColor).  The CPU figure beside it is the reference's np.array(Image.open(f)) on the same bytes."""
+    cv2.cvtColor).  The decodes of frames i+2 and i+3 (two decoders, two high-priority streams, no host wait: decode_async,
+    convergence confirmed before the frame is used) run BESIDE the LK launch of pair i, which is capped at two of its three
+    CTAs per SM (cv.set_lk_resident_ctas(2)); p1 / FB distance of every step are read back to the host and consumed one
+    step later.  The CPU figure beside it is the reference's np.array(Image.open(f)) on the same bytes."""
     import io
     import torch
     from PIL import Image
@@ -261,29 +264,74 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
     g = dec.decode(blobs[0], rgb=False, gray=True)[1]
     ref = cv.cvtColor(torch.from_numpy(np.array(Image.open(io.BytesIO(blobs[0])))).to(dev))
     exact = bool(torch.equal(g, ref))
-    h_p1 = torch.empty((NPTS, 2), dtype=torch.float32).pin_memory()
-    h_fbd = torch.empty((NPTS,), dtype=torch.float32).pin_memory()
-    pyr = pipe.pyr
-    p1, fbd = pipe.p1[0], pipe.fbd[0]
+    h_p1 = [torch.empty((NPTS, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_fbd = [torch.empty((NPTS,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    NS = 4
+    pyr = list(pipe.pyr) + [trk.prepare(g)]                   # four pyramid slots: two frames are being decoded ahead
+    main = torch.cuda.current_stream()
+    # two decoders on two high-priority streams: a decode is a chain of small latency-bound kernels, two in flight overlap
+    decs = [dec, jpeg.JpegDecoder(dev)]
+    decs[1].decode(blobs[1], rgb=False, gray=True)
+    dstream = [torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev, priority=-1)]
+    lk_done = [None] * NS
+    redone = [0]
 
-    def loop(n, first):
-        for k in range(n):
-            i = first + k
-            slot = (i + 1) & 1
-            gray = dec.decode(blobs[pingpong(i + 1)], rgb=False, gray=True)[1]
-            cur = trk.prepare(gray, reuse=pyr[slot])
-            cv.lk_fb_into(pyr[slot ^ 1], cur, pts[pingpong(i)], LK, p1, fbd, None, None)
-            h_p1.copy_(p1, non_blocking=True); h_fbd.copy_(fbd, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-    g0 = dec.decode(blobs[pingpong(0)], rgb=False, gray=True)[1]
-    pyr[0].rebuild(g0)
-    loop(6, 0)
-    pyr[0].rebuild(g0)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    loop(steps, 0)
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) * 1e3 / steps
+    def stage(j):
+        """decode frame j (asynchronously: no host wait) -> gray -> pyramid into pyr[j % NS]; returns (handle, ready event)"""
+        d = j & 1
+        with torch.cuda.stream(dstream[d]):
+            if lk_done[j % NS] is not None:
+                dstream[d].wait_event(lk_done[j % NS])
+            h = decs[d].decode_async(blobs[pingpong(j)], rgb=False, gray=True)
+            trk.prepare(h["gray"], reuse=pyr[j % NS])
+            ev = torch.cuda.Event()
+            ev.record(dstream[d])
+        return h, ev
+
+    def confirm(j, st):
+        """the Huffman pass of frame j had converged (else: decoded again, pyramid rebuilt)"""
+        h, _ev = st
+        if h["flags"] is None:
+            return
+        before = decs[j & 1].last_rounds
+        decs[j & 1].confirm(h)
+        if decs[j & 1].last_rounds == 0 or (before and decs[j & 1].last_rounds > h["rounds"]):
+            redone[0] += 1
+        if h.get("redo"):
+            trk.prepare(h["gray"], reuse=pyr[j % NS])
+
+    def loop(n):
+        acc = 0.0
+        st = {0: stage(0), 1: stage(1), 2: stage(2)}
+        for i in range(n):
+            k = i & 1
+            if i == 0:
+                confirm(0, st[0])
+            confirm(i + 1, st[i + 1])
+            main.wait_event(st.pop(i)[1]); main.wait_event(st[i + 1][1])
+            cv.lk_fb_into(pyr[i % NS], pyr[(i + 1) % NS], pts[pingpong(i)], LK, pipe.p1[k], pipe.fbd[k], None, None)
+            e = torch.cuda.Event(); e.record(main)
+            lk_done[i % NS] = e                               # pyr[i % NS] may be rebuilt once this launch has finished
+            h_p1[k].copy_(pipe.p1[k], non_blocking=True); h_fbd[k].copy_(pipe.fbd[k], non_blocking=True)
+            done[k].record(main)
+            if i + 3 <= n:
+                st[i + 3] = stage(i + 3)                      # decoded beside the LK launches of pairs i and i+1
+            if i >= 1:
+                done[k ^ 1].synchronize()
+                acc += float(h_fbd[k ^ 1][0])
+        done[(n - 1) & 1].synchronize()
+        return acc + float(h_fbd[(n - 1) & 1][0])
+    cv.set_lk_resident_ctas(2)
+    try:
+        loop(8)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loop(steps)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+    finally:
+        cv.set_lk_resident_ctas(0)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(10):
@@ -294,11 +342,12 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
         np.array(Image.open(io.BytesIO(blobs[k])))
     pil_ms = (time.perf_counter() - t0) * 1e3 / 3
     return {"value": NPTS / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "steps": steps,
-            "h2d_bytes_per_step": int(np.mean([len(b) for b in blobs])), "d2h_bytes_per_step": int(h_p1.numel() * 4 + h_fbd.numel() * 4),
+            "h2d_bytes_per_step": int(np.mean([len(b) for b in blobs])), "d2h_bytes_per_step": int(h_p1[0].numel() * 4 + h_fbd[0].numel() * 4),
             "jpeg_decode_ms": e0.elapsed_time(e1) / 10, "huffman_sync_rounds": dec.last_rounds,
-            "pillow_decode_ms_1_core": pil_ms, "bit_exact_vs_pillow_cvtcolor": exact,
-            "api": "jpeg.JpegDecoder.decode(gray) + SequenceTracker.prepare + fused LK, JPEG bytes in host memory, "
-                   "p1 + FB distance read back every step"}
+            "pillow_decode_ms_1_core": pil_ms, "bit_exact_vs_pillow_cvtcolor": exact, "decodes_repeated": redone[0],
+            "api": "jpeg.JpegDecoder.decode_async(gray) on two streams + SequenceTracker.prepare + fused LK (2 of 3 CTAs per SM), "
+                   "JPEG bytes in host memory, the next two frames decode beside the LK launches, p1 + FB distance read back "
+                   "every step; wall clock"}
 
 
 def run_sharded_sequence(dev, rank, world, dist):
@@ -444,6 +493,8 @@ def main():
 
     from iceberg_tracking_code_b200 import build
     build.build()
+    from iceberg_tracking_code_b200 import _native
+    numa_node = _native.bind_to_gpu_numa_node(local_rank) if os.environ.get("IBT_NO_NUMA_BIND") is None else None
     from iceberg_tracking_code_b200 import cv
     from iceberg_tracking_code_b200.tracking import SequenceTracker
 
@@ -644,6 +695,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 2x2 solve", "data": "synthetic",
         "config": CONFIG,
         "inner_repeats": repeats, "timed_steps": nsteps, "timed_region_ms": ms,
+        "numa_node_rank0": numa_node,
         "pipelining": "none (one stream)" if args.no_pipeline else "consecutive (independent) frame pairs overlap on two CUDA streams, three pyramid slots",
         "frame_pairs_per_s": world * nsteps / (ms * 1e-3),
         "feature_pair_iterations_per_s": iters / (ms * 1e-3),

@@ -75,6 +75,9 @@ SIGNATURES = {
     "ibt_jpeg_parse": (_i, [_vp, _i64, _JPG]),
     "ibt_jpeg_workspace_bytes": (_i64, [_JPG]),
     "ibt_jpeg_decode": (_i, [_vp, _JPG, _vp, _i64, _vp, _i64, _vp, _i64, _i, C.POINTER(C.c_int), _vp]),
+    "ibt_jpeg_async_host_bytes": (_i64, []),
+    "ibt_jpeg_decode_async": (_i, [_vp, _JPG, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _vp]),
+    "ibt_lk_set_max_ctas_per_sm": (_i, [_i]),
 }
 
 _lib = None
@@ -108,3 +111,31 @@ def check(rc, where):
     if rc != IBT_OK:
         detail = lib().ibt_last_cuda_error().decode() if rc == IBT_E_CUDA else ""
         raise IbtError(rc, where, detail)
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (and so the pages it touches first: pinned staging buffers) to the CPUs of the NUMA node the GPU hangs
+    off.  With one process per GPU, frames that travel host -> device every step otherwise all stream out of whichever node
+    the ranks happened to start on, and 4-8 ranks saturate that node's memory / inter-socket link (round 1: host-fed throughput
+    stopped scaling at 4 GPUs).  Returns the node, or None when the topology cannot be read (then nothing is changed)."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:                                   # noqa: BLE001  (no sysfs / no permission: leave the placement alone)
+        return None

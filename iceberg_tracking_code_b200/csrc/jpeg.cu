@@ -869,8 +869,13 @@ IBT_API int64_t ibt_jpeg_workspace_bytes(const ibt_jpeg_info_t *I)
     return (int64_t)L.total;
 }
 
-IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, void *d_ws, int64_t ws_bytes, uint8_t *d_rgb,
-                            int64_t rgb_pitch, uint8_t *d_gray, int64_t gray_pitch, int coeffset, int *out_rounds, void *stream)
+// Shared body of ibt_jpeg_decode / ibt_jpeg_decode_async.  fixed_rounds == 0: synchronous form (rounds in batches, the host
+// reads the change counters after each batch and stops at the fixed point).  fixed_rounds > 0: exactly that many rounds are
+// enqueued (a round after the fixed point changes nothing and costs a few microseconds), the change counters travel to
+// h_pinned[0 .. fixed_rounds) and the function returns without waiting: the caller checks them later.
+static int jpeg_decode_impl(const uint8_t *d_file, const ibt_jpeg_info_t *I, void *d_ws, int64_t ws_bytes, uint8_t *d_rgb,
+                            int64_t rgb_pitch, uint8_t *d_gray, int64_t gray_pitch, int coeffset, int *out_rounds,
+                            int fixed_rounds, uint8_t *h_pinned, void *stream)
 {
     using namespace ibt;
     int rc = jpeg_validate(I);
@@ -880,13 +885,18 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     if (d_gray && gray_pitch < I->width) return IBT_E_INVALID;
     if (coeffset != IBT_GRAY_CV4_15BIT && coeffset != IBT_GRAY_CV3_14BIT) return IBT_E_INVALID;
     if (reinterpret_cast<uintptr_t>(d_ws) % 256 != 0) return IBT_E_INVALID;
+    if (fixed_rounds < 0 || fixed_rounds > JPG_MAX_ROUNDS_BATCH) return IBT_E_INVALID;
     static thread_local JpgLayout L;                        // ~1 KB of geometry, reused as a kernel parameter below
     jpeg_layout(I, L);
     if ((size_t)ws_bytes < L.total) return IBT_E_WORKSPACE;
-    // pinned per-thread staging: [0, 256) round counters read back, then the Huffman tables on their way to the device.
-    // The function synchronises the stream before it returns, so the staging is free again at the next call.
-    static thread_local uint8_t *h_pinned = nullptr;
-    if (!h_pinned) IBT_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_pinned), 256 + sizeof(JpgTables), cudaHostAllocDefault));
+    // pinned staging: [0, 256) round counters read back, then the Huffman tables on their way to the device.  The synchronous
+    // form owns a per-thread buffer (it synchronises the stream before it returns, so the staging is free again at the next
+    // call); the asynchronous form uses the caller's (free again when the caller has seen the stream pass this decode).
+    if (!h_pinned) {
+        static thread_local uint8_t *h_own = nullptr;
+        if (!h_own) IBT_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_own), 256 + sizeof(JpgTables), cudaHostAllocDefault));
+        h_pinned = h_own;
+    }
     uint32_t *h_flag = reinterpret_cast<uint32_t *>(h_pinned);
     JpgTables &T = *reinterpret_cast<JpgTables *>(h_pinned + 256);
     rc = build_tables(I, L.G, T);
@@ -930,25 +940,34 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
         jpg_sync_init<<<(L.nsub + 255) / 256, 256, 0, st>>>(start, dirty, L.nsub, L.sbits);
     }
     const int sync_ctas = (L.nsub + 127) / 128;
-    // first batch: the caller's hint (rounds the previous, similar file needed) + 2, else 8
-    int round = 0, batch = 8, rounds_used = -1;
-    if (out_rounds && *out_rounds > 0) batch = *out_rounds + 2 > JPG_MAX_ROUNDS_BATCH ? JPG_MAX_ROUNDS_BATCH : *out_rounds + 2;
-    while (rounds_used < 0) {
+    if (fixed_rounds > 0) {
         IBT_CUDA_TRY(cudaMemsetAsync(changed, 0, JPG_MAX_ROUNDS_BATCH * 4, st));
-        for (int r = 0; r < batch; r++)
-            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, qstart, dirty, nblk, L.nsub, round + r, changed + r, rst, L.sbits);
-        IBT_CUDA_TRY(cudaMemcpyAsync(h_flag, changed, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
-        IBT_CUDA_TRY(cudaStreamSynchronize(st));
-        for (int r = 0; r < batch; r++)
-            if (h_flag[r] == 0) { rounds_used = round + r + 1; break; }     // a round without changes: fixed point reached
-        round += batch;
-        if (round > L.nsub + 8) break;                                     // cannot happen: one subsequence settles per round
-        batch = batch * 2 > JPG_MAX_ROUNDS_BATCH ? JPG_MAX_ROUNDS_BATCH : batch * 2;
+        for (int r = 0; r < fixed_rounds; r++)
+            jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, qstart, dirty, nblk, L.nsub, r, changed + r, rst, L.sbits);
+        IBT_CUDA_TRY(cudaMemcpyAsync(h_flag, changed, (size_t)fixed_rounds * 4, cudaMemcpyDeviceToHost, st));
+        rc = check_launch("jpeg sync");
+        if (rc) return rc;
+    } else {
+        // first batch: the caller's hint (rounds the previous, similar file needed) + 2, else 8
+        int round = 0, batch = 8, rounds_used = -1;
+        if (out_rounds && *out_rounds > 0) batch = *out_rounds + 2 > JPG_MAX_ROUNDS_BATCH ? JPG_MAX_ROUNDS_BATCH : *out_rounds + 2;
+        while (rounds_used < 0) {
+            IBT_CUDA_TRY(cudaMemsetAsync(changed, 0, JPG_MAX_ROUNDS_BATCH * 4, st));
+            for (int r = 0; r < batch; r++)
+                jpg_sync_round<<<sync_ctas, 128, 0, st>>>(words, meta, dT, start, qstart, dirty, nblk, L.nsub, round + r, changed + r, rst, L.sbits);
+            IBT_CUDA_TRY(cudaMemcpyAsync(h_flag, changed, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+            IBT_CUDA_TRY(cudaStreamSynchronize(st));
+            for (int r = 0; r < batch; r++)
+                if (h_flag[r] == 0) { rounds_used = round + r + 1; break; }     // a round without changes: fixed point reached
+            round += batch;
+            if (round > L.nsub + 8) break;                                     // cannot happen: one subsequence settles per round
+            batch = batch * 2 > JPG_MAX_ROUNDS_BATCH ? JPG_MAX_ROUNDS_BATCH : batch * 2;
+        }
+        rc = check_launch("jpeg sync");
+        if (rc) return rc;
+        if (rounds_used < 0) return IBT_E_INVALID;
+        if (out_rounds) *out_rounds = rounds_used;
     }
-    rc = check_launch("jpeg sync");
-    if (rc) return rc;
-    if (rounds_used < 0) return IBT_E_INVALID;
-    if (out_rounds) *out_rounds = rounds_used;
 
     // 3. output block of every subsequence, coefficient pass
     rc = launch_scan(nblk, base, partial, L.nsub * JPG_Q, 1, 0, st);
@@ -975,4 +994,21 @@ IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
     else { IBT_JPG_COLOR(14, 1868, 9617, 4899) }
 #undef IBT_JPG_COLOR
     return check_launch("ibt_jpeg_decode");
+}
+
+IBT_API int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *I, void *d_ws, int64_t ws_bytes, uint8_t *d_rgb,
+                            int64_t rgb_pitch, uint8_t *d_gray, int64_t gray_pitch, int coeffset, int *out_rounds, void *stream)
+{
+    return jpeg_decode_impl(d_file, I, d_ws, ws_bytes, d_rgb, rgb_pitch, d_gray, gray_pitch, coeffset, out_rounds, 0, nullptr, stream);
+}
+
+IBT_API int64_t ibt_jpeg_async_host_bytes(void) { return 256 + (int64_t)sizeof(ibt::JpgTables); }
+
+IBT_API int ibt_jpeg_decode_async(const uint8_t *d_file, const ibt_jpeg_info_t *I, void *d_ws, int64_t ws_bytes, uint8_t *d_rgb,
+                                  int64_t rgb_pitch, uint8_t *d_gray, int64_t gray_pitch, int coeffset, int rounds,
+                                  void *h_pinned, int64_t h_pinned_bytes, void *stream)
+{
+    if (rounds < 1 || !h_pinned || h_pinned_bytes < ibt_jpeg_async_host_bytes()) return IBT_E_INVALID;
+    return jpeg_decode_impl(d_file, I, d_ws, ws_bytes, d_rgb, rgb_pitch, d_gray, gray_pitch, coeffset, nullptr, rounds,
+                            static_cast<uint8_t *>(h_pinned), stream);
 }

@@ -703,6 +703,7 @@ static int fill_pyr(const ibt_pyramid_t *p, LKPyr &o, bool need_deriv)
 // queue when its last warp leaves, so queues of different streams never alias however many launches are in flight.
 struct LKQueue { int dev; cudaStream_t stream; unsigned int *words; };
 static std::mutex lk_mu;
+static int lk_max_ctas_per_sm = 0;          // ibt_lk_set_max_ctas_per_sm: 0 = fill the SM
 static std::vector<LKQueue> lk_queues;
 static bool lk_attr_set[64] = {false};
 
@@ -795,6 +796,10 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
             if (const char *c = getenv("IBT_LK_CTAS")) { const int v = atoi(c); if (v >= 1 && v < best_ctas) best_ctas = v; }
         }
     }
+    {
+        std::lock_guard<std::mutex> lock(lk_mu);
+        if (lk_max_ctas_per_sm > 0 && best_ctas > lk_max_ctas_per_sm) best_ctas = lk_max_ctas_per_sm;
+    }
     const size_t smem = (size_t)a.warp_smem * wpc;
     void (*kern)(const LKArgs, const LKMaps) = lk_kernel<0, 0>;      // generic window; the sizes the configs use are specialised
     if (winW == 21 && winH == 21) kern = lk_kernel<21, 21>;
@@ -825,6 +830,14 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
 }
 
 } // namespace ibt
+
+IBT_API int ibt_lk_set_max_ctas_per_sm(int ctas)
+{
+    if (ctas < 0) return IBT_E_INVALID;
+    std::lock_guard<std::mutex> lock(ibt::lk_mu);
+    ibt::lk_max_ctas_per_sm = ctas;
+    return IBT_OK;
+}
 
 IBT_API int ibt_lk(const ibt_pyramid_t *pyrI, const ibt_pyramid_t *pyrJ, const float *pts, float *next_pts, int N,
                    int winW, int winH, int max_count, double epsilon, double min_eig_threshold, int flags,

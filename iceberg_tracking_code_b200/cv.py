@@ -334,6 +334,12 @@ def calcOpticalFlowPyrLK_FB(prev, next, p0, winSize=(21, 21), maxLevel=3,
     return r
 
 
+def set_lk_resident_ctas(ctas):
+    """Process-wide occupancy cap of the persistent LK launches (ibt_lk_set_max_ctas_per_sm): 0 = fill the SMs (default), 2 =
+    leave a third of every SM to kernels of other streams (the GPU JPEG decode of the next frame runs beside the tracker)."""
+    N.check(N.lib().ibt_lk_set_max_ctas_per_sm(int(ctas)), "ibt_lk_set_max_ctas_per_sm")
+
+
 def lk_fb_into(prev, next, p0, lk_params, p1, fbdist, alive=None, iter_total=None):
     """Allocation-free form of calcOpticalFlowPyrLK_FB for steady-state loops: prev / next are FramePyramids with
     derivatives, p0 (N,2) f32, p1 (N,2) f32 and fbdist (N,) f32 are preallocated device tensors; alive (N,) u8 is

@@ -105,6 +105,73 @@ class JpegDecoder:
         return out_rgb, out_gray
 
 
+    # -- asynchronous form: nothing waits for the GPU; convergence of the speculative Huffman pass is checked afterwards --------
+    def decode_async(self, data, rgb=False, gray=True, coeffset=0, margin=4):
+        """Like decode(), but the host does not wait: `last_rounds + margin` synchronisation rounds are enqueued (consecutive
+        frames of a camera need about the same number; the first file of a decoder goes through decode()).  Returns a handle;
+        `outputs(handle)` gives (rgb, gray) at once (valid once the stream has passed the decode AND confirm(handle) is True)."""
+        if self.last_rounds <= 0:
+            r, g = self.decode(data, rgb, gray, coeffset)
+            ev = torch.cuda.Event(); ev.record()
+            return {"rgb": r, "gray": g, "event": ev, "flags": None, "rounds": 0, "data": None}
+        buf = np.frombuffer(data, dtype=np.uint8)
+        slot = self._pinned_slot(buf.size)
+        view = slot[0].numpy()
+        view[:buf.size] = buf
+        info = parse(view[:buf.size])
+        H, W = info.height, info.width
+        if info.ncomp == 1:
+            rgb, gray = False, True
+        need = N.lib().ibt_jpeg_workspace_bytes(C.byref(info))
+        if need <= 0:
+            raise Unsupported("JPEG variant not handled on the GPU")
+        rounds = min(64, self.last_rounds + int(margin))
+        hb = int(N.lib().ibt_jpeg_async_host_bytes())
+        if not hasattr(self, "_hpin"):
+            self._hpin, self._hk = [None] * 4, 0
+        k = self._hk
+        self._hk = (k + 1) % 4
+        hp = self._hpin[k]
+        if hp is None:
+            hp = self._hpin[k] = (torch.empty((hb,), dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+        hp[1].synchronize()                              # the decode that used this staging four calls ago has passed
+        with torch.cuda.device(self.device):
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty((int(need * 1.1) + 256,), dtype=torch.uint8, device=self.device)
+            dfile = self._upload(slot, buf.size)
+            out_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=self.device) if rgb else None
+            out_gray = torch.empty((H, W), dtype=torch.uint8, device=self.device) if gray else None
+            N.check(N.lib().ibt_jpeg_decode_async(cv._ptr(dfile), C.byref(info), cv._ptr(self._ws), self._ws.numel(),
+                                                  cv._ptr(out_rgb), W * 3, cv._ptr(out_gray), W, int(coeffset), rounds,
+                                                  C.c_void_p(hp[0].data_ptr()), hb, cv._stream()), "ibt_jpeg_decode_async")
+            hp[1].record(torch.cuda.current_stream())
+            ev = torch.cuda.Event(); ev.record()
+        return {"rgb": out_rgb, "gray": out_gray, "event": ev, "flags": hp[0], "rounds": rounds, "data": bytes(data),
+                "args": (rgb, gray, coeffset)}
+
+    def confirm(self, h):
+        """Wait for the decode of handle h and check that its Huffman pass had converged; if not (the file needed more rounds
+        than its predecessors) the file is decoded again synchronously INTO THE SAME outputs' place: returns (rgb, gray)."""
+        h["event"].synchronize()
+        if h["flags"] is None:
+            return h["rgb"], h["gray"]
+        fl = h["flags"][:4 * h["rounds"]].numpy().view(np.uint32)
+        zero = np.flatnonzero(fl == 0)
+        if zero.size:
+            self.last_rounds = int(zero[0]) + 1
+            return h["rgb"], h["gray"]
+        self.last_rounds = 0                              # not converged: decode() finds the count again
+        h["redo"] = True                                  # (whatever the caller derived from the outputs must be rebuilt)
+        rgb, gray, coeffset = h["args"]
+        r, g = self.decode(h["data"], rgb, gray, coeffset)
+        if h["rgb"] is not None:
+            h["rgb"].copy_(r)
+        if h["gray"] is not None:
+            h["gray"].copy_(g)
+        torch.cuda.current_stream().synchronize()
+        return h["rgb"], h["gray"]
+
+
 _default = {}
 
 

@@ -450,6 +450,8 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         # A finished group is compacted and copied to pinned host memory asynchronously and finalised (np.savez, callbacks)
         # one group later.  The order of all arithmetic is that of the reference loop.
         NSLOT = 4
+        if gpu is not None or isinstance(loader, ViewLoader):
+            cv.set_lk_resident_ctas(2)                    # the JPEG decode of the next frame shares the SMs with the tracker
         main = torch.cuda.current_stream()
         side = trk.side
         slots = getattr(trk, "_slots", None)
@@ -529,6 +531,8 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
             if pool is not None:
                 pool.shutdown(wait=False)
             main.wait_stream(side)
+            if gpu is not None or isinstance(loader, ViewLoader):
+                cv.set_lk_resident_ctas(0)
     return results
 
 

@@ -113,6 +113,10 @@ int ibt_lk_fb(const ibt_pyramid_t *prev, const ibt_pyramid_t *next,
               float *p0r, uint8_t *st0, float *err0,
               float *fbdist, uint8_t *alive, int32_t *iters, unsigned long long *iter_total,
               void *stream);
+/* Process-wide occupancy cap of the persistent LK launches: at most `ctas` resident CTAs (of 8 warps) per SM, 0 = fill the SM
+ * (default, 3 for the usual window sizes).  With 2 the launch leaves a third of every SM's shared memory and registers to
+ * kernels of other streams -- e.g. the JPEG decode of the next frame (measured: LK 7 % slower, decode fully overlapped). */
+int ibt_lk_set_max_ctas_per_sm(int ctas);
 
 /* ---- K2: cv2.goodFeaturesToTrack(frame_gray, mask=mask, **feature_params)  s1:437; s0_1:167.
  * cornerMinEigenVal test hook (Sobel3 -> products -> blockSize^2 box sum -> lambda_min). */
@@ -203,6 +207,15 @@ int64_t ibt_jpeg_workspace_bytes(const ibt_jpeg_info_t *info);
 int ibt_jpeg_decode(const uint8_t *d_file, const ibt_jpeg_info_t *info, void *workspace, int64_t workspace_bytes,
                     uint8_t *rgb, int64_t rgb_pitch, uint8_t *gray, int64_t gray_pitch, int coeffset,
                     int *out_rounds, void *stream);
+/* ibt_jpeg_decode without the host round trip: exactly `rounds` synchronisation rounds are enqueued (1..64; a round after the
+ * fixed point changes nothing and costs a few microseconds), their change counters are copied to h_pinned[0 .. rounds) (uint32,
+ * PINNED host memory of at least ibt_jpeg_async_host_bytes(), owned by this call until the stream has passed it) and the
+ * rest of the decode is enqueued right away.  Once the stream has reached that point: the output is valid iff one of the
+ * counters is 0; otherwise call ibt_jpeg_decode (and use more rounds next time). */
+int64_t ibt_jpeg_async_host_bytes(void);
+int ibt_jpeg_decode_async(const uint8_t *d_file, const ibt_jpeg_info_t *info, void *workspace, int64_t workspace_bytes,
+                          uint8_t *rgb, int64_t rgb_pitch, uint8_t *gray, int64_t gray_pitch, int coeffset, int rounds,
+                          void *h_pinned, int64_t h_pinned_bytes, void *stream);
 
 /* ---- s3 consumer: the cell-binning loop of s3_utm_to_gridded_utm.py:391-421 over the square grid of
  *      imports/tracking_misc.py:25-58.  Cell (i, j), i < cols, j < rows, is the square with top-left corner

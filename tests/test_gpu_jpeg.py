@@ -162,3 +162,30 @@ def test_corrupt_streams_terminate(jpeg):
         out = jpeg.imread(c)
         assert tuple(out.shape) == (info.height, info.width, 3)
         assert int(out.sum().item()) >= 0                 # forces completion
+
+
+def test_decode_async_equals_decode(ibt):
+    """ibt_jpeg_decode_async (fixed number of Huffman synchronisation rounds, no host round trip) == ibt_jpeg_decode, and
+    confirm() repairs a decode that was given too few rounds."""
+    import torch
+    from PIL import Image
+    from iceberg_tracking_code_b200 import jpeg, synthetic as syn
+    base = syn.base_texture(600, 900, 5)
+    blobs = []
+    for t in range(3):
+        bio = io.BytesIO()
+        Image.fromarray(syn.frame_rgb(base, t, seed=5).numpy()).save(bio, "JPEG")
+        blobs.append(bio.getvalue())
+    dec = jpeg.JpegDecoder()
+    ref = [dec.decode(b, rgb=True, gray=True) for b in blobs]
+    assert dec.last_rounds > 0
+    for b, (r_rgb, r_gray) in zip(blobs, ref):
+        h = dec.decode_async(b, rgb=True, gray=True)
+        rgb, gray = dec.confirm(h)
+        assert torch.equal(rgb, r_rgb) and torch.equal(gray, r_gray)
+    need = dec.last_rounds
+    if need > 1:                                          # starve the decoder: confirm() must notice and decode again
+        dec.last_rounds = 1
+        h = dec.decode_async(blobs[0], rgb=False, gray=True, margin=0)
+        _, gray = dec.confirm(h)
+        assert torch.equal(gray, ref[0][1]) and dec.last_rounds > 1 and h.get("redo")
