@@ -326,7 +326,7 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
         return acc + float(h_fbd[(n - 1) & 1][0])
     cv.set_lk_resident_ctas(2)
     try:
-        loop(8)
+        loop(12)                                              # (every pinned staging buffer of both decoders exists afterwards)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         loop(steps)

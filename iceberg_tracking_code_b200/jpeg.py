@@ -105,49 +105,90 @@ class JpegDecoder:
         return out_rgb, out_gray
 
 
+    # -- staging on a helper thread: file read, copy into page-locked memory and marker parsing cost ~2 ms of host time per
+    # 24 MP frame -- more than the GPU needs for the frame -- so the frame loop runs them ahead on worker threads --------------
+    NSTAGE = 4
+
+    def stage(self, src):
+        """src: path or bytes.  Reads the file, copies it into one of NSTAGE pinned staging buffers and parses its markers.
+        Safe to call from worker threads (one decoder may be staged by several); the returned handle goes to
+        decode_async(staged=...) on the thread that owns the CUDA stream, in the order the frames were staged."""
+        import threading
+        if not isinstance(src, (bytes, bytearray, memoryview, np.ndarray)):
+            with open(str(src), "rb") as f:
+                src = f.read()
+        buf = np.frombuffer(src, dtype=np.uint8)
+        if not hasattr(self, "_stage_lock"):
+            self._stage_lock = threading.Lock()
+        with self._stage_lock:
+            if not hasattr(self, "_stage_slots"):
+                self._stage_slots, self._stage_k = [None] * self.NSTAGE, 0
+            k = self._stage_k
+            self._stage_k = (k + 1) % self.NSTAGE
+            slot = self._stage_slots[k]
+            if slot is None:
+                free = threading.Event(); free.set()
+                slot = self._stage_slots[k] = {"host": None, "ev": torch.cuda.Event(), "free": free}
+        slot["free"].wait()                               # the decode that used this buffer has been enqueued ...
+        slot["ev"].synchronize()                          # ... and its host -> device copy has finished
+        slot["free"].clear()
+        if slot["host"] is None or slot["host"].numel() < buf.size:
+            slot["host"] = torch.empty((max(buf.size, 1 << 20) * 5 // 4,), dtype=torch.uint8).pin_memory()
+        view = slot["host"].numpy()
+        view[:buf.size] = buf
+        try:
+            info = parse(view[:buf.size])
+        except Exception:
+            slot["free"].set()
+            raise
+        return {"slot": slot, "n": int(buf.size), "info": info, "data": src}
+
     # -- asynchronous form: nothing waits for the GPU; convergence of the speculative Huffman pass is checked afterwards --------
-    def decode_async(self, data, rgb=False, gray=True, coeffset=0, margin=4):
+    def decode_async(self, data=None, rgb=False, gray=True, coeffset=0, margin=4, staged=None):
         """Like decode(), but the host does not wait: `last_rounds + margin` synchronisation rounds are enqueued (consecutive
         frames of a camera need about the same number; the first file of a decoder goes through decode()).  Returns a handle;
-        `outputs(handle)` gives (rgb, gray) at once (valid once the stream has passed the decode AND confirm(handle) is True)."""
-        if self.last_rounds <= 0:
-            r, g = self.decode(data, rgb, gray, coeffset)
-            ev = torch.cuda.Event(); ev.record()
-            return {"rgb": r, "gray": g, "event": ev, "flags": None, "rounds": 0, "data": None}
-        buf = np.frombuffer(data, dtype=np.uint8)
-        slot = self._pinned_slot(buf.size)
-        view = slot[0].numpy()
-        view[:buf.size] = buf
-        info = parse(view[:buf.size])
-        H, W = info.height, info.width
-        if info.ncomp == 1:
-            rgb, gray = False, True
-        need = N.lib().ibt_jpeg_workspace_bytes(C.byref(info))
-        if need <= 0:
-            raise Unsupported("JPEG variant not handled on the GPU")
-        rounds = min(64, self.last_rounds + int(margin))
-        hb = int(N.lib().ibt_jpeg_async_host_bytes())
-        if not hasattr(self, "_hpin"):
-            self._hpin, self._hk = [None] * 4, 0
-        k = self._hk
-        self._hk = (k + 1) % 4
-        hp = self._hpin[k]
-        if hp is None:
-            hp = self._hpin[k] = (torch.empty((hb,), dtype=torch.uint8).pin_memory(), torch.cuda.Event())
-        hp[1].synchronize()                              # the decode that used this staging four calls ago has passed
-        with torch.cuda.device(self.device):
-            if self._ws is None or self._ws.numel() < need:
-                self._ws = torch.empty((int(need * 1.1) + 256,), dtype=torch.uint8, device=self.device)
-            dfile = self._upload(slot, buf.size)
-            out_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=self.device) if rgb else None
-            out_gray = torch.empty((H, W), dtype=torch.uint8, device=self.device) if gray else None
-            N.check(N.lib().ibt_jpeg_decode_async(cv._ptr(dfile), C.byref(info), cv._ptr(self._ws), self._ws.numel(),
-                                                  cv._ptr(out_rgb), W * 3, cv._ptr(out_gray), W, int(coeffset), rounds,
-                                                  C.c_void_p(hp[0].data_ptr()), hb, cv._stream()), "ibt_jpeg_decode_async")
-            hp[1].record(torch.cuda.current_stream())
-            ev = torch.cuda.Event(); ev.record()
-        return {"rgb": out_rgb, "gray": out_gray, "event": ev, "flags": hp[0], "rounds": rounds, "data": bytes(data),
-                "args": (rgb, gray, coeffset)}
+        confirm(handle) waits for the decode and returns (rgb, gray) -- of a repeated, synchronous decode if the Huffman pass
+        had not converged within the rounds given.  staged: a handle of stage() instead of `data`."""
+        if staged is None:
+            staged = self.stage(data)
+        slot, n, info, data = staged["slot"], staged["n"], staged["info"], staged["data"]
+        host = slot["host"]
+        try:
+            if self.last_rounds <= 0:
+                r, g = self._decode_staged(host.numpy()[:n], (host, slot["ev"]), rgb, gray, coeffset)
+                ev = torch.cuda.Event(); ev.record()
+                return {"rgb": r, "gray": g, "event": ev, "flags": None, "rounds": 0, "data": None}
+            H, W = info.height, info.width
+            if info.ncomp == 1:
+                rgb, gray = False, True
+            need = N.lib().ibt_jpeg_workspace_bytes(C.byref(info))
+            if need <= 0:
+                raise Unsupported("JPEG variant not handled on the GPU")
+            rounds = min(64, self.last_rounds + int(margin))
+            hb = int(N.lib().ibt_jpeg_async_host_bytes())
+            if not hasattr(self, "_hpin"):
+                self._hpin, self._hk = [None] * 4, 0
+            k = self._hk
+            self._hk = (k + 1) % 4
+            hp = self._hpin[k]
+            if hp is None:
+                hp = self._hpin[k] = (torch.empty((hb,), dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+            hp[1].synchronize()                          # the decode that used this staging four calls ago has passed
+            with torch.cuda.device(self.device):
+                if self._ws is None or self._ws.numel() < need:
+                    self._ws = torch.empty((int(need * 1.1) + 256,), dtype=torch.uint8, device=self.device)
+                dfile = self._upload((host, slot["ev"]), n)
+                out_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=self.device) if rgb else None
+                out_gray = torch.empty((H, W), dtype=torch.uint8, device=self.device) if gray else None
+                N.check(N.lib().ibt_jpeg_decode_async(cv._ptr(dfile), C.byref(info), cv._ptr(self._ws), self._ws.numel(),
+                                                      cv._ptr(out_rgb), W * 3, cv._ptr(out_gray), W, int(coeffset), rounds,
+                                                      C.c_void_p(hp[0].data_ptr()), hb, cv._stream()), "ibt_jpeg_decode_async")
+                hp[1].record(torch.cuda.current_stream())
+                ev = torch.cuda.Event(); ev.record()
+            return {"rgb": out_rgb, "gray": out_gray, "event": ev, "flags": hp[0], "rounds": rounds, "data": bytes(data),
+                    "args": (rgb, gray, coeffset)}
+        finally:
+            slot["free"].set()                            # (the CUDA event of the slot guards the copy itself)
 
     def confirm(self, h):
         """Wait for the decode of handle h and check that its Huffman pass had converged; if not (the file needed more rounds

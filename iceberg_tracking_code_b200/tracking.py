@@ -45,9 +45,12 @@ def read_file(path):
 
 
 class GpuJpegLoader:
-    """loader="gpu": path -> (gray CUDA tensor, ready event), the handle SequenceTracker.prepare() accepts.
-    The decode runs on its own CUDA stream: issued right after a frame's tracking kernels, its kernels (and the one
-    host wait of the Huffman convergence check) overlap that frame's work on the main stream."""
+    """loader="gpu": path -> (gray CUDA tensor, ready event, confirm), the handle SequenceTracker.prepare() accepts.
+    Two decoders on two high-priority CUDA streams take the frames alternately and never make the host wait
+    (jpeg.JpegDecoder.decode_async): a decode is a chain of small latency-bound kernels, so two in flight -- beside the LK
+    launch of the pair being tracked, which track_sequence caps at two of its three CTAs per SM -- cost little more than one.
+    confirm() must be called before the frame is consumed: it waits for the decode, checks that the speculative Huffman
+    pass had converged and returns None, or (gray, event) of a repeated decode."""
 
     def __init__(self, device, coeffset=0, crop_box=None):
         """crop_box = (left, upper, right, lower) as PIL's Image.crop takes it (camtools.py:79): the decoded plane is cropped
@@ -57,28 +60,45 @@ class GpuJpegLoader:
         self.device = device
         self.coeffset = coeffset
         self.crop_box = None if crop_box is None else tuple(int(v) for v in crop_box)
-        self.dec = _jpeg.JpegDecoder(device)
-        self.stream = torch.cuda.Stream(device=device)
+        self.decs = [_jpeg.JpegDecoder(device), _jpeg.JpegDecoder(device)]
+        self.dec = self.decs[0]
+        self.streams = [torch.cuda.Stream(device=device, priority=-1), torch.cuda.Stream(device=device, priority=-1)]
+        self.stream = self.streams[0]
+        self._n = 0
 
-    def decode(self, data):
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            gray = self.dec.decode(data, rgb=False, gray=True, coeffset=self.coeffset)[1]   # s1:310-311 in one pass
-            if self.crop_box is not None:
-                l, u, r, b = self.crop_box
-                gray = gray[u:b, l:r].contiguous()
+    def _crop(self, gray):
+        if self.crop_box is None:
+            return gray
+        l, u, r, b = self.crop_box
+        return gray[u:b, l:r].contiguous()
+
+    def stage(self, path, index):
+        """read + stage + parse the file for the decoder that will take frame `index` (worker threads)"""
+        return self.decs[index & 1].stage(path)
+
+    def decode(self, data=None, staged=None):
+        k = self._n & 1
+        self._n += 1
+        dec, st = self.decs[k], self.streams[k]
+        with torch.cuda.device(self.device), torch.cuda.stream(st):
+            h = dec.decode_async(data, rgb=False, gray=True, coeffset=self.coeffset, staged=staged)     # s1:310-311 in one pass
+            gray = self._crop(h["gray"])
             ev = torch.cuda.Event()
-            ev.record(self.stream)
-        return gray, ev
+            ev.record(st)
+
+        def confirm():
+            with torch.cuda.device(self.device), torch.cuda.stream(st):
+                dec.confirm(h)
+                if not h.get("redo"):
+                    return None
+                g2 = self._crop(h["gray"])
+                e2 = torch.cuda.Event()
+                e2.record(st)
+            return g2, e2
+        return gray, ev, confirm
 
     def __call__(self, path):
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            gray = self.dec.decode_file(path, rgb=False, gray=True, coeffset=self.coeffset)[1]
-            if self.crop_box is not None:
-                l, u, r, b = self.crop_box
-                gray = gray[u:b, l:r].contiguous()
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        return gray, ev
+        return self.decode(read_file(path))
 
 
 class ViewLoader:
@@ -185,7 +205,7 @@ class SequenceTracker:
             else:
                 handle = None
             if handle is not None:
-                frame, ev = handle
+                frame, ev = handle[0], handle[1]
                 torch.cuda.current_stream().wait_event(ev)
                 frame.record_stream(torch.cuda.current_stream())
             if frame.ndim == 3:
@@ -424,8 +444,15 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         seed_idx = None
         counters = range(g0 * T, g1 * T + 1)
         pool, futures = None, {}
-        # (the "gpu" loader reads the few MB of a file in the calling thread: a pool only adds GIL contention there)
-        if host_loader is not None and gpu is None and decode_workers and decode_workers > 1:
+        if gpu is not None and decode_workers:
+            # the GPU decoder's host side (file read, copy into pinned memory, marker parsing: ~2 ms per 24 MP frame) runs on two
+            # worker threads, four frames ahead; frames must reach the two decoders alternately, in order
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(max_workers=2)
+            gpu._n = 0
+            for i, c in enumerate(counters[:4]):
+                futures[c] = pool.submit(gpu.stage, frames[c], i)
+        elif host_loader is not None and gpu is None and decode_workers and decode_workers > 1:
             from concurrent.futures import ThreadPoolExecutor
             pool = ThreadPoolExecutor(max_workers=int(decode_workers))
             for c in counters[:decode_workers]:
@@ -433,6 +460,11 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
 
         def fetch(c):
             """frame c as prepare() takes it (host array, device tensor, or (device tensor, event) from the GPU decoder)"""
+            if pool is not None and gpu is not None:
+                nxt = c + 4
+                if nxt <= counters[-1]:
+                    futures[nxt] = pool.submit(gpu.stage, frames[nxt], nxt - counters[0])
+                return gpu.decode(staged=futures.pop(c).result())
             if pool is not None:
                 nxt = c + decode_workers
                 if nxt <= counters[-1]:
@@ -449,13 +481,15 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         # idle while its last warps finish.  Four pyramid slots: slot (c+1) % 4 was last read by the LK launch of frame c-2.
         # A finished group is compacted and copied to pinned host memory asynchronously and finalised (np.savez, callbacks)
         # one group later.  The order of all arithmetic is that of the reference loop.
-        NSLOT = 4
-        if gpu is not None or isinstance(loader, ViewLoader):
-            cv.set_lk_resident_ctas(2)                    # the JPEG decode of the next frame shares the SMs with the tracker
+        on_gpu = gpu is not None or isinstance(loader, ViewLoader)
+        LOOK = 2 if on_gpu else 1                         # frames prepared ahead (two decoders work in parallel)
+        NSLOT = LOOK + 3
+        if on_gpu:
+            cv.set_lk_resident_ctas(2)                    # the JPEG decodes of the next frames share the SMs with the tracker
         main = torch.cuda.current_stream()
         side = trk.side
         slots = getattr(trk, "_slots", None)
-        if slots is None:
+        if slots is None or len(slots) != NSLOT:
             slots = trk._slots = [None] * NSLOT
         lk_done = [None] * NSLOT
         side.wait_stream(main)
@@ -463,8 +497,7 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         def is_seed(c):
             return (c - g0 * T) % T == 0 and c < g1 * T
 
-        def prepare_ahead(c):
-            data = fetch(c)
+        def build_on_side(c, data):
             k = c % NSLOT
             with torch.cuda.stream(side):
                 if lk_done[k] is not None:
@@ -485,6 +518,20 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
                 ev.record(side)
             return pyr, ev, pf
 
+        def prepare_ahead(c):
+            data = fetch(c)
+            conf = data[2] if isinstance(data, tuple) and len(data) > 2 else None
+            return build_on_side(c, data) + (conf, c)
+
+        def confirmed(item):
+            """the frame's GPU decode had converged -- else its pyramid (and corners) are rebuilt from the repeated decode"""
+            pyr, ev, pf, conf, c = item
+            if conf is not None:
+                again = conf()
+                if again is not None:
+                    pyr, ev, pf = build_on_side(c, again)
+            return pyr, ev, pf
+
         pending = []                                      # (seed_idx, ok, path, harvest handle) of groups not finalised yet
 
         def finalize_oldest():
@@ -500,11 +547,12 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
                     on_group(start + sidx, tracks, quality)
 
         try:
-            ahead = prepare_ahead(counters[0])
+            queue = [prepare_ahead(c) for c in counters[:LOOK]]
             for counter in counters:
-                cur, ev_cur, pf_cur = ahead
-                # the next frame is fetched and prepared now: a GPU decode / upload / pyramid build overlaps this frame's kernels
-                ahead = prepare_ahead(counter + 1) if counter < counters[-1] else None
+                cur, ev_cur, pf_cur = confirmed(queue.pop(0))
+                # the next frames are fetched and prepared now: GPU decode / upload / pyramid build overlap this frame's kernels
+                if counter + LOOK <= counters[-1]:
+                    queue.append(prepare_ahead(counter + LOOK))
                 main.wait_event(ev_cur)
                 if prev is not None and trk.n > 0:
                     trk.track(prev, cur)
@@ -531,7 +579,7 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
             if pool is not None:
                 pool.shutdown(wait=False)
             main.wait_stream(side)
-            if gpu is not None or isinstance(loader, ViewLoader):
+            if on_gpu:
                 cv.set_lk_resident_ctas(0)
     return results
 
@@ -616,7 +664,10 @@ class LucasKanade:
         prev = None
         loader = GpuJpegLoader(trk.device) if self.loader == "gpu" else self.loader
         for counter, image in enumerate(self.imagelist):
-            cur = trk.prepare(loader(image))
+            frame = loader(image)
+            if isinstance(frame, tuple) and len(frame) > 2:      # GPU decode: confirm it before the frame is used
+                frame = frame[2]() or frame[:2]
+            cur = trk.prepare(frame)
             if prev is not None and trk.n > 0:
                 trk.track(prev, cur)
             if counter % self.detect_interval == 0:

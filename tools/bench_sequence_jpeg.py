@@ -12,13 +12,13 @@ from iceberg_tracking_code_b200 import build, synthetic as syn
 from iceberg_tracking_code_b200.tracking import track_sequence, SequenceTracker, load_image
 
 build.build()
-H, W, NF, T = 4000, 6000, int(os.environ.get("NF", 13)), 2
+H, W, NF, T = 4000, 6000, int(os.environ.get("NF", 37)), 2
 maxc = int(os.environ.get("MAXC", 20000))
 tmp = tempfile.mkdtemp(prefix="ibt_seq_")
 base = syn.base_texture(H, W, 7, device="cuda", scene=os.environ.get("SCENE", "texture"))
 files = []
 for t in range(NF):
-    rgb = syn.frame_rgb(base, t, seed=7).cpu().numpy()
+    rgb = syn.frame_rgb(base, t % 12, seed=7 + t).cpu().numpy()          # (the scene wraps every 12 frames: stays inside the margin)
     f = os.path.join(tmp, "20190724-13%02d00.jpg" % t)
     Image.fromarray(rgb).save(f)
     files.append(f)
