@@ -43,8 +43,10 @@ __host__ __device__ constexpr int lk_trows(int w, int h) { return lk_ng(w, h) * 
 // template-build mapping: lane = column of a strip of <= 32 of the TCOLS template columns
 __host__ __device__ constexpr int lk_nstrips(int w) { return (lk_tcols(w) + 31) / 32; }
 __host__ __device__ constexpr int lk_strip_cols(int w) { return (lk_tcols(w) + lk_nstrips(w) - 1) / lk_nstrips(w); }
+// window widths whose compiled-in kernel builds the template with build_template_split (columns 32.. spread over the lanes)
+__host__ __device__ constexpr bool lk_split(int w) { return w == 35; }
 // every lane of every strip reads two adjacent elements per row, active or not: pitches keep those reads in the slab
-__host__ __device__ constexpr int lk_reach(int w) { return (lk_nstrips(w) - 1) * lk_strip_cols(w) + 33; }
+__host__ __device__ constexpr int lk_reach(int w) { return lk_split(w) ? lk_tcols(w) + 1 : (lk_nstrips(w) - 1) * lk_strip_cols(w) + 33; }
 __host__ __device__ constexpr int lk_dpitch(int w) { return (lk_reach(w) + 6) & ~3; }                 // words; rows are 16-byte multiples (TMA box); + window offset 0..3
 // TMA boxes start on 16-byte boundaries of the image row: up to 15 extra columns on the left
 __host__ __device__ constexpr int lk_ipitch(int w) { return (15 + lk_reach(w) + 15) & ~15; }
@@ -277,11 +279,95 @@ __device__ __forceinline__ void stage_deriv(const LKLevel &L, const LKArgs &a, i
 //   A11 = sum Ix^2, A12 = sum Ix*Iy, A22 = sum Iy^2, C1 = sum Iw*Ix, C2 = sum Iw*Iy.
 // The template row r overwrites Scharr patch bytes below row r+1 only (TCOLS <= DPITCH), which every lane has consumed
 // by then (one __syncwarp per row keeps the lanes within a row of each other).
+// Windows 33 .. 36 px wide (the reference's own 35 x 35): a second 32-lane strip would run the whole row loop again for 1 .. 4
+// columns.  Instead the columns 32 .. TCOLS-1 are spread over the 32 lanes as (column, row phase): a lane handles rows
+// ph, ph + PH, ... of one of them (5 pixels at 35 x 35) without a row-to-row carry.  That pass runs FIRST (the template overlays
+// the Scharr patch and would overwrite what it reads), keeps its results in registers, and stores them after the main strip.
+template <int WW, int WH>
+__device__ __forceinline__ void build_template_split(const uint8_t *ip0, const uint32_t *dp0, uint32_t *tmpl, uint32_t wtop,
+                                                     uint32_t wbot, int iw00, int iw01, int iw10, int iw11, int lane,
+                                                     long long &sA11, long long &sA12, long long &sA22, long long &sC1, long long &sC2)
+{
+    constexpr int TC = lk_tcols(WW), TR = lk_trows(WW, WH), IP = lk_ipitch(WW), DP = lk_dpitch(WW);
+    constexpr int C1 = TC - 32, PH = 32 / C1, NR = (WH + PH - 1) / PH;
+    static_assert(C1 >= 1 && C1 <= 4 && (32 % C1) == 0 || C1 == 3, "split template: 1, 2 or 4 extra columns");
+    // ---- the extra columns ------------------------------------------------------------------------------------------------------
+    const int xc = 32 + lane % C1, ph = lane / C1;
+    const bool lane1 = ph < PH;
+    uint32_t tv[NR];
+    int e11 = 0, e12 = 0, e22 = 0, ec1 = 0, ec2 = 0;
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+        const int r = ph + PH * i;
+        const bool act = lane1 && r < WH && xc < WW;
+        const int rr = act ? r : 0;                              // (idle lanes read row 0: any staged address will do)
+        const uint8_t *ip = ip0 + rr * IP + xc;
+        const uint32_t *dp = dp0 + rr * DP + xc;
+        const uint32_t p0 = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8), p1 = (uint32_t)ip[IP] | ((uint32_t)ip[IP + 1] << 8);
+        const uint32_t q00 = dp[0], q01 = dp[1], q10 = dp[DP], q11 = dp[DP + 1];
+        const uint32_t v = dp2a_lo(wbot, p1, dp2a_lo(wtop, p0, 256u));
+        int Iw = (int)(v >> 9);
+        int Ix = ((int)(short)(q00 & 0xffffu) * iw00 + (int)(short)(q01 & 0xffffu) * iw01 + (int)(short)(q10 & 0xffffu) * iw10 +
+                  (int)(short)(q11 & 0xffffu) * iw11 + 8192) >> 14;
+        int Iy = (((int)q00 >> 16) * iw00 + ((int)q01 >> 16) * iw01 + ((int)q10 >> 16) * iw10 + ((int)q11 >> 16) * iw11 + 8192) >> 14;
+        if (!act) { Iw = 0; Ix = 0; Iy = 0; }
+        tv[i] = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
+        e11 += Ix * Ix; e12 += Ix * Iy; e22 += Iy * Iy; ec1 += Iw * Ix; ec2 += Iw * Iy;
+    }
+    __syncwarp();
+    // ---- the main strip: columns 0 .. 31, one per lane, rows top to bottom (all inside the window) ----------------------------------
+    int a11 = 0, a12 = 0, a22 = 0, c1 = 0, c2 = 0;
+    const uint8_t *ipl = ip0 + lane;
+    const uint32_t *dpl = dp0 + lane;
+    uint32_t ipair = (uint32_t)ipl[0] | ((uint32_t)ipl[1] << 8);
+    int d00x, d00y, d01x, d01y;
+    {
+        const uint32_t dc = dpl[0], dcr = dpl[1];
+        d00x = (int)(short)(dc & 0xffffu); d00y = (int)dc >> 16;
+        d01x = (int)(short)(dcr & 0xffffu); d01y = (int)dcr >> 16;
+    }
+#pragma unroll 4
+    for (int r = 0; r < WH; r++) {
+        const uint8_t *ip = ipl + (r + 1) * IP;
+        const uint32_t *dp = dpl + (r + 1) * DP;
+        const uint32_t cpair = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8);
+        const uint32_t dc = dp[0], dcr = dp[1];
+        const int d10x = (int)(short)(dc & 0xffffu), d10y = (int)dc >> 16;
+        const int d11x = (int)(short)(dcr & 0xffffu), d11y = (int)dcr >> 16;
+        uint32_t v = dp2a_lo(wtop, ipair, 256u);
+        v = dp2a_lo(wbot, cpair, v);
+        const int Iw = (int)(v >> 9);
+        const int Ix = (d00x * iw00 + d01x * iw01 + d10x * iw10 + d11x * iw11 + 8192) >> 14;
+        const int Iy = (d00y * iw00 + d01y * iw01 + d10y * iw10 + d11y * iw11 + 8192) >> 14;
+        tmpl[r * TC + lane] = ((uint32_t)Ix << 16) | ((uint32_t)Iy & 0xffffu);
+        a11 += Ix * Ix; a12 += Ix * Iy; a22 += Iy * Iy;
+        c1 += Iw * Ix; c2 += Iw * Iy;
+        ipair = cpair; d00x = d10x; d00y = d10y; d01x = d11x; d01y = d11y;
+        __syncwarp();            // the template overlays the Scharr patch rows already consumed (see launch_lk)
+    }
+    // ---- the extra columns' entries, the template rows below the window -------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+        const int r = ph + PH * i;
+        if (lane1 && r < WH) tmpl[r * TC + xc] = tv[i];
+    }
+    for (int i = WH * TC + lane; i < TR * TC; i += 32) tmpl[i] = 0u;
+    sA11 = warp_sum_wide(a11) + warp_sum_wide(e11); sA12 = warp_sum_wide(a12) + warp_sum_wide(e12);
+    sA22 = warp_sum_wide(a22) + warp_sum_wide(e22);
+    sC1 = warp_sum_wide(c1) + warp_sum_wide(ec1); sC2 = warp_sum_wide(c2) + warp_sum_wide(ec2);
+    __syncwarp();
+}
+
 template <int WW, int WH>
 __device__ __forceinline__ void build_template(const LKArgs &a, const uint8_t *ip0, const uint32_t *dp0, uint32_t *tmpl,
                                                uint32_t wtop, uint32_t wbot, int iw00, int iw01, int iw10, int iw11, int lane,
                                                long long &sA11, long long &sA12, long long &sA22, long long &sC1, long long &sC2)
 {
+    if (WW > 0 && WH > 0 && lk_split(WW)) {
+        build_template_split<lk_split(WW) ? WW : 35, WH ? WH : 35>(ip0, dp0, tmpl, wtop, wbot, iw00, iw01, iw10, iw11, lane,
+                                                                             sA11, sA12, sA22, sC1, sC2);
+        return;
+    }
     const int winW = WW ? WW : a.winW, winH = WH ? WH : a.winH;
     constexpr int NS = WW ? lk_nstrips(WW) : 2;                 // strips held in registers (generic kernel: at most 2)
     const int nstrips = WW ? lk_nstrips(WW) : a.nstrips, SC = WW ? lk_strip_cols(WW) : a.strip_cols;
