@@ -304,3 +304,45 @@ def test_config5_tracks_to_utm(ibt, golden):
     en = cam.tracks_to_utm(tracks)
     assert en.shape == tracks.shape and en.dtype == np.float64
     assert np.abs(en.reshape(-1, 2) - g["EN"]).max() <= 1e-6
+
+
+def test_async_pieces_equal_synchronous(ibt):
+    """The asynchronous forms the pipelined loop uses give the same answers as the synchronous calls they replace:
+    gftt_prefetch + seed(prefetched=) vs goodFeaturesToTrack, harvest_async + finalize vs harvest, and the LK launch under an
+    occupancy cap (ibt_lk_set_max_ctas_per_sm) vs the full-occupancy launch."""
+    from iceberg_tracking_code_b200 import synthetic as syn
+    from iceberg_tracking_code_b200.tracking import SequenceTracker
+    base = syn.base_texture(700, 900, 11, device="cuda")
+    f = [syn.frame_gray(base, t) for t in range(3)]
+    gp = dict(maxCorners=3000, qualityLevel=0.007, minDistance=10, blockSize=10)
+    lp = dict(winSize=(31, 31), maxLevel=3, criteria=(3, 30, 0.01))
+    a, b = SequenceTracker(gp, lp), SequenceTracker(gp, lp)
+    pa = [a.prepare(x) for x in f]
+    pb = [b.prepare(x) for x in f]
+    na = a.seed(pa[0], None, 2)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        pf = b.gftt_prefetch(pb[0], None)
+    nb = b.seed(pb[0], None, 2, prefetched=pf)
+    assert na == nb and torch.equal(a._tracks[0], b._tracks[0])
+    ref = ibt.goodFeaturesToTrack(f[0], **gp)
+    assert torch.equal(a._tracks[0], ref.reshape(-1, 2))
+    a.track(pa[0], pa[1]); a.track(pa[1], pa[2])
+    ibt.set_lk_resident_ctas(1)
+    try:
+        b.track(pb[0], pb[1])
+        ibt.set_lk_resident_ctas(2)
+        b.track(pb[1], pb[2])
+    finally:
+        ibt.set_lk_resident_ctas(0)
+    ta, qa = a.harvest()
+    tb, qb = b.finalize(b.harvest_async())
+    assert np.array_equal(ta, tb) and np.array_equal(qa, qb) and ta.shape[0] > 2000
+    # all corners (maxCorners = 0) and a mask through the asynchronous form
+    c = SequenceTracker(dict(gp, maxCorners=0), lp)
+    mask = torch.zeros((700, 900), dtype=torch.uint8, device="cuda"); mask[100:600, 50:800] = 255
+    pc = c.prepare(f[0])
+    n = c.seed(pc, mask, 2, prefetched=c.gftt_prefetch(pc, mask))
+    ref = ibt.goodFeaturesToTrack(f[0], mask=mask, **dict(gp, maxCorners=0))
+    assert n == ref.shape[0] and torch.equal(c._tracks[0], ref.reshape(-1, 2))
