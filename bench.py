@@ -766,6 +766,15 @@ def main():
             out["roofline"]["traffic"] = tf.get("dram_bytes_per_prepare", tf.get("dram_bytes_per_launch"))
             out["roofline"]["traffic_source"] = tf.get("source")
             out["lk"]["ncu"] = tf.get("lk")
+            # issue roofline of the dominant kernel: warp-instructions per point pair (ncu, same kernel) x the point pairs per
+            # second measured in this run, against 4 issue slots per SM per clock at the SM clock sampled in this run
+            ipp = (tf.get("lk") or {}).get("p1_fbdist_only", {}).get("warp_instructions_per_point_pair")
+            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
+            if ipp and mhz:
+                ach = ipp * (value / world)                       # per GPU
+                pk = 148 * 4 * mhz * 1e6
+                out["lk"]["issue_roofline"] = {"bound": "instruction issue", "achieved": ach, "peak": pk, "unit": "warp-instructions/s",
+                                               "frac": ach / pk, "note": "whole step time in the denominator (LK is ~92 % of it)"}
         except Exception:                           # noqa: BLE001
             pass
     if frames_np is not None:
