@@ -116,8 +116,9 @@ def check(rc, where):
 def bind_to_gpu_numa_node(device_index):
     """Pin this process (and so the pages it touches first: pinned staging buffers) to the CPUs of the NUMA node the GPU hangs
     off.  With one process per GPU, frames that travel host -> device every step otherwise all stream out of whichever node
-    the ranks happened to start on, and 4-8 ranks saturate that node's memory / inter-socket link (round 1: host-fed throughput
-    stopped scaling at 4 GPUs).  Returns the node, or None when the topology cannot be read (then nothing is changed)."""
+    the ranks happened to start on, and 4-8 ranks can saturate that node's memory / inter-socket link.  Returns the node, or
+    None when the topology cannot be read -- as on this pool's VMs, which expose one node and no GPU affinity; their host
+    fabric stops at ~115 GB/s for 4+ GPUs whatever the placement (then nothing is changed)."""
     import os
     try:
         import torch

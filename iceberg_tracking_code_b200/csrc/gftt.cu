@@ -1184,7 +1184,20 @@ static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask,
     a.md2 = (float)(minDistance * minDistance);
     a.out_xy = out_xy;
     a.out_count = count_dev ? count_dev : reinterpret_cast<int *>(&cnt->pad);
-    gftt_select_kernel<<<kNumSMs * SEL_CTAS_PER_SM, SEL_THREADS, 0, st>>>(a);        // every CTA resident: the kernel synchronises its grid itself
+    // every CTA must be resident (the kernel synchronises its grid itself): size the grid from what THIS device can hold
+    static int sel_grid[64] = {0};
+    int dev_id = 0;
+    IBT_CUDA_TRY(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64) return IBT_E_INVALID;
+    if (!sel_grid[dev_id]) {
+        int sms = 0, per_sm = 0;
+        IBT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+        IBT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gftt_select_kernel, SEL_THREADS, 0));
+        if (per_sm > SEL_CTAS_PER_SM) per_sm = SEL_CTAS_PER_SM;
+        if (sms < 1 || per_sm < 1) return IBT_E_CUDA;
+        sel_grid[dev_id] = sms * per_sm;
+    }
+    gftt_select_kernel<<<sel_grid[dev_id], SEL_THREADS, 0, st>>>(a);
     return check_launch("gftt_select_kernel");
 }
 

@@ -266,8 +266,10 @@ class SequenceTracker:
         p = cv._ptr
         N.check(N.lib().ibt_gftt_async(p(img), img.stride(0), p(m), W, H, W, maxc, q, md, bs, p(self._ws), self._ws.numel(),
                                        p(out), cap, p(cnt), cv._stream()), "ibt_gftt_async")
-        h = self._pin((1,), torch.int32)
-        h.copy_(cnt, non_blocking=True)
+        # (nout, error) of the workspace counters (GfttCounters: maxbits, ncand, nsel, nacc, nout, error): a capacity overflow
+        # raised on the device must not pass as "no corners"
+        h = self._pin((2,), torch.int32)
+        h.copy_(self._ws[16:24].view(torch.int32), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         return out, cnt, h, ev
@@ -278,8 +280,9 @@ class SequenceTracker:
         if prefetched is not None:
             out, _cnt, h, ev = prefetched
             ev.synchronize()                              # (issued a frame ago: normally long finished)
-            n = int(h[0])
+            n, err = int(h[0]), int(h[1])
             self._unpin(h)
+            N.check(err, "ibt_gftt_async")
             torch.cuda.current_stream().wait_event(ev)
             out.record_stream(torch.cuda.current_stream())
             p = out[:n] if n else None

@@ -207,3 +207,32 @@ def test_device_tensors_stay_on_device(ibt, golden):
     pb = ibt.FramePyramid(f1, LK_SETS[0]["winSize"], LK_SETS[0]["maxLevel"], True)
     q1, qs, _ = ibt.calcOpticalFlowPyrLK(pa, pb, pts, None, **LK_SETS[0])
     assert torch.equal(q1, p1) and torch.equal(qs, st)
+
+
+def test_gftt_prefilter_fallback_and_ties_vs_oracle(ibt, oracle):
+    """Two paths of the selection kernel that the texture scenes do not reach, against the CPU oracle:
+    (1) the top-k prefilter ranks only the strongest ~4*maxCorners candidates, all of them lie in one bright patch, min-distance
+        culling leaves fewer than maxCorners of them -> the kernel must start over with every candidate;
+    (2) a periodic image: many candidates with EXACTLY equal responses -> OpenCV's tie-break (higher address first) decides."""
+    rng = np.random.default_rng(12)
+    h, w = 700, 900
+    weak = (rng.integers(0, 256, (h, w)).astype(np.float32) - 128) * 0.08 + 128
+    img = weak.copy()
+    img[150:550, 200:600] = rng.integers(0, 256, (400, 400))          # the strongest corners by far
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    gp = dict(maxCorners=300, qualityLevel=0.0005, minDistance=30, blockSize=3)
+    got = as_corners(ibt.goodFeaturesToTrack(img, **gp))
+    ref = as_corners(oracle.goodFeaturesToTrack(img, **gp))
+    assert got.shape == ref.shape and got.shape[0] == 300
+    assert np.mean(np.all(got == ref, axis=(1, 2))) >= 0.99
+    # more than the patch can hold at this distance: the prefix must have come from the full candidate set
+    inside = (got[:, 0, 0] >= 200) & (got[:, 0, 0] < 600) & (got[:, 0, 1] >= 150) & (got[:, 0, 1] < 550)
+    assert inside.sum() < 300 and (~inside).sum() > 0
+    block = rng.integers(0, 256, (16, 16)).astype(np.uint8)
+    per = np.tile(block, (16, 20))                                    # 256 x 320, exact period 16: exact response ties
+    for gp in (dict(maxCorners=0, qualityLevel=0.01, minDistance=3, blockSize=3),
+               dict(maxCorners=150, qualityLevel=0.01, minDistance=9, blockSize=5)):
+        got = as_corners(ibt.goodFeaturesToTrack(per, **gp))
+        ref = as_corners(oracle.goodFeaturesToTrack(per, **gp))
+        assert got.shape == ref.shape and len(ref) > 50
+        assert np.array_equal(got, ref), gp                            # order included: ties resolved like OpenCV
