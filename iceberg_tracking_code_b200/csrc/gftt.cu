@@ -687,7 +687,9 @@ __device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target)
         target += gridDim.x;
         __threadfence();
         atomicAdd(bar, 1u);
-        while (*reinterpret_cast<volatile uint32_t *>(bar) < target) { }
+        unsigned spins = 0;
+        while (*reinterpret_cast<volatile uint32_t *>(bar) < target)
+            if (++spins > (1u << 28)) __trap();                    // a lost CTA must fail loudly, not hang the GPU
         __threadfence();
     }
     __syncthreads();
@@ -1236,9 +1238,11 @@ IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, in
                           workspace_bytes, out_xy, cap, nullptr, st);
     if (rc) return rc;
     // the one host round trip of the synchronous form: the corner count decides the shapes the caller allocates next
-    struct { uint32_t maxbits, ncand, nsel, nacc, nout; int32_t error; } hc;
-    IBT_CUDA_TRY(cudaMemcpyAsync(&hc, workspace, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    struct Head { uint32_t maxbits, ncand, nsel, nacc, nout; int32_t error; };
+    static thread_local Head *hc = nullptr;                        // page-locked: the copy is a real asynchronous DMA
+    if (!hc) IBT_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&hc), sizeof(Head), cudaHostAllocDefault));
+    IBT_CUDA_TRY(cudaMemcpyAsync(hc, workspace, sizeof(Head), cudaMemcpyDeviceToHost, st));
     IBT_CUDA_TRY(cudaStreamSynchronize(st));
-    *out_count = (int)hc.nout;
-    return hc.error ? hc.error : IBT_OK;
+    *out_count = (int)hc->nout;
+    return hc->error ? hc->error : IBT_OK;
 }
