@@ -161,6 +161,7 @@ constexpr int EN_WARPS = 4;               // warps per CTA (independent of each 
 constexpr int EN_COLS = 128;              // support columns per warp (4 per lane)
 constexpr int EN_CB = 192;                // per-warp candidate buffer (flushed every 8 rows once it holds >= 96 entries)
 constexpr int EN_PAD = 32;                // generic blockSize: padding of the shared row buffer on both sides
+constexpr int EN_MIN_CTAS = 5;            // CTAs of 4 warps per SM the register budget is compiled for
 constexpr int EN_BORDER_SPLIT = 4;        // border strips (byte gathers, ~4x slower per row) get 4x shorter jobs
 
 struct EigNmsArgs {
@@ -418,7 +419,7 @@ __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int 
 }
 
 template <int BS, bool MASK>
-__global__ void __launch_bounds__(EN_WARPS * 32, 4)
+__global__ void __launch_bounds__(EN_WARPS * 32, EN_MIN_CTAS)
 eig_nms_kernel(const __grid_constant__ EigNmsArgs a)
 {
     extern __shared__ __align__(16) int en_smem[];
@@ -483,7 +484,7 @@ static int launch_eig_nms(const uint8_t *gray, int H, int W, int64_t pitch, int 
     // rows per job: one wave of warps over the GPU (warm-up costs bs + 2 rows per job), at least 32 rows (8 for border strips)
     int wps = (int)((227 * 1024) / ((size_t)a.warp_smem_ints * 4 * EN_WARPS + 1024)) * EN_WARPS;       // resident warps per SM
     if (wps < 1) wps = 1;
-    if (wps > 16) wps = 16;                                       // 128 registers per thread
+    if (wps > EN_MIN_CTAS * EN_WARPS) wps = EN_MIN_CTAS * EN_WARPS;   // register budget (launch bounds)
     const int nfast = a.nstrips - a.nborder;
     const int weight = nfast + EN_BORDER_SPLIT * a.nborder;       // jobs per row chunk, border strips count EN_BORDER_SPLIT times
     int chunks = (kNumSMs * wps) / weight;
