@@ -109,6 +109,24 @@ inline bool make_map_2d(CUtensorMap *m, CUtensorMapDataType dt, const void *base
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- programmatic dependent launch (PDL): the kernels of the per-frame chain (gray -> level 0 -> level 1 -> ...) are launched
+// with programmatic stream serialisation: a kernel's CTAs are scheduled and run their prologue while the previous kernel
+// drains, and block in pdl_wait() until that kernel has completed and its writes are visible.  pdl_launch_dependents() at the
+// top of a kernel lets the next launch start as early as possible.  Both are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // gftt.cu: stable LSD radix sort of 64-bit keys on a byte range (also used by grid.cu)
 size_t radix_sort_scratch_words(uint32_t n);
 unsigned long long *radix_sort_u64_bytes(unsigned long long *keys0, unsigned long long *keys1, uint32_t n, int first_byte,

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256)
 gray_c3_vec_kernel(const uint8_t *__restrict__ src, int64_t src_pitch, uint8_t *__restrict__ dst,
                    int64_t dst_pitch, int H, int units_per_row, int64_t total_units, int k0, int k1, int k2)
 {
+    pdl_launch_dependents();                              // (the pyramid launch that follows waits for this grid before it reads)
     for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < total_units;
          u += (int64_t)gridDim.x * blockDim.x) {
         const int y = (int)(u / units_per_row);

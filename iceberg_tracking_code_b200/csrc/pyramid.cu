@@ -190,6 +190,8 @@ pyr_level_kernel(const __grid_constant__ PyrArgs a)
     constexpr int SROWS = NW * RPW + 3;
     __shared__ __align__(16) uint8_t tiles[2][SROWS * SPITCH];
     const int tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();                                           // the source level is the previous launch's output
     int t = blockIdx.x, buf = 0;
     if (t < a.ntiles) stage_tile<NW>(a, t, tiles[0], tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -253,11 +255,13 @@ pyr_level_tma_kernel(const __grid_constant__ PyrArgs a, const __grid_constant__ 
     __shared__ __align__(128) uint8_t tiles[2][TILE_ALLOC];
     __shared__ __align__(8) uint64_t full[2];
     const int tid = threadIdx.x;
+    pdl_launch_dependents();
     if (tid == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();                                           // the source level is the previous launch's output
     auto issue = [&](int t, int b) {                      // one thread: arm the barrier, launch the bulk tensor copy
         if (tid == 0) {
             const int ty = t / a.ntx, tx = t - ty * a.ntx;
@@ -307,10 +311,10 @@ static void launch_variant(const PyrArgs &a0, cudaStream_t st)
     static const bool no_tma = getenv("IBT_NO_TMA") != nullptr;
     CUtensorMap tmap;
     if (!no_tma && a.src_vec_ok && a.h >= 8 && a.w >= 16 && make_tile_map(&tmap, a.src, a.h, a.w, a.pitch, TH + 3)) {
-        pyr_level_tma_kernel<DERIV, DOWN, NW><<<blocks, NW * 32, 0, st>>>(a, tmap);
+        (void)launch_pdl(pyr_level_tma_kernel<DERIV, DOWN, NW>, dim3(blocks), dim3(NW * 32), 0, st, a, tmap);
         return;
     }
-    pyr_level_kernel<DERIV, DOWN, NW><<<blocks, NW * 32, 0, st>>>(a);
+    (void)launch_pdl(pyr_level_kernel<DERIV, DOWN, NW>, dim3(blocks), dim3(NW * 32), 0, st, a);
 }
 
 static int launch_level(const uint8_t *src, int h, int w, int64_t pitch, int16_t *deriv, int64_t dpitch,
