@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(EN_WARPS * 32, EN_MIN_CTAS)
 eig_nms_kernel(const __grid_constant__ EigNmsArgs a)
 {
     extern __shared__ __align__(16) int en_smem[];
+    pdl_launch_dependents();                              // (the selection kernel's CTAs may take their places while this grid drains)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int job = blockIdx.x * EN_WARPS + wib;
     if (job >= a.njobs) return;
@@ -795,6 +796,7 @@ gftt_select_kernel(const __grid_constant__ SelArgs a)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t gtid = blockIdx.x * SEL_THREADS + tid, gsize = gridDim.x * SEL_THREADS;
     uint32_t bar_target = 0;
+    pdl_wait();                                           // candidates, maximum and counters are the previous launch's output
     stamp(cnt, 0);
     const uint32_t mb = __ldcg(&cnt->maxbits);
     const uint32_t ncand = __ldcg(&cnt->ncand);
@@ -1200,7 +1202,7 @@ static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask,
         if (sms < 1 || per_sm < 1) return IBT_E_CUDA;
         sel_grid[dev_id] = sms * per_sm;
     }
-    gftt_select_kernel<<<sel_grid[dev_id], SEL_THREADS, 0, st>>>(a);
+    IBT_CUDA_TRY(launch_pdl(gftt_select_kernel, dim3(sel_grid[dev_id]), dim3(SEL_THREADS), 0, st, a));
     return check_launch("gftt_select_kernel");
 }
 
