@@ -535,6 +535,15 @@ def main():
         pts.append(p.reshape(NPTS, 2).contiguous())
     trk = SequenceTracker(GFTT, LK, count_iterations=True)
     pipe = PairPipeline(trk, dev, frames[0])
+    # the form the frame loop uses (ibt_gftt_async: both launches enqueued, count left on the device, no host round trip)
+    gftt_async_ms = []
+    for k in range(4):
+        t0.record()
+        pf = trk.gftt_prefetch(pipe.pyr[0], None)
+        t1.record(); torch.cuda.synchronize()
+        gftt_async_ms.append(t0.elapsed_time(t1))
+        assert int(pf[2][0]) == NPTS
+        trk._unpin(pf[2])
     if args.no_pipeline:
         pipe.streams[1] = pipe.streams[0]
     nlev = pipe.pyr[0].maxLevel + 1
@@ -731,6 +740,7 @@ def main():
                             "note": "same step with st/err buffers of both passes passed (what cv2 returns, s1:323,326): "
                                     "adds OpenCV's level-0 bounds test and residual"},
         "gftt_ms": float(np.median(gftt_ms)),
+        "gftt_async_ms": float(np.median(gftt_async_ms[1:])),
         "gpu_launches": own_launches_per_step * nsteps,
         "clocks": clocks,
         "e2e_rgb_frames": {"value": world * NPTS * n_e2e / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
