@@ -279,13 +279,24 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
     lk_done = [None] * NS
     redone = [0]
 
+    # the host side of a decode (copy of the file bytes into page-locked memory, marker parsing: ~1 ms) runs on two worker threads
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=2)
+    staged = {}
+
+    def prestage(j):
+        if j not in staged:
+            staged[j] = pool.submit(decs[j & 1].stage, blobs[pingpong(j)])
+
     def stage(j):
         """decode frame j (asynchronously: no host wait) -> gray -> pyramid into pyr[j % NS]; returns (handle, ready event)"""
         d = j & 1
+        prestage(j); prestage(j + 1); prestage(j + 2)
+        sj = staged.pop(j).result()
         with torch.cuda.stream(dstream[d]):
             if lk_done[j % NS] is not None:
                 dstream[d].wait_event(lk_done[j % NS])
-            h = decs[d].decode_async(blobs[pingpong(j)], rgb=False, gray=True)
+            h = decs[d].decode_async(rgb=False, gray=True, staged=sj)
             trk.prepare(h["gray"], reuse=pyr[j % NS])
             ev = torch.cuda.Event()
             ev.record(dstream[d])
@@ -323,6 +334,9 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
                 done[k ^ 1].synchronize()
                 acc += float(h_fbd[k ^ 1][0])
         done[(n - 1) & 1].synchronize()
+        for f in staged.values():                             # frames staged beyond the end of this loop: release their buffers
+            f.result()["slot"]["free"].set()
+        staged.clear()
         return acc + float(h_fbd[(n - 1) & 1][0])
     cv.set_lk_resident_ctas(2)
     try:
@@ -334,6 +348,7 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
         ms = (time.perf_counter() - t0) * 1e3 / steps
     finally:
         cv.set_lk_resident_ctas(0)
+        pool.shutdown(wait=True)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(10):
