@@ -75,6 +75,10 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
                  ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1),
                  "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_map(const CUtensorMap *tmap)     // pull the 128-byte descriptor into the TMA unit's cache
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // host: 2-D tiled tensor map (zero fill outside the tensor); false if the driver entry point or the encode fails

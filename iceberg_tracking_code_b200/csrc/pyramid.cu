@@ -3,10 +3,10 @@
 // cv2.calcOpticalFlowPyrLK repeats on every call (s1_lucaskanade_tracking.py:323,326).
 //
 // HBM-bound: per level-l pixel 1 B is read once, 4 B (int16 dx,dy interleaved) and 1/4 B (level l+1) are written.
-// Persistent CTAs walk over 128 x (16*NW) pixel tiles with a two-stage cp.async pipeline: while the warps filter
+// Persistent CTAs walk over 128 x (RPW*NW) pixel tiles with a two-stage pipeline (TMA, else cp.async): while the warps filter
 // tile t out of one shared-memory buffer, the 16-byte cp.async copies of tile t+1 are in flight into the other
 // (tiles touching the left/right image border take a byte path that resolves REFLECT_101; rows reflect by index).
-// Each lane slides a 4-pixel-wide strip down 16 rows: per row it reads its word and the two neighbouring words and
+// Each lane slides a 4-pixel-wide strip down RPW rows: per row it reads its word and the two neighbouring words and
 // evaluates the horizontal halves of both separable filters with dp4a on funnel-shifted byte windows -- (3,10,3) and
 // (-1,0,1) for Scharr, (1,4,6,4,1) for pyrDown -- so no byte is ever unpacked; the vertical halves run on the per-lane
 // register history of the previous rows.  Each derivative row leaves as one 16-byte store per lane (512 contiguous
@@ -19,7 +19,6 @@
 namespace ibt {
 
 constexpr int TW = 128;                 // tile width  (input pixels)
-constexpr int RPW = 16;                 // rows per warp
 constexpr int HXB = 16;                 // staged bytes left/right of the tile (keeps 16-byte chunks aligned)
 constexpr int SPITCH = TW + 2 * HXB;    // 160 bytes per staged row
 
@@ -32,6 +31,9 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
 }
 __device__ __forceinline__ uint32_t pack_i16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
 
+// resident CTAs per SM the kernels are compiled for: 4-warp CTAs 7 (register-bound), 1-warp CTAs 24
+constexpr int pyr_ctas_per_sm(int nw) { return nw == 4 ? 7 : 24; }
+
 struct PyrArgs {
     const uint8_t *src; int h, w; int64_t pitch;
     uint8_t *deriv; int64_t dpitch;
@@ -42,7 +44,7 @@ struct PyrArgs {
 
 // stage bytes [x0-16, x0+144) of rows y0-2 .. y0+TH into `tile`: every 16-byte chunk that lies inside the row goes
 // as cp.async; the columns left of 0 / right of w-1 are filled in later from shared memory itself (reflect_tile)
-template <int NW>
+template <int NW, int RPW>
 __device__ __forceinline__ void stage_tile(const PyrArgs &a, int t, uint8_t *tile, int tid)
 {
     constexpr int TH = NW * RPW, SROWS = TH + 3, NT = NW * 32;
@@ -72,7 +74,7 @@ __device__ __forceinline__ void stage_tile(const PyrArgs &a, int t, uint8_t *til
 }
 
 // REFLECT_101 columns of a staged tile, from the tile itself: -1 -> 1, -2 -> 2, w+k -> w-2-k.  Returns whether it wrote.
-template <int NW>
+template <int NW, int RPW>
 __device__ __forceinline__ bool reflect_tile(const PyrArgs &a, int t, uint8_t *tile, int tid)
 {
     constexpr int TH = NW * RPW, SROWS = TH + 3, NT = NW * 32;
@@ -103,7 +105,7 @@ __device__ __forceinline__ bool reflect_tile(const PyrArgs &a, int t, uint8_t *t
 }
 
 // FULL: the tile lies completely inside the image (no per-row / per-column bounds checks)
-template <bool DERIV, bool DOWN, int NW, bool FULL>
+template <bool DERIV, bool DOWN, int NW, int RPW, bool FULL>
 __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8_t *tile, int tid)
 {
     constexpr int TH = NW * RPW;
@@ -126,7 +128,7 @@ __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8
     uint8_t *op = DOWN ? a.down + (int64_t)(ybase >> 1) * a.downpitch + (x >> 1) : nullptr;
     const bool dvec = a.down_vec_ok && (FULL || (x >> 1) + 1 < ow);
 #pragma unroll
-    for (int j = 0; j <= RPW + 2; j++) {                 // staged rows ybase-2 .. ybase+16
+    for (int j = 0; j <= RPW + 2; j++) {                 // staged rows ybase-2 .. ybase+RPW
         const uint32_t Lw = trow[j * (SPITCH / 4)], O = trow[j * (SPITCH / 4) + 1], Rw = trow[j * (SPITCH / 4) + 2];
         // byte windows: w0 = (x-1..x+2), O = (x..x+3), w2 = (x+1..x+4), w3 = (x+2..x+5)
         const uint32_t w0 = __funnelshift_r(Lw, O, 24);
@@ -183,8 +185,8 @@ __device__ __forceinline__ void filter_tile(const PyrArgs &a, int t, const uint8
     }
 }
 
-template <bool DERIV, bool DOWN, int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 4 ? 7 : 16)
+template <bool DERIV, bool DOWN, int NW, int RPW>
+__global__ void __launch_bounds__(NW * 32, pyr_ctas_per_sm(NW))
 pyr_level_kernel(const __grid_constant__ PyrArgs a)
 {
     constexpr int SROWS = NW * RPW + 3;
@@ -193,21 +195,21 @@ pyr_level_kernel(const __grid_constant__ PyrArgs a)
     pdl_launch_dependents();
     pdl_wait();                                           // the source level is the previous launch's output
     int t = blockIdx.x, buf = 0;
-    if (t < a.ntiles) stage_tile<NW>(a, t, tiles[0], tid);
+    if (t < a.ntiles) stage_tile<NW, RPW>(a, t, tiles[0], tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (; t < a.ntiles; t += gridDim.x) {
         const int tn = t + gridDim.x;
-        if (tn < a.ntiles) stage_tile<NW>(a, tn, tiles[buf ^ 1], tid);       // prefetch the next tile of this CTA
+        if (tn < a.ntiles) stage_tile<NW, RPW>(a, tn, tiles[buf ^ 1], tid);       // prefetch the next tile of this CTA
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");                  // tile t has landed
         __syncthreads();
-        if (reflect_tile<NW>(a, t, tiles[buf], tid)) __syncthreads();
+        if (reflect_tile<NW, RPW>(a, t, tiles[buf], tid)) __syncthreads();
         {
             constexpr int TH = NW * RPW;
             const int ty = t / a.ntx, tx = t - ty * a.ntx;
             const bool full = (tx + 1) * TW <= a.w && (ty + 1) * TH <= a.h;
-            if (full) filter_tile<DERIV, DOWN, NW, true>(a, t, tiles[buf], tid);
-            else filter_tile<DERIV, DOWN, NW, false>(a, t, tiles[buf], tid);
+            if (full) filter_tile<DERIV, DOWN, NW, RPW, true>(a, t, tiles[buf], tid);
+            else filter_tile<DERIV, DOWN, NW, RPW, false>(a, t, tiles[buf], tid);
         }
         __syncthreads();                                                      // buffer may be refilled next round
         buf ^= 1;
@@ -221,7 +223,7 @@ pyr_level_kernel(const __grid_constant__ PyrArgs a)
 // tensor map covers the w x h image; coordinates left / above / right / below it come back as zeros and the
 // REFLECT_101 rows and columns are then patched from the tile itself.
 // REFLECT_101 rows of a TMA-staged tile (zeros outside the image): rows -2, -1 and h, h+1, copied inside the tile.
-template <int NW>
+template <int NW, int RPW>
 __device__ __forceinline__ bool reflect_rows(const PyrArgs &a, int t, uint8_t *tile, int tid)
 {
     constexpr int TH = NW * RPW, SROWS = TH + 3, NT = NW * 32;
@@ -245,8 +247,8 @@ __device__ __forceinline__ bool reflect_rows(const PyrArgs &a, int t, uint8_t *t
     return true;
 }
 
-template <bool DERIV, bool DOWN, int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 4 ? 7 : 16)
+template <bool DERIV, bool DOWN, int NW, int RPW>
+__global__ void __launch_bounds__(NW * 32, pyr_ctas_per_sm(NW))
 pyr_level_tma_kernel(const __grid_constant__ PyrArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int TH = NW * RPW, SROWS = TH + 3;
@@ -257,6 +259,7 @@ pyr_level_tma_kernel(const __grid_constant__ PyrArgs a, const __grid_constant__ 
     const int tid = threadIdx.x;
     pdl_launch_dependents();
     if (tid == 0) {
+        tma_prefetch_map(&tmap);                          // the descriptor does not depend on the previous launch
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -278,13 +281,13 @@ pyr_level_tma_kernel(const __grid_constant__ PyrArgs a, const __grid_constant__ 
         if (tn < a.ntiles) issue(tn, buf ^ 1);                                // prefetch the next tile of this CTA
         mbar_wait(&full[buf], (phases >> buf) & 1u);                          // tile t has landed
         phases ^= 1u << buf;
-        if (reflect_rows<NW>(a, t, tiles[buf], tid)) __syncthreads();
-        if (reflect_tile<NW>(a, t, tiles[buf], tid)) __syncthreads();
+        if (reflect_rows<NW, RPW>(a, t, tiles[buf], tid)) __syncthreads();
+        if (reflect_tile<NW, RPW>(a, t, tiles[buf], tid)) __syncthreads();
         {
             const int ty = t / a.ntx, tx = t - ty * a.ntx;
             const bool fullt = (tx + 1) * TW <= a.w && (ty + 1) * TH <= a.h;
-            if (fullt) filter_tile<DERIV, DOWN, NW, true>(a, t, tiles[buf], tid);
-            else filter_tile<DERIV, DOWN, NW, false>(a, t, tiles[buf], tid);
+            if (fullt) filter_tile<DERIV, DOWN, NW, RPW, true>(a, t, tiles[buf], tid);
+            else filter_tile<DERIV, DOWN, NW, RPW, false>(a, t, tiles[buf], tid);
         }
         __syncthreads();                                                      // buffer may be refilled next round
         buf ^= 1;
@@ -296,7 +299,7 @@ static bool make_tile_map(CUtensorMap *m, const uint8_t *src, int h, int w, int6
     return make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, src, w, h, pitch, SPITCH, srows);
 }
 
-template <bool DERIV, bool DOWN, int NW>
+template <bool DERIV, bool DOWN, int NW, int RPW>
 static void launch_variant(const PyrArgs &a0, cudaStream_t st)
 {
     PyrArgs a = a0;
@@ -304,17 +307,17 @@ static void launch_variant(const PyrArgs &a0, cudaStream_t st)
     a.ntx = (a.w + TW - 1) / TW;
     a.ntiles = a.ntx * ((a.h + TH - 1) / TH);
     // persistent CTAs, every CTA the same number of tiles: no partial last wave
-    const int resident = kNumSMs * (NW == 4 ? 7 : 16);
+    const int resident = kNumSMs * pyr_ctas_per_sm(NW);
     const int per_cta = (a.ntiles + resident - 1) / resident;
     const int blocks = (a.ntiles + per_cta - 1) / per_cta;
     // TMA staging needs a 16-byte aligned image and enough rows / columns for the in-tile reflections
     static const bool no_tma = getenv("IBT_NO_TMA") != nullptr;
     CUtensorMap tmap;
     if (!no_tma && a.src_vec_ok && a.h >= 8 && a.w >= 16 && make_tile_map(&tmap, a.src, a.h, a.w, a.pitch, TH + 3)) {
-        (void)launch_pdl(pyr_level_tma_kernel<DERIV, DOWN, NW>, dim3(blocks), dim3(NW * 32), 0, st, a, tmap);
+        (void)launch_pdl(pyr_level_tma_kernel<DERIV, DOWN, NW, RPW>, dim3(blocks), dim3(NW * 32), 0, st, a, tmap);
         return;
     }
-    (void)launch_pdl(pyr_level_kernel<DERIV, DOWN, NW>, dim3(blocks), dim3(NW * 32), 0, st, a);
+    (void)launch_pdl(pyr_level_kernel<DERIV, DOWN, NW, RPW>, dim3(blocks), dim3(NW * 32), 0, st, a);
 }
 
 static int launch_level(const uint8_t *src, int h, int w, int64_t pitch, int16_t *deriv, int64_t dpitch,
@@ -333,11 +336,12 @@ static int launch_level(const uint8_t *src, int h, int w, int64_t pitch, int16_t
     a.deriv_vec_ok = deriv && (reinterpret_cast<uintptr_t>(deriv) % 16 == 0) && (dpitch % 16 == 0);
     a.down_vec_ok = down && (reinterpret_cast<uintptr_t>(down) % 2 == 0) && (downpitch % 2 == 0);
     a.ntx = a.ntiles = 0;
-    // big levels: 128 x 64 tiles (4 warps); small levels: 128 x 16 tiles (1 warp) so that they still spread over the SMs
+    // big levels: 128 x 64 tiles (4 warps x 16 rows).  Smaller levels are latency-bound -- a launch lasts as long as one warp
+    // needs for its rows -- so they take 1-warp tiles of 4 rows: every SM gets work and no warp walks more than 7 rows
     const bool big = (int64_t)((w + TW - 1) / TW) * ((h + 63) / 64) >= 2 * kNumSMs;
-    if (deriv && down) { if (big) launch_variant<true, true, 4>(a, st); else launch_variant<true, true, 1>(a, st); }
-    else if (deriv)    { if (big) launch_variant<true, false, 4>(a, st); else launch_variant<true, false, 1>(a, st); }
-    else               { if (big) launch_variant<false, true, 4>(a, st); else launch_variant<false, true, 1>(a, st); }
+    if (deriv && down) { if (big) launch_variant<true, true, 4, 16>(a, st); else launch_variant<true, true, 1, 4>(a, st); }
+    else if (deriv)    { if (big) launch_variant<true, false, 4, 16>(a, st); else launch_variant<true, false, 1, 4>(a, st); }
+    else               { if (big) launch_variant<false, true, 4, 16>(a, st); else launch_variant<false, true, 1, 4>(a, st); }
     return check_launch("ibt_pyr_level_u8");
 }
 
