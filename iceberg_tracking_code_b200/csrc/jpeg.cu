@@ -613,6 +613,196 @@ __global__ void __launch_bounds__(256) jpg_color(const __grid_constant__ JpgGeom
     }
 }
 
+// ---- save-and-reopen round trip of the cropping pre-pass (camtools.py:80,102,232 -> s1:310) ----------------------------------
+// `img_crop.save(outpath)` re-encodes every cropped frame with Pillow's defaults (libjpeg-turbo: quality 75, 4:2:0, islow DCT)
+// and the tracking loop reads that file back.  Entropy coding is lossless, so the pixels the reference tracks are
+//   decode( quantise( FDCT( downsample( RGB->YCbCr( crop ))))).
+// jpg_enc_planes: jccolor.c rgb_ycc_convert (16-bit fixed point) + jcsample.c box filters (alternating bias) with libjpeg's edge
+//                 replication (jcprepct.c / expand_right_edge), written straight into the decoder's plane layout;
+// jpg_enc_requant: one thread per 8x8 block, in place: jfdctint.c forward DCT, jcdctmgr.c quantisation (divisor 8q, magnitude
+//                 rounded half up), dequantisation and the islow inverse DCT of jpg_idct;
+// then the decoder's own jpg_color kernel (fancy upsampling, YCbCr->RGB, gray).
+struct JpgEncQ {
+    uint16_t q[2][64];                    // luma / chroma tables, natural order
+    uint32_t magic[2][64];                // floor(2^32 / (8 q)) + 1: exact quotients for numerators < 2^20
+};
+
+// 8 RGB pixels of row `row` (already clamped) starting at column x0; columns past W - 1 replicate the last one
+__device__ __forceinline__ void enc_load8(const uint8_t *__restrict__ rgb, int64_t pitch, int row, int x0, int W, uint32_t *px)
+{
+    const uint8_t *p = rgb + (size_t)row * pitch + (size_t)x0 * 3;
+    if (x0 + 10 <= W) {                                          // the 28 bytes of the seven aligned words stay inside the row
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+        uint32_t v[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) v[j] = __ldg(w + j);
+        uint32_t b[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) b[j] = __funnelshift_r(v[j], v[j + 1], sh);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {                             // pixel j = bytes 3j .. 3j+2 of the 24
+            const int o = 3 * j, wi = o >> 2, bi = (o & 3) * 8;
+            const uint32_t t = bi == 0 ? b[wi] : __funnelshift_r(b[wi], wi + 1 < 6 ? b[wi + 1] : 0u, bi);
+            px[j] = t & 0xffffffu;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint8_t *q = rgb + (size_t)row * pitch + (size_t)min(x0 + j, W - 1) * 3;
+            px[j] = (uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16;
+        }
+    }
+}
+__device__ __forceinline__ void enc_ycc(uint32_t p, int &Y, int &Cb, int &Cr)
+{
+    const int r = p & 255, g = (p >> 8) & 255, b = (p >> 16) & 255;
+    Y = (19595 * r + 38470 * g + 7471 * b + 32768) >> 16;
+    Cb = (-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16;
+    Cr = (32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16;
+}
+
+// thread = 8 luma columns x VS luma rows (one chroma row); grid.y = chroma plane rows
+template <int HS, int VS>
+__global__ void __launch_bounds__(256) jpg_enc_planes(const uint8_t *__restrict__ rgb, int64_t pitch, const __grid_constant__ JpgGeom G)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int gy = blockIdx.y;
+    if (x0 >= G.pw[0]) return;
+    const int W = G.W, H = G.H;
+    // chroma row gy: rows past the last real row group copy that group (jcprepct.c pads the DOWNSAMPLED rows)
+    const int ce = min(gy, G.dh[1] - 1);
+    int cb[VS][8], cr[VS][8], yy[VS][8];
+    int srow[VS];
+#pragma unroll
+    for (int r = 0; r < VS; r++) {
+        srow[r] = min(VS * ce + r, H - 1);
+        uint32_t px[8];
+        enc_load8(rgb, pitch, srow[r], x0, W, px);
+#pragma unroll
+        for (int j = 0; j < 8; j++) enc_ycc(px[j], yy[r][j], cb[r][j], cr[r][j]);
+    }
+    // luma rows VS*gy + r take source row min(VS*gy + r, H - 1): the same rows except in the padding below an even-height image
+#pragma unroll
+    for (int r = 0; r < VS; r++) {
+        const int lrow = min(VS * gy + r, H - 1);
+        if (lrow != srow[r]) {
+            uint32_t px[8];
+            enc_load8(rgb, pitch, lrow, x0, W, px);
+            int d0, d1;
+#pragma unroll
+            for (int j = 0; j < 8; j++) enc_ycc(px[j], yy[r][j], d0, d1);
+        }
+        uint2 o;
+        o.x = (uint32_t)yy[r][0] | (uint32_t)yy[r][1] << 8 | (uint32_t)yy[r][2] << 16 | (uint32_t)yy[r][3] << 24;
+        o.y = (uint32_t)yy[r][4] | (uint32_t)yy[r][5] << 8 | (uint32_t)yy[r][6] << 16 | (uint32_t)yy[r][7] << 24;
+        *reinterpret_cast<uint2 *>(G.plane[0] + (size_t)(VS * gy + r) * G.pw[0] + x0) = o;
+    }
+    if (HS == 1) {
+        uint2 ob, orr;
+        ob.x = (uint32_t)cb[0][0] | (uint32_t)cb[0][1] << 8 | (uint32_t)cb[0][2] << 16 | (uint32_t)cb[0][3] << 24;
+        ob.y = (uint32_t)cb[0][4] | (uint32_t)cb[0][5] << 8 | (uint32_t)cb[0][6] << 16 | (uint32_t)cb[0][7] << 24;
+        orr.x = (uint32_t)cr[0][0] | (uint32_t)cr[0][1] << 8 | (uint32_t)cr[0][2] << 16 | (uint32_t)cr[0][3] << 24;
+        orr.y = (uint32_t)cr[0][4] | (uint32_t)cr[0][5] << 8 | (uint32_t)cr[0][6] << 16 | (uint32_t)cr[0][7] << 24;
+        *reinterpret_cast<uint2 *>(G.plane[1] + (size_t)gy * G.pw[1] + x0) = ob;
+        *reinterpret_cast<uint2 *>(G.plane[2] + (size_t)gy * G.pw[2] + x0) = orr;
+    } else {
+        uint32_t ob = 0, orr = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                             // chroma column x0/2 + j: bias 1,2,1,2 (h2v2) / 0,1,0,1 (h2v1)
+            int sb = cb[0][2 * j] + cb[0][2 * j + 1], sr = cr[0][2 * j] + cr[0][2 * j + 1];
+            if (VS == 2) {
+                sb += cb[VS - 1][2 * j] + cb[VS - 1][2 * j + 1] + 1 + (j & 1);
+                sr += cr[VS - 1][2 * j] + cr[VS - 1][2 * j + 1] + 1 + (j & 1);
+                sb >>= 2; sr >>= 2;
+            } else {
+                sb = (sb + (j & 1)) >> 1; sr = (sr + (j & 1)) >> 1;
+            }
+            ob |= (uint32_t)sb << (8 * j);
+            orr |= (uint32_t)sr << (8 * j);
+        }
+        *reinterpret_cast<uint32_t *>(G.plane[1] + (size_t)gy * G.pw[1] + (x0 >> 1)) = ob;
+        *reinterpret_cast<uint32_t *>(G.plane[2] + (size_t)gy * G.pw[2] + (x0 >> 1)) = orr;
+    }
+}
+
+// jfdctint.c, one 8-point pass.  PASS 1: rows, outputs scaled up by 2^PASS1_BITS; PASS 2: columns, scaled back (overall x8)
+template <int PASS>
+__device__ __forceinline__ void fdct8(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7)
+{
+    const int t0 = d0 + d7, t7 = d0 - d7, t1 = d1 + d6, t6 = d1 - d6, t2 = d2 + d5, t5 = d2 - d5, t3 = d3 + d4, t4 = d3 - d4;
+    const int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    constexpr int SH = PASS == 1 ? 11 : 15, R = 1 << (SH - 1);
+    if (PASS == 1) { d0 = (t10 + t11) * 4; d4 = (t10 - t11) * 4; }
+    else { d0 = (t10 + t11 + 2) >> 2; d4 = (t10 - t11 + 2) >> 2; }
+    int z1 = (t12 + t13) * 4433;
+    d2 = (z1 + t13 * 6270 + R) >> SH;
+    d6 = (z1 + t12 * (-15137) + R) >> SH;
+    z1 = t4 + t7;
+    int z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
+    const int z5 = (z3 + z4) * 9633;
+    const int a4 = t4 * 2446, a5 = t5 * 16819, a6 = t6 * 25172, a7 = t7 * 12299;
+    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+    z3 += z5; z4 += z5;
+    d7 = (a4 + z1 + z3 + R) >> SH;
+    d5 = (a5 + z2 + z4 + R) >> SH;
+    d3 = (a6 + z2 + z3 + R) >> SH;
+    d1 = (a7 + z1 + z4 + R) >> SH;
+}
+
+__global__ void __launch_bounds__(128) jpg_enc_requant(const __grid_constant__ JpgGeom G, const __grid_constant__ JpgEncQ Q, int total_blocks)
+{
+    __shared__ int sq[2][64];
+    __shared__ uint32_t sm[2][64];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) { sq[i >> 6][i & 63] = Q.q[i >> 6][i & 63]; sm[i >> 6][i & 63] = Q.magic[i >> 6][i & 63]; }
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_blocks) return;
+    int c = 0;
+    while (c < G.ncomp - 1 && t >= G.bw[c] * G.bh[c]) { t -= G.bw[c] * G.bh[c]; c++; }
+    const int by = t / G.bw[c], bx = t - by * G.bw[c];
+    const int tq = c ? 1 : 0;
+    uint8_t *blk = G.plane[c] + (size_t)by * 8 * G.pw[c] + bx * 8;
+    int w[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(blk + (size_t)r * G.pw[c]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            w[r * 8 + j] = (int)((v.x >> (8 * j)) & 255u) - 128;
+            w[r * 8 + 4 + j] = (int)((v.y >> (8 * j)) & 255u) - 128;
+        }
+        fdct8<1>(w[r * 8], w[r * 8 + 1], w[r * 8 + 2], w[r * 8 + 3], w[r * 8 + 4], w[r * 8 + 5], w[r * 8 + 6], w[r * 8 + 7]);
+    }
+    int ws[64];
+#pragma unroll
+    for (int col = 0; col < 8; col++) {
+        fdct8<2>(w[col], w[8 + col], w[16 + col], w[24 + col], w[32 + col], w[40 + col], w[48 + col], w[56 + col]);
+        // quantise (magnitude + half the divisor, truncating division by 8q) and dequantise
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int i = r * 8 + col, q = sq[tq][i], v = w[i];
+            const uint32_t a = (uint32_t)abs(v) + (uint32_t)(q * 4);
+            const int m = (int)__umulhi(a, sm[tq][i]) * q;
+            w[i] = v < 0 ? -m : m;
+        }
+        int o[8];
+        idct8<11>(w[col], w[8 + col], w[16 + col], w[24 + col], w[32 + col], w[40 + col], w[48 + col], w[56 + col], o);
+#pragma unroll
+        for (int r = 0; r < 8; r++) ws[r * 8 + col] = o[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int o[8];
+        idct8<18>(ws[r * 8], ws[r * 8 + 1], ws[r * 8 + 2], ws[r * 8 + 3], ws[r * 8 + 4], ws[r * 8 + 5], ws[r * 8 + 6], ws[r * 8 + 7], o);
+        uint2 px;
+        px.x = sat_u8(o[0] + 128) | sat_u8(o[1] + 128) << 8 | sat_u8(o[2] + 128) << 16 | sat_u8(o[3] + 128) << 24;
+        px.y = sat_u8(o[4] + 128) | sat_u8(o[5] + 128) << 8 | sat_u8(o[6] + 128) << 16 | sat_u8(o[7] + 128) << 24;
+        *reinterpret_cast<uint2 *>(blk + (size_t)r * G.pw[c]) = px;
+    }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------------
 static const uint8_t h_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
@@ -750,6 +940,20 @@ static int build_tables(const ibt_jpeg_info_t *I, const JpgGeom &G, JpgTables &T
             T.compmap |= (uint32_t)c << (2 * (G.blkoff[c] + j));
         }
     return IBT_OK;
+}
+
+// geometry of the file Pillow would write for a W x H RGB image with luma sampling hs x vs
+static void recompress_layout(int W, int H, int hs, int vs, JpgLayout &L)
+{
+    ibt_jpeg_info_t I;
+    memset(&I, 0, sizeof(I));
+    I.width = W; I.height = H; I.ncomp = 3;
+    I.hsamp[0] = hs; I.vsamp[0] = vs; I.hsamp[1] = I.vsamp[1] = I.hsamp[2] = I.vsamp[2] = 1;
+    I.scan_bytes = 1;
+    jpeg_layout(&I, L);
+    size_t o = 0;
+    for (int c = 0; c < 3; c++) { L.off_plane[c] = o; o += ((size_t)L.G.pw[c] * L.G.ph[c] + 255) & ~(size_t)255; }
+    L.total = o;
 }
 
 } // namespace ibt
@@ -1011,4 +1215,80 @@ IBT_API int ibt_jpeg_decode_async(const uint8_t *d_file, const ibt_jpeg_info_t *
     if (rounds < 1 || !h_pinned || h_pinned_bytes < ibt_jpeg_async_host_bytes()) return IBT_E_INVALID;
     return jpeg_decode_impl(d_file, I, d_ws, ws_bytes, d_rgb, rgb_pitch, d_gray, gray_pitch, coeffset, nullptr, rounds,
                             static_cast<uint8_t *>(h_pinned), stream);
+}
+
+// ---- ibt_jpeg_recompress --------------------------------------------------------------------------------------------------
+static const uint8_t k_std_luma_q[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                                         14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                                         18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                                         49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+static const uint8_t k_std_chroma_q[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                           24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                                           99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                           99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+
+static bool recompress_args_ok(int W, int H, int hs, int vs)
+{
+    if (W <= 0 || H <= 0 || W > 65535 || H > 65535) return false;
+    return (hs == 1 && vs == 1) || (hs == 2 && vs == 1) || (hs == 2 && vs == 2);
+}
+
+IBT_API int64_t ibt_jpeg_recompress_workspace_bytes(int width, int height, int hsamp, int vsamp)
+{
+    if (!recompress_args_ok(width, height, hsamp, vsamp)) return 0;
+    ibt::JpgLayout L;
+    ibt::recompress_layout(width, height, hsamp, vsamp, L);
+    return (int64_t)L.total;
+}
+
+IBT_API int ibt_jpeg_recompress(const uint8_t *d_rgb_in, int64_t in_pitch, int width, int height, int quality, int hsamp, int vsamp,
+                                void *d_ws, int64_t ws_bytes, uint8_t *d_rgb, int64_t rgb_pitch, uint8_t *d_gray, int64_t gray_pitch,
+                                int coeffset, void *stream)
+{
+    using namespace ibt;
+    if (!recompress_args_ok(width, height, hsamp, vsamp)) return IBT_E_INVALID;
+    if (!d_rgb_in || !d_ws || (!d_rgb && !d_gray) || in_pitch < (int64_t)width * 3) return IBT_E_INVALID;
+    if (d_rgb && rgb_pitch < (int64_t)width * 3) return IBT_E_INVALID;
+    if (d_gray && gray_pitch < width) return IBT_E_INVALID;
+    if (coeffset != IBT_GRAY_CV4_15BIT && coeffset != IBT_GRAY_CV3_14BIT) return IBT_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(d_ws) % 256 != 0) return IBT_E_INVALID;
+    static thread_local JpgLayout L;
+    recompress_layout(width, height, hsamp, vsamp, L);
+    if ((size_t)ws_bytes < L.total) return IBT_E_WORKSPACE;
+    // jcparam.c: jpeg_quality_scaling + jpeg_add_quant_table(force_baseline)
+    if (quality <= 0) quality = 1;
+    if (quality > 100) quality = 100;
+    const int scale = quality < 50 ? 5000 / quality : 200 - quality * 2;
+    JpgEncQ Q;
+    for (int t = 0; t < 2; t++)
+        for (int i = 0; i < 64; i++) {
+            long v = ((long)(t ? k_std_chroma_q[i] : k_std_luma_q[i]) * scale + 50) / 100;
+            v = v < 1 ? 1 : (v > 255 ? 255 : v);
+            Q.q[t][i] = (uint16_t)v;
+            Q.magic[t][i] = (uint32_t)(0x100000000ull / (unsigned long long)(v * 8)) + 1u;
+            L.G.quant[t][i] = (uint16_t)v;
+        }
+    for (int i = 0; i < 64; i++) L.G.quant[2][i] = L.G.quant[1][i];
+    uint8_t *ws = static_cast<uint8_t *>(d_ws);
+    for (int c = 0; c < 3; c++) L.G.plane[c] = ws + L.off_plane[c];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 pgrid((unsigned)((L.G.pw[0] / 8 + 255) / 256), (unsigned)L.G.ph[1]);
+    if (hsamp == 1) jpg_enc_planes<1, 1><<<pgrid, 256, 0, st>>>(d_rgb_in, in_pitch, L.G);
+    else if (vsamp == 1) jpg_enc_planes<2, 1><<<pgrid, 256, 0, st>>>(d_rgb_in, in_pitch, L.G);
+    else jpg_enc_planes<2, 2><<<pgrid, 256, 0, st>>>(d_rgb_in, in_pitch, L.G);
+    int total_blocks = 0;
+    for (int c = 0; c < 3; c++) total_blocks += L.G.bw[c] * L.G.bh[c];
+    jpg_enc_requant<<<(total_blocks + 127) / 128, 128, 0, st>>>(L.G, Q, total_blocks);
+    const dim3 cgrid((unsigned)((width + 8 * 256 - 1) / (8 * 256)), (unsigned)height);
+    const int mode = hsamp == 1 ? 1 : (vsamp == 1 ? 2 : 3);
+#define IBT_JPG_COLOR(SH, K0, K1, K2)                                                                                              \
+    switch (mode) {                                                                                                                \
+    case 1: jpg_color<SH, 3, 1, 1><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, K0, K1, K2); break;           \
+    case 2: jpg_color<SH, 3, 2, 1><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, K0, K1, K2); break;           \
+    default: jpg_color<SH, 3, 2, 2><<<cgrid, 256, 0, st>>>(L.G, d_rgb, rgb_pitch, d_gray, gray_pitch, K0, K1, K2); break;          \
+    }
+    if (coeffset == IBT_GRAY_CV4_15BIT) { IBT_JPG_COLOR(15, 3735, 19235, 9798) }
+    else { IBT_JPG_COLOR(14, 1868, 9617, 4899) }
+#undef IBT_JPG_COLOR
+    return check_launch("ibt_jpeg_recompress");
 }

@@ -22,6 +22,9 @@ from . import _native as N
 from . import cv
 
 
+SUBSAMPLING = {"4:4:4": (1, 1), "4:2:2": (2, 1), "4:2:0": (2, 2), 0: (1, 1), 1: (2, 1), 2: (2, 2)}     # Image.save(subsampling=)
+
+
 class Unsupported(ValueError):
     """A valid JPEG this decoder does not handle (IBT_E_UNSUPPORTED)."""
 
@@ -104,6 +107,31 @@ class JpegDecoder:
             self.last_rounds = rounds.value
         return out_rgb, out_gray
 
+
+    def recompress(self, rgb_in, quality=75, subsampling="4:2:0", rgb=True, gray=False, coeffset=0):
+        """What np.array(Image.open(f)) holds after Image.fromarray(rgb_in).save(f, quality=, subsampling=) -- the
+        save-and-reopen round trip of the reference's cropping pre-pass (imports/camtools.py:80,102,232 -> s1:310), bit-exact,
+        without the file (ibt_jpeg_recompress).  rgb_in: (H,W,3) u8 CUDA tensor, may be a crop VIEW of a decoded frame (last two
+        strides (3, 1)).  Pillow's defaults are the defaults.  Returns (rgb, gray) like decode(); asynchronous on the current stream."""
+        hs, vs = SUBSAMPLING[subsampling]
+        if rgb_in.dim() != 3 or rgb_in.shape[2] != 3 or rgb_in.dtype != torch.uint8 or not rgb_in.is_cuda:
+            raise ValueError("recompress: (H,W,3) u8 CUDA tensor expected")
+        if rgb_in.stride(2) != 1 or rgb_in.stride(1) != 3:
+            rgb_in = rgb_in.contiguous()
+        H, W = int(rgb_in.shape[0]), int(rgb_in.shape[1])
+        need = N.lib().ibt_jpeg_recompress_workspace_bytes(W, H, hs, vs)
+        if need <= 0:
+            raise ValueError("recompress: image size / subsampling not handled")
+        with torch.cuda.device(self.device):
+            ws = getattr(self, "_ws_enc", None)
+            if ws is None or ws.numel() < need:
+                ws = self._ws_enc = torch.empty((int(need * 1.1) + 256,), dtype=torch.uint8, device=self.device)
+            out_rgb = torch.empty((H, W, 3), dtype=torch.uint8, device=self.device) if rgb else None
+            out_gray = torch.empty((H, W), dtype=torch.uint8, device=self.device) if gray else None
+            N.check(N.lib().ibt_jpeg_recompress(cv._ptr(rgb_in), int(rgb_in.stride(0)), W, H, int(quality), hs, vs, cv._ptr(ws),
+                                                ws.numel(), cv._ptr(out_rgb), W * 3, cv._ptr(out_gray), W, int(coeffset),
+                                                cv._stream()), "ibt_jpeg_recompress")
+        return out_rgb, out_gray
 
     # -- staging on a helper thread: file read, copy into page-locked memory and marker parsing cost ~2 ms of host time per
     # 24 MP frame -- more than the GPU needs for the frame -- so the frame loop runs them ahead on worker threads --------------
@@ -231,3 +259,13 @@ def imread(src, gray=False, device=None, coeffset=0):
             src = f.read()
     r, g = _decoder(device).decode(src, rgb=not gray, gray=gray, coeffset=coeffset)
     return g if (gray or r is None) else r
+
+
+def save_reopen(rgb, quality=75, subsampling="4:2:0", gray=False, device=None, coeffset=0):
+    """np.array(Image.open(f)) after Image.fromarray(rgb).save(f) (the reference's crop_image_standalone + s1:310), computed
+    on the GPU without the file.  rgb: (H,W,3) u8 CUDA tensor or numpy array.  gray=True: the cvtColor plane of the result."""
+    dec = _decoder(device)
+    if isinstance(rgb, np.ndarray):
+        rgb = torch.from_numpy(np.ascontiguousarray(rgb)).to(dec.device)
+    r, g = dec.recompress(rgb, quality, subsampling, rgb=not gray, gray=gray, coeffset=coeffset)
+    return g if gray else r

@@ -217,6 +217,21 @@ int ibt_jpeg_decode_async(const uint8_t *d_file, const ibt_jpeg_info_t *info, vo
                           uint8_t *rgb, int64_t rgb_pitch, uint8_t *gray, int64_t gray_pitch, int coeffset, int rounds,
                           void *h_pinned, int64_t h_pinned_bytes, void *stream);
 
+/* ---- the save-and-reopen round trip of the reference's cropping pre-pass, without the files:
+ *      `img_crop.save(outpath)` (imports/camtools.py:80,102,232 via crop_image_parallel, s1_lucaskanade_tracking.py:272)
+ *      followed by `np.array(Image.open(image))` (s1:310; + the cv2.cvtColor of s1:311 fused).  Pillow's save re-encodes the
+ *      crop with libjpeg-turbo (defaults: quality 75, 4:2:0, islow DCT); entropy coding is lossless, so the pixels the
+ *      reference tracks are decode(quantise(FDCT(downsample(RGB->YCbCr(crop))))) -- computed here bit-exactly as pure integer
+ *      work on the GPU, which removes the ~0.3 s per 24 MP frame host pre-pass without changing a pixel.
+ *      rgb_in: DEVICE (height, width, 3) u8 with row pitch in_pitch bytes, any alignment (a crop VIEW of a decoded frame).
+ *      quality 1..100 as Image.save(quality=); hsamp x vsamp = luma sampling 2x2 (4:2:0, Pillow's default), 2x1, 1x1.
+ *      workspace: 256-byte aligned, ibt_jpeg_recompress_workspace_bytes().  rgb / gray / coeffset as ibt_jpeg_decode.
+ *      Asynchronous on `stream`. */
+int64_t ibt_jpeg_recompress_workspace_bytes(int width, int height, int hsamp, int vsamp);
+int ibt_jpeg_recompress(const uint8_t *rgb_in, int64_t in_pitch, int width, int height, int quality, int hsamp, int vsamp,
+                        void *workspace, int64_t workspace_bytes, uint8_t *rgb, int64_t rgb_pitch, uint8_t *gray,
+                        int64_t gray_pitch, int coeffset, void *stream);
+
 /* ---- s3 consumer: the cell-binning loop of s3_utm_to_gridded_utm.py:391-421 over the square grid of
  *      imports/tracking_misc.py:25-58.  Cell (i, j), i < cols, j < rows, is the square with top-left corner
  *      (topleft_x + i*spacing, topleft_y - j*spacing); membership is matplotlib.path.Path(poly).contains_points (radius 0).

@@ -343,6 +343,24 @@ static int chroma_at(const jpg_t *J, const comp_t *c, int x, int y)
     return (3 * cs + os + ((x & 1) ? 7 : 8)) >> 4;
 }
 
+/* planes -> (H, W, 3) RGB u8 / (H, W) u8: fancy upsampling + jdcolor.c */
+static void emit_pixels(const jpg_t *J, uint8_t *out)
+{
+    if (J->nc == 1) {
+        for (int y = 0; y < J->H; y++) memcpy(out + (size_t)y * J->W, J->c[0].plane + (size_t)y * J->c[0].pw, J->W);
+        return;
+    }
+    for (int y = 0; y < J->H; y++)
+        for (int x = 0; x < J->W; x++) {
+            const int Y = J->c[0].plane[(size_t)y * J->c[0].pw + x];
+            const int cb = chroma_at(J, &J->c[1], x, y) - 128, cr = chroma_at(J, &J->c[2], x, y) - 128;
+            uint8_t *o = out + ((size_t)y * J->W + x) * 3;
+            o[0] = sat8(Y + ((91881 * cr + 32768) >> 16));
+            o[1] = sat8(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
+            o[2] = sat8(Y + ((116130 * cb + 32768) >> 16));
+        }
+}
+
 int orc_jpeg_info(const uint8_t *file, long n, int *W, int *H, int *nc)
 {
     jpg_t J;
@@ -363,21 +381,151 @@ int orc_jpeg_decode(const uint8_t *file, long n, uint8_t *out)
         if (!J.c[i].plane) return ORC_JPEG_E_FORMAT;
     }
     rc = decode_scan(&J);
-    if (rc == ORC_JPEG_OK) {
-        if (J.nc == 1) {
-            for (int y = 0; y < J.H; y++) memcpy(out + (size_t)y * J.W, J.c[0].plane + (size_t)y * J.c[0].pw, J.W);
-        } else {
-            for (int y = 0; y < J.H; y++)
-                for (int x = 0; x < J.W; x++) {
-                    const int Y = J.c[0].plane[(size_t)y * J.c[0].pw + x];
-                    const int cb = chroma_at(&J, &J.c[1], x, y) - 128, cr = chroma_at(&J, &J.c[2], x, y) - 128;
-                    uint8_t *o = out + ((size_t)y * J.W + x) * 3;
-                    o[0] = sat8(Y + ((91881 * cr + 32768) >> 16));
-                    o[1] = sat8(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
-                    o[2] = sat8(Y + ((116130 * cb + 32768) >> 16));
-                }
-        }
-    }
+    if (rc == ORC_JPEG_OK) emit_pixels(&J, out);
     for (int i = 0; i < J.nc; i++) free(J.c[i].plane);
     return rc;
+}
+
+/* ================================================================================================================
+ * Save-and-reopen round trip of the reference's cropping pre-pass: `img_crop.save(outpath)` (imports/camtools.py:80,102,
+ * 232) followed by `np.array(Image.open(image))` (s1_lucaskanade_tracking.py:310).  Pillow's save with default settings
+ * = libjpeg-turbo compression at quality 75, 4:2:0, JDCT_ISLOW, no smoothing; entropy coding is lossless, so the pixels
+ * the tracker sees are: decode( quantise( FDCT( downsample( RGB->YCbCr(crop) )))).  Restated from the published libjpeg
+ * algorithm (jccolor.c rgb_ycc_convert, jcprepct.c / jcsample.c edge replication + h2v2 / h2v1 box filters with the
+ * alternating bias, jfdctint.c, jcdctmgr.c quantisation with divisor 8 * q and round-half-up on the magnitude,
+ * jcparam.c quality scaling of the Annex K tables) + the decode half above.
+ * Pinning: tests/test_jpeg_oracle.py compares this with Pillow's own save + open on random crops.
+ * ================================================================================================================ */
+static const uint8_t STD_LUMA_Q[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                                       14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                                       18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                                       49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+static const uint8_t STD_CHROMA_Q[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                         24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                                         99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                         99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+
+/* jcparam.c: jpeg_quality_scaling + jpeg_add_quant_table(force_baseline = TRUE); tables in natural order */
+void orc_jpeg_quality_tables(int quality, uint16_t *luma, uint16_t *chroma)
+{
+    if (quality <= 0) quality = 1;
+    if (quality > 100) quality = 100;
+    const int scale = quality < 50 ? 5000 / quality : 200 - quality * 2;
+    for (int i = 0; i < 64; i++) {
+        long a = ((long)STD_LUMA_Q[i] * scale + 50) / 100, b = ((long)STD_CHROMA_Q[i] * scale + 50) / 100;
+        luma[i] = (uint16_t)(a < 1 ? 1 : (a > 255 ? 255 : a));
+        chroma[i] = (uint16_t)(b < 1 ? 1 : (b > 255 ? 255 : b));
+    }
+}
+
+/* jfdctint.c: one 8-point pass; pass 1 = rows (results scaled up by 2^PASS1_BITS), pass 2 = columns */
+static void fdct_1d(int *d, int stride, int pass)
+{
+    const int t0 = d[0] + d[7 * stride], t7 = d[0] - d[7 * stride], t1 = d[stride] + d[6 * stride], t6 = d[stride] - d[6 * stride];
+    const int t2 = d[2 * stride] + d[5 * stride], t5 = d[2 * stride] - d[5 * stride], t3 = d[3 * stride] + d[4 * stride],
+              t4 = d[3 * stride] - d[4 * stride];
+    const int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    const int sh = pass == 1 ? CONST_BITS - PASS1_BITS : CONST_BITS + PASS1_BITS;
+    if (pass == 1) {
+        d[0] = (int)((unsigned)(t10 + t11) << PASS1_BITS);
+        d[4 * stride] = (int)((unsigned)(t10 - t11) << PASS1_BITS);
+    } else {
+        d[0] = DESCALE(t10 + t11, PASS1_BITS);
+        d[4 * stride] = DESCALE(t10 - t11, PASS1_BITS);
+    }
+    int z1 = (t12 + t13) * 4433;
+    d[2 * stride] = DESCALE(z1 + t13 * 6270, sh);
+    d[6 * stride] = DESCALE(z1 + t12 * (-15137), sh);
+    z1 = t4 + t7;
+    int z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
+    const int z5 = (z3 + z4) * 9633;
+    const int a4 = t4 * 2446, a5 = t5 * 16819, a6 = t6 * 25172, a7 = t7 * 12299;
+    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+    z3 += z5; z4 += z5;
+    d[7 * stride] = DESCALE(a4 + z1 + z3, sh);
+    d[5 * stride] = DESCALE(a5 + z2 + z4, sh);
+    d[3 * stride] = DESCALE(a6 + z2 + z3, sh);
+    d[stride] = DESCALE(a7 + z1 + z4, sh);
+}
+
+/* one block in place: samples -> FDCT -> quantise (jcdctmgr.c) -> [entropy coding is lossless] -> dequantise -> IDCT */
+static void requantise_block(uint8_t *blk, int pitch, const uint16_t *q)
+{
+    int w[64];
+    int16_t coef[64];
+    for (int r = 0; r < 8; r++)
+        for (int c = 0; c < 8; c++) w[r * 8 + c] = (int)blk[r * pitch + c] - 128;
+    for (int r = 0; r < 8; r++) fdct_1d(w + r * 8, 1, 1);
+    for (int c = 0; c < 8; c++) fdct_1d(w + c, 8, 2);
+    for (int i = 0; i < 64; i++) {
+        const int qv = (int)q[i] << 3;
+        int t = w[i];
+        if (t < 0) { t = -t; t += qv >> 1; t = t >= qv ? t / qv : 0; t = -t; }
+        else { t += qv >> 1; t = t >= qv ? t / qv : 0; }
+        coef[i] = (int16_t)t;
+    }
+    idct_block(coef, q, blk, pitch);
+}
+
+/* rgb: (H, W, 3) u8 with row pitch `pitch` bytes; hs, vs = luma sampling factors (2,2 = Pillow's default 4:2:0; 2,1; 1,1);
+ * out: (H, W, 3) u8, what np.array(Image.open(saved_file)) returns */
+int orc_jpeg_recompress(const uint8_t *rgb, long pitch, int W, int H, int quality, int hs, int vs, uint8_t *out)
+{
+    if (W <= 0 || H <= 0 || W > 65535 || H > 65535) return ORC_JPEG_E_FORMAT;
+    if (!((hs == 1 && vs == 1) || (hs == 2 && vs == 1) || (hs == 2 && vs == 2))) return ORC_JPEG_E_UNSUPPORTED;
+    jpg_t J;
+    memset(&J, 0, sizeof(J));
+    J.W = W; J.H = H; J.nc = 3; J.hmax = hs; J.vmax = vs;
+    J.c[0].h = hs; J.c[0].v = vs; J.c[1].h = J.c[1].v = J.c[2].h = J.c[2].v = 1;
+    J.c[0].tq = 0; J.c[1].tq = J.c[2].tq = 1;
+    orc_jpeg_quality_tables(quality, J.q[0], J.q[1]);
+    J.mcux = (W + 8 * hs - 1) / (8 * hs);
+    J.mcuy = (H + 8 * vs - 1) / (8 * vs);
+    for (int i = 0; i < 3; i++) {
+        comp_t *c = &J.c[i];
+        c->pw = J.mcux * c->h * 8; c->ph = J.mcuy * c->v * 8;
+        c->dw = (W * c->h + hs - 1) / hs; c->dh = (H * c->v + vs - 1) / vs;
+        c->plane = (uint8_t *)calloc((size_t)c->pw * c->ph, 1);
+        if (!c->plane) return ORC_JPEG_E_FORMAT;
+    }
+    /* jccolor.c rgb_ycc_convert at full resolution (16-bit fixed point) */
+    uint8_t *ycc = (uint8_t *)malloc((size_t)W * H * 3);
+    if (!ycc) return ORC_JPEG_E_FORMAT;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const uint8_t *p = rgb + (size_t)y * pitch + (size_t)x * 3;
+            const int r = p[0], g = p[1], b = p[2];
+            uint8_t *o = ycc + ((size_t)y * W + x) * 3;
+            o[0] = (uint8_t)((19595 * r + 38470 * g + 7471 * b + 32768) >> 16);
+            o[1] = (uint8_t)((-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16);
+            o[2] = (uint8_t)((32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16);
+        }
+#define YCC(x, y, k) ycc[((size_t)((y) < H - 1 ? (y) : H - 1) * W + ((x) < W - 1 ? (x) : W - 1)) * 3 + (k)]
+    /* luma: fullsize_downsample; rows and columns past the image replicate the last one (jcprepct.c, expand_right_edge) */
+    for (int y = 0; y < J.c[0].ph; y++)
+        for (int x = 0; x < J.c[0].pw; x++) J.c[0].plane[(size_t)y * J.c[0].pw + x] = YCC(x, y, 0);
+    /* chroma: box filter on the edge-replicated full-resolution rows; rows of the plane past the last real row group copy it */
+    for (int k = 1; k < 3; k++) {
+        comp_t *c = &J.c[k];
+        for (int cy = 0; cy < c->ph; cy++) {
+            const int ce = cy < c->dh - 1 ? cy : c->dh - 1;
+            for (int cx = 0; cx < c->pw; cx++) {
+                int v;
+                if (hs == 1) v = YCC(cx, ce, k);
+                else if (vs == 1) v = (YCC(2 * cx, ce, k) + YCC(2 * cx + 1, ce, k) + (cx & 1)) >> 1;
+                else v = (YCC(2 * cx, 2 * ce, k) + YCC(2 * cx + 1, 2 * ce, k) + YCC(2 * cx, 2 * ce + 1, k) + YCC(2 * cx + 1, 2 * ce + 1, k) + 1 + (cx & 1)) >> 2;
+                c->plane[(size_t)cy * c->pw + cx] = (uint8_t)v;
+            }
+        }
+    }
+#undef YCC
+    free(ycc);
+    for (int i = 0; i < 3; i++) {
+        comp_t *c = &J.c[i];
+        for (int by = 0; by < c->ph / 8; by++)
+            for (int bx = 0; bx < c->pw / 8; bx++) requantise_block(c->plane + (size_t)by * 8 * c->pw + bx * 8, c->pw, J.q[c->tq]);
+    }
+    emit_pixels(&J, out);
+    for (int i = 0; i < 3; i++) free(J.c[i].plane);
+    return ORC_JPEG_OK;
 }

@@ -260,6 +260,19 @@ def imread_jpeg(data):
     return out
 
 
+def jpeg_recompress(rgb, quality=75, subsampling="4:2:0"):
+    """What np.array(Image.open(f)) holds after Image.fromarray(rgb).save(f, quality=, subsampling=): the save-and-reopen
+    round trip of the reference's cropping pre-pass (imports/camtools.py:80,102,232 -> s1:310); Pillow defaults = 75, 4:2:0."""
+    hs, vs = {"4:4:4": (1, 1), "4:2:2": (2, 1), "4:2:0": (2, 2)}[subsampling]
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    H, W = rgb.shape[:2]
+    out = np.zeros((H, W, 3), np.uint8)
+    rc = lib().orc_jpeg_recompress(_p(rgb), C.c_long(W * 3), W, H, int(quality), hs, vs, _p(out))
+    if rc != 0:
+        raise ValueError("oracle: recompress failed (%d)" % rc)
+    return out
+
+
 # ---- s3 gridding (numpy restatement of s3_utm_to_gridded_utm.py:391-421 + imports/tracking_misc.py:15-58) -----------------
 def contains_points(poly, points):
     """matplotlib.path.Path(poly).contains_points(points), radius 0: the even-odd "crossings" rule of matplotlib's

@@ -189,3 +189,73 @@ def test_decode_async_equals_decode(ibt):
         h = dec.decode_async(blobs[0], rgb=False, gray=True, margin=0)
         _, gray = dec.confirm(h)
         assert torch.equal(gray, ref[0][1]) and dec.last_rounds > 1 and h.get("redo")
+
+
+# ---- ibt_jpeg_recompress: the save-and-reopen round trip of the cropping pre-pass (camtools.py:80 -> s1:310) ---------------
+SUBS = {0: "4:4:4", 1: "4:2:2", 2: "4:2:0"}
+
+
+def test_recompress_matches_pillow_golden(jpeg, ibt, oracle):
+    z = dict(np.load(os.path.join(JDIR, "recompress.npz")))
+    names = [k[3:] for k in z if k.startswith("in_")]
+    assert len(names) >= 12
+    for name in names:
+        src, exp, kw = z["in_" + name], z["out_" + name], z["kw_" + name]
+        out = jpeg.save_reopen(src, int(kw[0]), SUBS[int(kw[1])]).cpu().numpy()
+        assert np.array_equal(out, exp), name
+        g = jpeg.save_reopen(src, int(kw[0]), SUBS[int(kw[1])], gray=True).cpu().numpy()
+        assert np.array_equal(g, oracle.cvtColor(exp)), name
+
+
+def test_recompress_matrix_vs_oracle_and_pillow(jpeg, oracle):
+    """sizes 1..70 x qualities x sampling modes against the oracle (and the Pillow of this box when present); crop VIEWS with
+    odd byte offsets (the kernel reads unaligned rows through aligned words)."""
+    import torch
+    try:
+        from PIL import Image
+    except ImportError:
+        Image = None
+    rng = np.random.default_rng(29)
+    big = torch.from_numpy(rng.integers(0, 256, (90, 100, 3), dtype=np.uint8)).cuda()
+    smooth = np.cumsum(np.cumsum(rng.normal(0, 3, (90, 100, 3)), 0), 1)
+    smooth = torch.from_numpy(((smooth - smooth.min()) / (np.ptp(smooth) + 1e-9) * 255).astype(np.uint8)).cuda()
+    dec = jpeg.JpegDecoder()
+    n = 0
+    for trial in range(120):
+        H, W = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        u, l = int(rng.integers(0, 90 - H + 1)), int(rng.integers(0, 100 - W + 1))
+        view = (big if trial % 2 else smooth)[u:u + H, l:l + W]
+        a = view.cpu().numpy().copy()
+        q = int(rng.integers(1, 101))
+        sub = int(rng.integers(0, 3)) if trial % 4 else 2
+        if trial % 5 == 0:
+            q = 75
+        out = dec.recompress(view, q, SUBS[sub])[0].cpu().numpy()
+        assert np.array_equal(out, oracle.jpeg_recompress(a, q, SUBS[sub])), (H, W, q, sub, u, l)
+        if Image is not None:
+            b = io.BytesIO()
+            Image.fromarray(a).save(b, "JPEG", quality=q, subsampling=sub)
+            assert np.array_equal(out, np.array(Image.open(io.BytesIO(b.getvalue())))), (H, W, q, sub)
+        n += 1
+    assert n == 120
+
+
+@pytest.mark.parametrize("scene", ["texture", "iceberg"])
+def test_recompress_24mp_crop_vs_pillow(jpeg, ibt, scene):
+    """A 6000x4000 frame cropped like camtools.crop_image_standalone crops it (an odd box), saved with Pillow's defaults and
+    reopened -- against the GPU round trip on the crop view, RGB and fused gray."""
+    import torch
+    Image = pytest.importorskip("PIL.Image")
+    from iceberg_tracking_code_b200 import synthetic as syn
+    base = syn.base_texture(4000, 6000, 7, device="cuda", scene=scene)
+    rgb = syn.frame_rgb(base, 0, seed=7)
+    box = (251, 401, 5994, 3999)                                         # left, upper, right, lower
+    bio = io.BytesIO()
+    Image.fromarray(rgb.cpu().numpy()).crop(box).save(bio, "JPEG")
+    ref = torch.from_numpy(np.array(Image.open(io.BytesIO(bio.getvalue()))))
+    dec = jpeg.JpegDecoder()
+    out, gray = dec.recompress(rgb[box[1]:box[3], box[0]:box[2]], rgb=True, gray=True)
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(gray, ibt.cvtColor(out))
+    # and the decoder agrees on the file Pillow wrote (the crop="reencode" route)
+    assert torch.equal(dec.decode(bio.getvalue(), rgb=True, gray=False)[0].cpu(), ref)

@@ -156,6 +156,14 @@ def test_lucaskanade_tracking_signature(ibt, oracle, tmp_path):
     z2 = np.load(tgt2 / "20190724-130000_120sec_at_60sec_tracks.npz")
     assert z2["tracks"].shape == ref2[0][0].shape and np.abs(z2["tracks"] - ref2[0][0]).max() <= 0.01
 
+    # crop="emulate": no host pre-pass and no cropped copies either, but the SAME pixels as crop="reencode" (the reference's
+    # route): the save-and-reopen round trip of camtools.crop_image_standalone runs as integer arithmetic on the GPU
+    tgt3 = tmp_path / "out3" / "cam1" / "oblique" / "20190724"
+    trk.lucaskanade_tracking(str(tmp_path), str(src), str(tgt3), "cam1", 2, 60, [0], 1, 0, 0, 0, str(pf), 1, crop="emulate")
+    assert [f.name for f in sorted(tgt3.iterdir())] == ["20190724-130000_120sec_at_60sec_tracks.npz"]
+    z3 = np.load(tgt3 / "20190724-130000_120sec_at_60sec_tracks.npz")
+    assert z3["tracks"].tobytes() == z["tracks"].tobytes() and z3["trackquality"].tobytes() == z["trackquality"].tobytes()
+
 
 def crossing_mask(poly, xs, ys):
     """numpy restatement of the crossing-number rule matplotlib's Path.contains_points applies (camtools.py:208-209)."""

@@ -107,3 +107,50 @@ def test_parse_rejects():
     bio = io.BytesIO()
     Image.fromarray(np.zeros((16, 16, 3), np.uint8)).save(bio, "JPEG", progressive=True)
     assert _parse(bio.getvalue())[0] == N.IBT_E_UNSUPPORTED
+
+
+# ---- the save-and-reopen round trip of the cropping pre-pass (camtools.py:80 -> s1:310) -----------------------------------
+SUBS = {0: "4:4:4", 1: "4:2:2", 2: "4:2:0"}
+
+
+@pytest.fixture(scope="module")
+def recompress_golden():
+    z = dict(np.load(os.path.join(JDIR, "recompress.npz")))
+    return {k[3:]: (z[k], z["out_" + k[3:]], z["kw_" + k[3:]]) for k in z if k.startswith("in_")}
+
+
+def test_oracle_recompress_matches_pillow_golden(oracle, recompress_golden):
+    """recompress.npz holds Pillow's own save + open of each array (tests/golden/make_recompress_golden.py)."""
+    assert len(recompress_golden) >= 12
+    for name, (src, exp, kw) in recompress_golden.items():
+        out = oracle.jpeg_recompress(src, int(kw[0]), SUBS[int(kw[1])])
+        assert np.array_equal(out, exp), name
+
+
+def test_oracle_recompress_matches_pillow_live(oracle):
+    """img.save(f) + np.array(Image.open(f)) by the Pillow of this box: sizes 1..70 (every edge-replication case of the 16x16
+    MCU), random qualities, the three sampling modes, noise / ramps / blocks."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(23)
+
+    def round_trip(a, **kw):
+        b = io.BytesIO()
+        Image.fromarray(a).save(b, "JPEG", **kw)
+        return np.array(Image.open(io.BytesIO(b.getvalue())))
+
+    n = 0
+    for trial in range(90):
+        H, W = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        if trial % 3 == 0:
+            a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        elif trial % 3 == 1:
+            yy, xx = np.mgrid[0:H, 0:W]
+            a = np.stack([(xx * 3 + yy * 2) % 256, (xx * yy) % 256, (255 - xx * 4) % 256], -1).astype(np.uint8)
+        else:
+            a = rng.integers(0, 256, (H // 4 + 1, W // 4 + 1, 3), dtype=np.uint8).repeat(4, 0).repeat(4, 1)[:H, :W].copy()
+        q = int(rng.integers(1, 101))
+        for kw in ({}, dict(quality=q), dict(quality=q, subsampling=0), dict(quality=q, subsampling=1), dict(quality=100)):
+            out = oracle.jpeg_recompress(a, kw.get("quality", 75), SUBS[kw.get("subsampling", 2)])
+            assert np.array_equal(out, round_trip(a, **kw)), (H, W, kw)
+            n += 1
+    assert n == 450
