@@ -246,7 +246,7 @@ def timed_steps(pipe, frames, pts, first, n, iter_total=None, probes=None):
         pipe.step(i, frames[pingpong(i + 1)], pts[pingpong(i)], iter_total, None if probes is None else probes[k])
 
 
-def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
+def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev, ndec=None):
     """Same step, but the new frame arrives as the JPEG FILE the reference opens with Pillow (s1:310): the bytes are
     copied host->device compressed and csrc/jpeg.cu decodes them straight to the gray plane (bit-exact with Pillow +
     cv2.cvtColor).  The decodes of frames i+2 and i+3 (two decoders, two high-priority streams, no host wait: decode_async,
@@ -269,29 +269,34 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
     h_p1 = [torch.empty((NPTS, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
     h_fbd = [torch.empty((NPTS,), dtype=torch.float32).pin_memory() for _ in range(2)]
     done = [torch.cuda.Event(), torch.cuda.Event()]
-    NS = 4
-    pyr = list(pipe.pyr) + [trk.prepare(g)]                   # four pyramid slots: two frames are being decoded ahead
+    # ND decoders on ND high-priority streams: a decode is a chain of small latency-bound kernels that runs ~2x slower beside
+    # the LK launch (which keeps 80 % of the issue slots busy), so the step time is (decode latency under contention) / ND
+    # until the LK launches themselves are the limit
+    ND = int(ndec or os.environ.get("IBT_BENCH_NDEC", "2"))
+    NS = ND + 2                                               # pyramid slots: two being tracked, ND being decoded ahead
+    pyr = list(pipe.pyr) + [trk.prepare(g) for _ in range(NS - len(pipe.pyr))]
     main = torch.cuda.current_stream()
-    # two decoders on two high-priority streams: a decode is a chain of small latency-bound kernels, two in flight overlap
-    decs = [dec, jpeg.JpegDecoder(dev)]
-    decs[1].decode(blobs[1], rgb=False, gray=True)
-    dstream = [torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev, priority=-1)]
+    decs = [dec] + [jpeg.JpegDecoder(dev) for _ in range(ND - 1)]
+    for d in range(1, ND):
+        decs[d].decode(blobs[d % len(blobs)], rgb=False, gray=True)
+    dstream = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(ND)]
     lk_done = [None] * NS
     redone = [0]
 
     # the host side of a decode (copy of the file bytes into page-locked memory, marker parsing: ~1 ms) runs on two worker threads
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=2)
+    pool = ThreadPoolExecutor(max_workers=max(2, ND))
     staged = {}
 
     def prestage(j):
         if j not in staged:
-            staged[j] = pool.submit(decs[j & 1].stage, blobs[pingpong(j)])
+            staged[j] = pool.submit(decs[j % ND].stage, blobs[pingpong(j)])
 
     def stage(j):
         """decode frame j (asynchronously: no host wait) -> gray -> pyramid into pyr[j % NS]; returns (handle, ready event)"""
-        d = j & 1
-        prestage(j); prestage(j + 1); prestage(j + 2)
+        d = j % ND
+        for a in range(ND + 1):
+            prestage(j + a)
         sj = staged.pop(j).result()
         with torch.cuda.stream(dstream[d]):
             if lk_done[j % NS] is not None:
@@ -307,32 +312,42 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
         h, _ev = st
         if h["flags"] is None:
             return
-        before = decs[j & 1].last_rounds
-        decs[j & 1].confirm(h)
-        if decs[j & 1].last_rounds == 0 or (before and decs[j & 1].last_rounds > h["rounds"]):
+        before = decs[j % ND].last_rounds
+        decs[j % ND].confirm(h)
+        if decs[j % ND].last_rounds == 0 or (before and decs[j % ND].last_rounds > h["rounds"]):
             redone[0] += 1
         if h.get("redo"):
             trk.prepare(h["gray"], reuse=pyr[j % NS])
 
-    def loop(n):
+    host = {"stage": 0.0, "confirm": 0.0, "lk": 0.0, "wait": 0.0}       # host seconds spent per phase (breakdown only)
+    pc = time.perf_counter
+
+    def loop(n, skip_lk=False):
         acc = 0.0
-        st = {0: stage(0), 1: stage(1), 2: stage(2)}
+        st = {j: stage(j) for j in range(ND + 1)}
         for i in range(n):
             k = i & 1
+            t0 = pc()
             if i == 0:
                 confirm(0, st[0])
             confirm(i + 1, st[i + 1])
+            t1 = pc()
             main.wait_event(st.pop(i)[1]); main.wait_event(st[i + 1][1])
-            cv.lk_fb_into(pyr[i % NS], pyr[(i + 1) % NS], pts[pingpong(i)], LK, pipe.p1[k], pipe.fbd[k], None, None)
+            if not skip_lk:
+                cv.lk_fb_into(pyr[i % NS], pyr[(i + 1) % NS], pts[pingpong(i)], LK, pipe.p1[k], pipe.fbd[k], None, None)
             e = torch.cuda.Event(); e.record(main)
             lk_done[i % NS] = e                               # pyr[i % NS] may be rebuilt once this launch has finished
             h_p1[k].copy_(pipe.p1[k], non_blocking=True); h_fbd[k].copy_(pipe.fbd[k], non_blocking=True)
             done[k].record(main)
-            if i + 3 <= n:
-                st[i + 3] = stage(i + 3)                      # decoded beside the LK launches of pairs i and i+1
+            t2 = pc()
+            if i + ND + 1 <= n:
+                st[i + ND + 1] = stage(i + ND + 1)            # decoded beside the LK launches of pairs i .. i+ND-1
+            t3 = pc()
             if i >= 1:
                 done[k ^ 1].synchronize()
                 acc += float(h_fbd[k ^ 1][0])
+            t4 = pc()
+            host["confirm"] += t1 - t0; host["lk"] += t2 - t1; host["stage"] += t3 - t2; host["wait"] += t4 - t3
         done[(n - 1) & 1].synchronize()
         for f in staged.values():                             # frames staged beyond the end of this loop: release their buffers
             f.result()["slot"]["free"].set()
@@ -340,12 +355,29 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
         return acc + float(h_fbd[(n - 1) & 1][0])
     cv.set_lk_resident_ctas(2)
     try:
-        loop(12)                                              # (every pinned staging buffer of both decoders exists afterwards)
+        loop(12 + 4 * ND)                                     # (every pinned staging buffer of every decoder exists afterwards)
         torch.cuda.synchronize()
+        for k_ in host:
+            host[k_] = 0.0
         t0 = time.perf_counter()
         loop(steps)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / steps
+        breakdown = None
+        if os.environ.get("IBT_BENCH_BREAKDOWN"):
+            # where a from-files step goes: host time per phase of the loop above, the same loop without the LK launches
+            # (decode + pyramid + copies only) and the LK launches alone at the same occupancy cap
+            breakdown = {"host_ms_per_step": {k: v * 1e3 / steps for k, v in host.items()}}
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            loop(steps, skip_lk=True)
+            torch.cuda.synchronize()
+            breakdown["decode_prepare_only_ms"] = (time.perf_counter() - t0) * 1e3 / steps
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                cv.lk_fb_into(pyr[i % NS], pyr[(i + 1) % NS], pts[pingpong(i)], LK, pipe.p1[i & 1], pipe.fbd[i & 1], None, None)
+            e1.record(); torch.cuda.synchronize()
+            breakdown["lk_only_capped_ms"] = e0.elapsed_time(e1) / steps
     finally:
         cv.set_lk_resident_ctas(0)
         pool.shutdown(wait=True)
@@ -361,7 +393,8 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev):
     return {"value": NPTS / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "steps": steps,
             "h2d_bytes_per_step": int(np.mean([len(b) for b in blobs])), "d2h_bytes_per_step": int(h_p1[0].numel() * 4 + h_fbd[0].numel() * 4),
             "jpeg_decode_ms": e0.elapsed_time(e1) / 10, "huffman_sync_rounds": dec.last_rounds,
-            "pillow_decode_ms_1_core": pil_ms, "bit_exact_vs_pillow_cvtcolor": exact, "decodes_repeated": redone[0],
+            "pillow_decode_ms_1_core": pil_ms, "bit_exact_vs_pillow_cvtcolor": exact, "decodes_repeated": redone[0], "decoders": ND,
+            **({"breakdown": breakdown} if breakdown else {}),
             "api": "jpeg.JpegDecoder.decode_async(gray) on two streams + SequenceTracker.prepare + fused LK (2 of 3 CTAs per SM), "
                    "JPEG bytes in host memory, the next two frames decode beside the LK launches, p1 + FB distance read back "
                    "every step; wall clock"}

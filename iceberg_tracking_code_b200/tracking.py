@@ -143,7 +143,7 @@ class ViewLoader:
         from ._crop import open_cropped
         self.fallbacks += 1
         img = open_cropped(path, name, self.box)
-        if self.gpu.reencode is not None:                 # crop="emulate": the reference's save + reopen, in memory
+        if getattr(self.gpu, "reencode", None) is not None:   # crop="emulate": the reference's save + reopen, in memory
             import io
             from PIL import Image
             buf = io.BytesIO()

@@ -187,3 +187,10 @@ def test_view_loader_fallbacks(tmp_path, capsys, caplog):
     assert np.array_equal(p, np.array(Image.open(prog).crop((8, 4, 88, 60))))
     big = ViewLoader(StubGpu(), (8, 4, 120, 60), names)(str(tgt / "good.jpg"))         # box wider than the 96 px frame
     assert isinstance(big, np.ndarray) and big.shape == (56, 112, 3) and not big[:, 96 - 8:].any()   # PIL pads with zeros
+    # crop="emulate": the fallback does the reference's save + reopen in memory (camtools.py:80 -> s1:310)
+    class StubGpuRe(StubGpu):
+        reencode = (75, "4:2:0")
+    e = ViewLoader(StubGpuRe(), (8, 4, 88, 60), names)(str(tgt / "prog.jpg"))
+    ref = tmp_path / "ref.jpg"
+    Image.open(prog).crop((8, 4, 88, 60)).save(ref)
+    assert np.array_equal(e, np.array(Image.open(ref)))
