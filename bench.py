@@ -424,6 +424,8 @@ def run_sharded_sequence(dev, rank, world, dist):
     # warm-up: the whole job once, untimed (allocator pools, pinned staging buffers, NCCL channels, kernels)
     dev_res = {}
     res = trk.track_sequence(imagelist, None, SEQ_T, 60, first_group=g0, n_groups=n, device_results=dev_res, **kw)
+    for _seed, (t_d, _q_d) in dev_res.items():
+        cam.tracks_to_utm(t_d)
     sh.gather_results(res, SEQ_T, to_host="rank0", device_results=dev_res)
     del res, dev_res
     torch.cuda.synchronize()
