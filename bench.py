@@ -262,6 +262,9 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev, ndec=None):
         bio = io.BytesIO()
         Image.fromarray(f.numpy()).save(bio, "JPEG")          # Pillow defaults, as the reference's cropping step saves
         blobs.append(bio.getvalue())
+    # the loop keeps ND decodes in flight beside the tracker: their latency is hidden, so the entry-state probe of the Huffman pass
+    # (a full-grid kernel that saves two of nine low-occupancy synchronisation rounds) is switched off for its duration
+    jpeg.set_probe(os.environ.get("IBT_BENCH_PROBE") is not None)
     dec = jpeg.JpegDecoder(dev)
     g = dec.decode(blobs[0], rgb=False, gray=True)[1]
     ref = cv.cvtColor(torch.from_numpy(np.array(Image.open(io.BytesIO(blobs[0])))).to(dev))
@@ -380,8 +383,12 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev, ndec=None):
             breakdown["lk_only_capped_ms"] = e0.elapsed_time(e1) / steps
     finally:
         cv.set_lk_resident_ctas(0)
+        jpeg.set_probe(True)
         pool.shutdown(wait=True)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    dec.last_rounds = 0                                       # a lone synchronous decode (probe on again): fresh round-count hint
+    for k in range(2):
+        dec.decode(blobs[k], rgb=False, gray=True)
     e0.record()
     for k in range(10):
         dec.decode(blobs[k % len(blobs)], rgb=False, gray=True)
@@ -395,7 +402,7 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev, ndec=None):
             "jpeg_decode_ms": e0.elapsed_time(e1) / 10, "huffman_sync_rounds": dec.last_rounds,
             "pillow_decode_ms_1_core": pil_ms, "bit_exact_vs_pillow_cvtcolor": exact, "decodes_repeated": redone[0], "decoders": ND,
             **({"breakdown": breakdown} if breakdown else {}),
-            "api": "jpeg.JpegDecoder.decode_async(gray) on two streams + SequenceTracker.prepare + fused LK (2 of 3 CTAs per SM), "
+            "api": "jpeg.JpegDecoder.decode_async(gray, no entry-state probe) on two streams + SequenceTracker.prepare + fused LK (2 of 3 CTAs per SM), "
                    "JPEG bytes in host memory, the next two frames decode beside the LK launches, p1 + FB distance read back "
                    "every step; wall clock"}
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "ibt_jpeg_decode": (_i, [_vp, _JPG, _vp, _i64, _vp, _i64, _vp, _i64, _i, C.POINTER(C.c_int), _vp]),
     "ibt_jpeg_async_host_bytes": (_i64, []),
     "ibt_jpeg_decode_async": (_i, [_vp, _JPG, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _vp]),
+    "ibt_jpeg_set_probe": (_i, [_i]),
     "ibt_jpeg_recompress_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "ibt_jpeg_recompress": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _vp]),
     "ibt_lk_set_max_ctas_per_sm": (_i, [_i]),

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 
 namespace ibt {
 
@@ -846,6 +847,7 @@ struct JpgLayout {
     size_t stream_bytes, coef_bytes, rst_bytes;
 };
 constexpr int JPG_MAX_ROUNDS_BATCH = 64;
+static std::atomic<bool> jpeg_probe_enabled{true};        // ibt_jpeg_set_probe
 
 static void jpeg_layout(const ibt_jpeg_info_t *I, JpgLayout &L)
 {
@@ -1135,7 +1137,7 @@ static int jpeg_decode_impl(const uint8_t *d_file, const ibt_jpeg_info_t *I, voi
 
     // 2. synchronisation rounds; the host reads the per-round change counters once per batch
     static const bool no_probe = getenv("IBT_JPEG_NO_PROBE") != nullptr;       // A/B switch for the measurements in profiles/
-    if (L.G.nblk_mcu > 1 && !no_probe) {
+    if (L.G.nblk_mcu > 1 && !no_probe && jpeg_probe_enabled.load(std::memory_order_relaxed)) {
         unsigned long long *exits = reinterpret_cast<unsigned long long *>(ws + L.off_exits);
         const int P = L.G.nblk_mcu;
         jpg_sync_probe<<<(L.nsub * P + 127) / 128, 128, 0, st>>>(words, meta, dT, exits, L.nsub, P, rst, L.sbits);
@@ -1291,4 +1293,10 @@ IBT_API int ibt_jpeg_recompress(const uint8_t *d_rgb_in, int64_t in_pitch, int w
     else { IBT_JPG_COLOR(14, 1868, 9617, 4899) }
 #undef IBT_JPG_COLOR
     return check_launch("ibt_jpeg_recompress");
+}
+
+IBT_API int ibt_jpeg_set_probe(int enabled)
+{
+    ibt::jpeg_probe_enabled.store(enabled != 0, std::memory_order_relaxed);
+    return IBT_OK;
 }

@@ -511,6 +511,8 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
         NSLOT = LOOK + 3
         if on_gpu:
             cv.set_lk_resident_ctas(2)                    # the JPEG decodes of the next frames share the SMs with the tracker
+            from . import jpeg as _jpeg
+            _jpeg.set_probe(False)                        # decode latency hides behind the tracker: no full-grid probe kernel
         main = torch.cuda.current_stream()
         side = trk.side
         slots = getattr(trk, "_slots", None)
@@ -606,6 +608,7 @@ def track_sequence(imagelist, mask, track_len, track_len_sec, startlist=(0,), fe
             main.wait_stream(side)
             if on_gpu:
                 cv.set_lk_resident_ctas(0)
+                _jpeg.set_probe(True)
     return results
 
 

@@ -216,6 +216,11 @@ int64_t ibt_jpeg_async_host_bytes(void);
 int ibt_jpeg_decode_async(const uint8_t *d_file, const ibt_jpeg_info_t *info, void *workspace, int64_t workspace_bytes,
                           uint8_t *rgb, int64_t rgb_pitch, uint8_t *gray, int64_t gray_pitch, int coeffset, int rounds,
                           void *h_pinned, int64_t h_pinned_bytes, void *stream);
+/* Process-wide switch of the entry-state probe of the Huffman pass (default on).  The probe decodes every subsequence once per
+ * block position of the MCU to guess its entry state: fewer synchronisation rounds, i.e. a shorter decode LATENCY (7 instead of
+ * 9 rounds on a dense 24 MP file), at the price of a full-grid kernel.  A frame loop that keeps several decodes in flight beside
+ * the tracker (ibt_jpeg_decode_async) hides the latency anyway and runs ~4 % faster without it (the rounds occupy few SMs). */
+int ibt_jpeg_set_probe(int enabled);
 
 /* ---- the save-and-reopen round trip of the reference's cropping pre-pass, without the files:
  *      `img_crop.save(outpath)` (imports/camtools.py:80,102,232 via crop_image_parallel, s1_lucaskanade_tracking.py:272)
