@@ -26,6 +26,7 @@ is timed separately ("gftt_ms") and inside "sharded_sequence".  metric = tracked
           the numpy FB arithmetic of s1:329-333 -- on the host cores (falls back to the C oracle port when cv2 is absent).
 """
 import argparse
+import gc
 import hashlib
 import json
 import math
@@ -362,10 +363,12 @@ def run_from_files(trk, pipe, pts, host_frames, steps, cv, dev, ndec=None):
         torch.cuda.synchronize()
         for k_ in host:
             host[k_] = 0.0
+        gc.collect(); gc.disable()
         t0 = time.perf_counter()
         loop(steps)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / steps
+        gc.enable()
         breakdown = None
         if os.environ.get("IBT_BENCH_BREAKDOWN"):
             # where a from-files step goes: host time per phase of the loop above, the same loop without the LK launches
@@ -439,6 +442,7 @@ def run_sharded_sequence(dev, rank, world, dist):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    gc.collect(); gc.disable()                             # (see main(): no collector pauses inside the timed region)
     t0 = time.perf_counter()
     dev_res = {}
     res = trk.track_sequence(imagelist, None, SEQ_T, 60, first_group=g0, n_groups=n, device_results=dev_res, **kw)
@@ -458,6 +462,7 @@ def run_sharded_sequence(dev, rank, world, dist):
     allres = sh.gather_results(res, SEQ_T, to_host="rank0", device_results=dev_res)
     torch.cuda.synchronize()
     t_all = time.perf_counter() - t0
+    gc.enable()
     if dist is not None:
         dist.barrier()
     tt = torch.tensor([t_all, t_track, t_all - t_track - t_utm, t_utm], dtype=torch.float64, device=dev)
@@ -592,6 +597,11 @@ def main():
         pts.append(p.reshape(NPTS, 2).contiguous())
     trk = SequenceTracker(GFTT, LK, count_iterations=True)
     pipe = PairPipeline(trk, dev, frames[0])
+    # a full (generation-2) collection of CPython's cyclic GC walks every container object of the process -- ~0.1 s with torch
+    # imported -- and fires at arbitrary points: one of them inside a 50 ms timed region (seen at N = 8: max over ranks) is a
+    # host stall, not a property of the path.  Everything alive now is moved out of the collector's sight; the timed regions
+    # below additionally run with the collector off and collect explicitly between them.
+    gc.collect(); gc.freeze()
     # the form the frame loop uses (ibt_gftt_async: both launches enqueued, count left on the device, no host round trip)
     gftt_async_ms = []
     for k in range(4):
@@ -637,10 +647,12 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     trk.iter_total.zero_()
+    gc.collect(); gc.disable()
     sampler.start()
     e0, e1 = run_region(pipe, steps * repeats, 0, trk.iter_total)
     sampler.sample_now()                       # the GPU is still working through the queued steps
     torch.cuda.synchronize()
+    gc.enable()
     if dist is not None:
         dist.barrier()
     clocks = sampler.stop()
@@ -713,10 +725,12 @@ def main():
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    gc.collect(); gc.disable()
     tw0 = time.perf_counter()
     e2e_loop(n_e2e, 0)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - tw0) * 1e3            # wall clock around host-visible results (>= any device-side figure)
+    gc.enable()
     h2d = int(host_frames[0].numel())
     d2h = int(h_p1[0].numel() * 4 + h_fbd[0].numel() * 4)
 
