@@ -259,3 +259,32 @@ def test_recompress_24mp_crop_vs_pillow(jpeg, ibt, scene):
     assert torch.equal(gray, ibt.cvtColor(out))
     # and the decoder agrees on the file Pillow wrote (the crop="reencode" route)
     assert torch.equal(dec.decode(bio.getvalue(), rgb=True, gray=False)[0].cpu(), ref)
+
+
+def test_probe_switch_changes_rounds_not_pixels(jpeg):
+    """ibt_jpeg_set_probe: the entry-state probe only changes how many synchronisation rounds the speculative Huffman pass needs
+    (the fixed point is the sequential decode either way) -- same bytes out, synchronous and asynchronous form."""
+    import torch
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(31)
+    img = rng.integers(0, 256, (700, 900, 3), dtype=np.uint8)
+    bio = io.BytesIO()
+    Image.fromarray(img).save(bio, "JPEG", quality=90)
+    data = bio.getvalue()
+    ref = torch.from_numpy(np.array(Image.open(io.BytesIO(data))))
+    try:
+        outs, rounds = [], []
+        for on in (True, False):
+            jpeg.set_probe(on)
+            dec = jpeg.JpegDecoder()
+            rgb, gray = dec.decode(data, rgb=True, gray=True)
+            assert torch.equal(rgb.cpu(), ref)
+            rounds.append(dec.last_rounds)
+            h = dec.decode_async(data, rgb=True, gray=True)
+            r2, g2 = dec.confirm(h)
+            assert torch.equal(r2.cpu(), ref) and torch.equal(g2, gray)
+            outs.append(gray)
+        assert torch.equal(outs[0], outs[1])
+        assert rounds[0] >= 1 and rounds[1] >= rounds[0]           # the probe never costs rounds
+    finally:
+        jpeg.set_probe(True)
