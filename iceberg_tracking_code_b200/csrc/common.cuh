@@ -87,17 +87,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 inline EncodeTiledFn encode_tiled_fn()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // resolved once per process; a function-local static's initialiser runs exactly once even when host threads race here
+    static const EncodeTiledFn fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
+        EncodeTiledFn f = nullptr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
+            f = reinterpret_cast<EncodeTiledFn>(p);
         (void)cudaGetLastError();
-    }
+        return f;
+    }();
     return fn;
 }
 inline bool make_map_2d(CUtensorMap *m, CUtensorMapDataType dt, const void *base, int cols, int rows, int64_t pitch_bytes,

@@ -24,6 +24,7 @@
 //                        -> (x, y) float32 of the first maxCorners, count left in device memory.
 //   ibt_min_eigen_f32    (cornerMinEigenVal test hook) keeps the map-writing eig_kernel.
 #include "common.cuh"
+#include <atomic>
 #include <float.h>
 #include <stddef.h>
 #include <string.h>
@@ -1190,19 +1191,21 @@ static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask,
     a.out_xy = out_xy;
     a.out_count = count_dev ? count_dev : reinterpret_cast<int *>(&cnt->pad);
     // every CTA must be resident (the kernel synchronises its grid itself): size the grid from what THIS device can hold
-    static int sel_grid[64] = {0};
+    static std::atomic<int> sel_grid[64];                          // (host threads may race here: they compute the same value)
     int dev_id = 0;
     IBT_CUDA_TRY(cudaGetDevice(&dev_id));
     if (dev_id < 0 || dev_id >= 64) return IBT_E_INVALID;
-    if (!sel_grid[dev_id]) {
+    int grid = sel_grid[dev_id].load(std::memory_order_relaxed);
+    if (!grid) {
         int sms = 0, per_sm = 0;
         IBT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
         IBT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gftt_select_kernel, SEL_THREADS, 0));
         if (per_sm > SEL_CTAS_PER_SM) per_sm = SEL_CTAS_PER_SM;
         if (sms < 1 || per_sm < 1) return IBT_E_CUDA;
-        sel_grid[dev_id] = sms * per_sm;
+        grid = sms * per_sm;
+        sel_grid[dev_id].store(grid, std::memory_order_relaxed);
     }
-    IBT_CUDA_TRY(launch_pdl(gftt_select_kernel, dim3(sel_grid[dev_id]), dim3(SEL_THREADS), 0, st, a));
+    IBT_CUDA_TRY(launch_pdl(gftt_select_kernel, dim3(grid), dim3(SEL_THREADS), 0, st, a));
     return check_launch("gftt_select_kernel");
 }
 

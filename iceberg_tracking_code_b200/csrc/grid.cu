@@ -6,6 +6,7 @@
 // velocities IN POINT ORDER with numpy's pairwise summation (8 accumulators up to 128 elements, recursive halving above):
 // count and sums are bit-identical to the reference's np.sum over the boolean-indexed array.
 // Also here: Path.contains_point(s) for arbitrary points (cell centres inside the fjord outline, tracking_misc.py:52).
+#include <atomic>
 #include "common.cuh"
 
 namespace ibt {
@@ -175,10 +176,15 @@ IBT_API int ibt_points_in_polygon(const double *poly_xy, int E, const double *pt
     if (n == 0) return IBT_OK;
     const size_t smem = (size_t)E * sizeof(double2);
     if (smem > 48 * 1024) {
-        static bool attr_set = false;           // > 3072 vertices: opt in to more dynamic shared memory once
-        if (!attr_set) {
+        // > 3072 vertices: opt in to more dynamic shared memory, once per device (the attribute is per device; setting it
+        // again from a second host thread is harmless)
+        static std::atomic<bool> attr_set[64];
+        int dev_id = 0;
+        IBT_CUDA_TRY(cudaGetDevice(&dev_id));
+        if (dev_id < 0 || dev_id >= 64) return IBT_E_INVALID;
+        if (!attr_set[dev_id].load(std::memory_order_acquire)) {
             IBT_CUDA_TRY(cudaFuncSetAttribute(points_in_polygon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRID_MAX_POLY * 16));
-            attr_set = true;
+            attr_set[dev_id].store(true, std::memory_order_release);
         }
     }
     points_in_polygon_kernel<<<(unsigned)((n + 255) / 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(

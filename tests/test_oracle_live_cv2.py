@@ -118,8 +118,8 @@ def test_lk_live(oracle, seed):
         assert_lk_parity(p0r, st0, r_p0r, r_st0, "bwd %r" % (lp,))
         # the FB decision of s1:329-333 on the points both agree are tracked
         both = (st0.ravel() == 1) & (r_st0.ravel() == 1)
-        d_ref = np.abs(pts.reshape(-1, 2) - r_p0r.reshape(-1, 2)).max(1)
-        d_got = np.abs(pts.reshape(-1, 2) - p0r.reshape(-1, 2)).max(1)
+        d_ref = np.hypot(*(pts.reshape(-1, 2) - r_p0r.reshape(-1, 2)).T)
+        d_got = np.hypot(*(pts.reshape(-1, 2) - p0r.reshape(-1, 2)).T)
         clear = both & (np.abs(d_ref - 1.0) > 0.02)      # decisions within the position tolerance of the threshold may flip
         assert np.array_equal((d_ref < 1.0)[clear], (d_got < 1.0)[clear]), lp
 
