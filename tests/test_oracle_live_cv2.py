@@ -103,7 +103,8 @@ def test_lk_live(oracle, seed):
     n = 160
     pts = np.stack([rng.uniform(-3, w + 3, n), rng.uniform(-3, h + 3, n)], 1).astype(np.float32)
     pts[:20] = np.round(pts[:20])                        # integer positions (what goodFeaturesToTrack returns)
-    pts = pts.reshape(-1, 1, 2)
+    more = np.stack([rng.uniform(0, w, 640), rng.uniform(0, h, 640)], 1).astype(np.float32)
+    pts = np.concatenate([pts, more]).reshape(-1, 1, 2)  # 800 points (the GPU live test draws the same ones)
     for _ in range(3):
         win = (int(rng.choice([5, 9, 15, 21, 31, 35])), int(rng.choice([5, 9, 15, 21, 31, 35])))
         lp = dict(winSize=win, maxLevel=int(rng.integers(0, 5)),
@@ -111,8 +112,14 @@ def test_lk_live(oracle, seed):
         r_p1, r_st, r_err = cv2.calcOpticalFlowPyrLK(f0, f1, pts, None, **lp)
         p1, st, err = oracle.calcOpticalFlowPyrLK(f0, f1, pts, None, **lp)
         assert_lk_parity(p1, st, r_p1, r_st, "fwd %r" % (lp,))
-        ok = (st.ravel() == 1) & (r_st.ravel() == 1)
-        assert np.abs(err.ravel() - r_err.ravel())[ok].max(initial=0) <= ERR_TOL, lp
+        # err is the residual AT the returned position: compare it where the positions agree to 5e-4 px (a point whose last
+        # Newton step lands on the other side of epsilon stops one iteration apart, inside the 0.01 px criterion, and its
+        # residual moves with it: 0.003 px -> 0.007 in err on seed 400's (35, 15) window)
+        same = np.abs(np.asarray(p1) - r_p1).reshape(-1, 2).max(1) <= 5e-4
+        ok = (st.ravel() == 1) & (r_st.ravel() == 1) & same
+        # (err is an integer sum of |J - I| in 1/32 grey levels over the window: allow 16 such units on small windows)
+        assert np.abs(err.ravel() - r_err.ravel())[ok].max(initial=0) <= ERR_TOL + 16.0 / (32 * win[0] * win[1]), lp
+        assert np.mean(same[(st.ravel() == 1) & (r_st.ravel() == 1)]) >= 0.98, lp
         r_p0r, r_st0, _ = cv2.calcOpticalFlowPyrLK(f1, f0, r_p1, None, **lp)
         p0r, st0, _ = oracle.calcOpticalFlowPyrLK(f1, f0, r_p1, None, **lp)
         assert_lk_parity(p0r, st0, r_p0r, r_st0, "bwd %r" % (lp,))
