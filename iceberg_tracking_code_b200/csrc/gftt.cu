@@ -48,7 +48,7 @@ __device__ __forceinline__ float dec_f32(uint32_t e)
 }
 
 __global__ void __launch_bounds__(EW)
-eig_kernel(const uint8_t *__restrict__ img, int H, int W, int64_t pitch, int bs, double s2,
+eig_kernel(const uint8_t *__restrict__ img, int H, int W, int64_t pitch, int bs, double s2, int harris, float harris_k,
            float *__restrict__ eig, int64_t eig_pitch_f,
            const uint8_t *__restrict__ mask, int64_t mask_pitch, uint32_t *__restrict__ maxbits)
 {
@@ -97,10 +97,17 @@ eig_kernel(const uint8_t *__restrict__ img, int H, int W, int64_t pitch, int bs,
             rg[t] = h0; rg[EW + t] = h1; rg[2 * EW + t] = h2;
             if (k >= bs - 1 && xout) {
                 const int y = Y0 + k - (bs - 1);
-                const float a = __fmul_rn((float)((double)vs0 * s2), 0.5f), b = (float)((double)vs1 * s2);
-                const float c = __fmul_rn((float)((double)vs2 * s2), 0.5f);
-                const float d = __fsub_rn(a, c);
-                const float e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+                float e;
+                if (harris) {                                   // cv2.cornerHarris: (a*c - b*b) - k*((a + c)*(a + c)), float, unfused
+                    const float a = (float)((double)vs0 * s2), b = (float)((double)vs1 * s2), c = (float)((double)vs2 * s2);
+                    const float tr = __fadd_rn(a, c);
+                    e = __fsub_rn(__fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b)), __fmul_rn(harris_k, __fmul_rn(tr, tr)));
+                } else {
+                    const float a = __fmul_rn((float)((double)vs0 * s2), 0.5f), b = (float)((double)vs1 * s2);
+                    const float c = __fmul_rn((float)((double)vs2 * s2), 0.5f);
+                    const float d = __fsub_rn(a, c);
+                    e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+                }
                 eig[(int64_t)y * eig_pitch_f + x] = e;
                 if (maxbits && (!mask || mask[(int64_t)y * mask_pitch + x])) lmax = max(lmax, enc_f32(e));
             }
@@ -116,8 +123,8 @@ eig_kernel(const uint8_t *__restrict__ img, int H, int W, int64_t pitch, int bs,
 
 static size_t eig_smem_bytes(int bs) { return (size_t)(2 + bs) * 3 * EW * sizeof(int); }
 
-static int launch_eig(const uint8_t *gray, int H, int W, int64_t pitch, int bs, float *eig, int64_t eig_pitch_bytes,
-                      const uint8_t *mask, int64_t mask_pitch, uint32_t *maxbits, cudaStream_t st)
+static int launch_eig(const uint8_t *gray, int H, int W, int64_t pitch, int bs, int harris, double k, float *eig,
+                      int64_t eig_pitch_bytes, const uint8_t *mask, int64_t mask_pitch, uint32_t *maxbits, cudaStream_t st)
 {
     if (!gray || !eig || H <= 0 || W <= 0 || bs < 1 || bs > MAX_BLOCK || pitch < W || eig_pitch_bytes % 4 != 0 ||
         eig_pitch_bytes < (int64_t)W * 4)
@@ -128,7 +135,7 @@ static int launch_eig(const uint8_t *gray, int H, int W, int64_t pitch, int bs, 
     const double s2 = (double)scale * (double)scale;
     const int nout = EW - bs + 1;
     dim3 grid((W + nout - 1) / nout, (H + ERS - 1) / ERS);
-    eig_kernel<<<grid, EW, eig_smem_bytes(bs), st>>>(gray, H, W, pitch, bs, s2, eig, eig_pitch_bytes / 4, mask, mask_pitch, maxbits);
+    eig_kernel<<<grid, EW, eig_smem_bytes(bs), st>>>(gray, H, W, pitch, bs, s2, harris ? 1 : 0, (float)k, eig, eig_pitch_bytes / 4, mask, mask_pitch, maxbits);
     return check_launch("eig_kernel");
 }
 
@@ -168,7 +175,9 @@ constexpr int EN_BORDER_SPLIT = 4;        // border strips (byte gathers, ~4x sl
 struct EigNmsArgs {
     const uint8_t *img; int H, W; int64_t pitch;
     const uint8_t *mask; int64_t mask_pitch;
-    int bs; double s2, s2h, quality;
+    int bs;
+    float harris_k;           // HARRIS instantiations only: k of cv2.cornerHarris, rounded to float as OpenCV's calcHarris does
+    double s2, s2h, quality;
     GfttCounters *cnt; unsigned long long *keys; uint32_t cap;
     int outw, left, nstrips, word_ok;
     int first_right;          // strips >= first_right (and strip 0) reach outside the image: border variant
@@ -242,7 +251,7 @@ __device__ __forceinline__ void hbox_smem(const int *v, int *out, int *rowbuf, i
     for (int k = 1; k < 4; k++) { s += p[k - 1 + bs] - p[k - 1]; out[k] = s; }
 }
 
-template <int BS, bool MASK, bool BORDER>
+template <int BS, bool MASK, bool BORDER, bool HARRIS>
 __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int Y0, int Y1, int *wsm, int lane)
 {
     const int bs = BS ? BS : a.bs;
@@ -359,10 +368,17 @@ __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int 
         float e[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float fa = (float)((double)bxx[k] * a.s2h), fb = (float)((double)bxy[k] * a.s2);
-            const float fc = (float)((double)byy[k] * a.s2h);
-            const float d = __fsub_rn(fa, fc);
-            e[k] = __fsub_rn(__fadd_rn(fa, fc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(fb, fb))));
+            if (HARRIS) {                                 // cv2.cornerHarris: (a*c - b*b) - k*((a + c)*(a + c)), float, unfused
+                const float fa = (float)((double)bxx[k] * a.s2), fb = (float)((double)bxy[k] * a.s2);
+                const float fc = (float)((double)byy[k] * a.s2);
+                const float tr = __fadd_rn(fa, fc);
+                e[k] = __fsub_rn(__fsub_rn(__fmul_rn(fa, fc), __fmul_rn(fb, fb)), __fmul_rn(a.harris_k, __fmul_rn(tr, tr)));
+            } else {
+                const float fa = (float)((double)bxx[k] * a.s2h), fb = (float)((double)bxy[k] * a.s2);
+                const float fc = (float)((double)byy[k] * a.s2h);
+                const float d = __fsub_rn(fa, fc);
+                e[k] = __fsub_rn(__fadd_rn(fa, fc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(fb, fb))));
+            }
         }
         // ---- masked maximum over the pixels this lane owns ------------------------------------------------------------------
         unsigned mcur = 0xfu;
@@ -419,7 +435,7 @@ __device__ __forceinline__ void eig_nms_job(const EigNmsArgs &a, int strip, int 
     if (lane == 0 && lbits) atomicMax(&a.cnt->maxbits, lbits);
 }
 
-template <int BS, bool MASK>
+template <int BS, bool MASK, bool HARRIS = false>
 __global__ void __launch_bounds__(EN_WARPS * 32, EN_MIN_CTAS)
 eig_nms_kernel(const __grid_constant__ EigNmsArgs a)
 {
@@ -436,32 +452,32 @@ eig_nms_kernel(const __grid_constant__ EigNmsArgs a)
         const int sb = job % a.nborder, chunk = job / a.nborder;
         const int strip = a.nborder == a.nstrips ? sb : (sb == 0 ? 0 : a.first_right + sb - 1);
         const int Y0 = chunk * a.rows_border;
-        eig_nms_job<BS, MASK, true>(a, strip, Y0, min(a.H, Y0 + a.rows_border), wsm, lane);
+        eig_nms_job<BS, MASK, true, HARRIS>(a, strip, Y0, min(a.H, Y0 + a.rows_border), wsm, lane);
     } else {
         const int j = job - nbj, nfast = a.nstrips - a.nborder;
         const int strip = 1 + j % nfast, chunk = j / nfast;
         const int Y0 = chunk * a.rows_fast;
-        eig_nms_job<BS, MASK, false>(a, strip, Y0, min(a.H, Y0 + a.rows_fast), wsm, lane);
+        eig_nms_job<BS, MASK, false, HARRIS>(a, strip, Y0, min(a.H, Y0 + a.rows_fast), wsm, lane);
     }
 }
 
-template <int BS>
+template <int BS, bool HARRIS = false>
 static int launch_eig_nms_bs(const EigNmsArgs &a, cudaStream_t st)
 {
     const size_t smem = (size_t)a.warp_smem_ints * 4 * EN_WARPS;
     const int blocks = (a.njobs + EN_WARPS - 1) / EN_WARPS;
     if (a.mask) {
-        if (smem > 48 * 1024) IBT_CUDA_TRY(cudaFuncSetAttribute(eig_nms_kernel<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eig_nms_kernel<BS, true><<<blocks, EN_WARPS * 32, smem, st>>>(a);
+        if (smem > 48 * 1024) IBT_CUDA_TRY(cudaFuncSetAttribute(eig_nms_kernel<BS, true, HARRIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eig_nms_kernel<BS, true, HARRIS><<<blocks, EN_WARPS * 32, smem, st>>>(a);
     } else {
-        if (smem > 48 * 1024) IBT_CUDA_TRY(cudaFuncSetAttribute(eig_nms_kernel<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eig_nms_kernel<BS, false><<<blocks, EN_WARPS * 32, smem, st>>>(a);
+        if (smem > 48 * 1024) IBT_CUDA_TRY(cudaFuncSetAttribute(eig_nms_kernel<BS, false, HARRIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eig_nms_kernel<BS, false, HARRIS><<<blocks, EN_WARPS * 32, smem, st>>>(a);
     }
     return check_launch("eig_nms_kernel");
 }
 
-static int launch_eig_nms(const uint8_t *gray, int H, int W, int64_t pitch, int bs, const uint8_t *mask, int64_t mask_pitch,
-                          double quality, GfttCounters *cnt, unsigned long long *keys, uint32_t cap, cudaStream_t st)
+static int launch_eig_nms(const uint8_t *gray, int H, int W, int64_t pitch, int bs, int harris, double harris_k,
+                          const uint8_t *mask, int64_t mask_pitch, double quality, GfttCounters *cnt, unsigned long long *keys, uint32_t cap, cudaStream_t st)
 {
     if (bs < 1 || bs > MAX_BLOCK) return IBT_E_INVALID;
     EigNmsArgs a;
@@ -469,6 +485,7 @@ static int launch_eig_nms(const uint8_t *gray, int H, int W, int64_t pitch, int 
     const float scale = (float)(1.0 / (4.0 * bs * 255.0));       // OpenCV's Sobel scale for ksize 3
     a.s2 = (double)scale * (double)scale; a.s2h = a.s2 * 0.5;     // the halving of a and c folded in (exact: power of two)
     a.quality = quality; a.cnt = cnt; a.keys = keys; a.cap = cap;
+    a.harris_k = (float)harris_k;
     // strip geometry: lane 0's first column is `left` columns before the strip (Sobel edge + window reach + NMS halo, rounded
     // to words); a warp owns `outw` of its 128 support columns
     const int half = bs / 2;                                      // window offsets [-half, bs - 1 - half]
@@ -498,6 +515,9 @@ static int launch_eig_nms(const uint8_t *gray, int H, int W, int64_t pitch, int 
     if (a.rows_border < 8) a.rows_border = 8;
     a.chunks_border = (H + a.rows_border - 1) / a.rows_border;
     a.njobs = a.nborder * a.chunks_border + nfast * ((H + rows - 1) / rows);
+    // cv2's useHarrisDetector=True (never set by the reference): the response formula changes, nothing else; it takes the
+    // runtime-blockSize instantiation whatever the block size
+    if (harris) return launch_eig_nms_bs<0, true>(a, st);
     if (bs == 10) return launch_eig_nms_bs<10>(a, st);
     if (bs == 3) return launch_eig_nms_bs<3>(a, st);
     return launch_eig_nms_bs<0>(a, st);
@@ -1152,12 +1172,12 @@ static GfttLayout gftt_layout(int H, int W)
 
 // Both launches of goodFeaturesToTrack on `st`; nothing is read back.  count_dev (device int) receives the corner count.
 static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch, int H, int W,
-                        int maxCorners, double qualityLevel, double minDistance, int blockSize, void *workspace,
-                        size_t workspace_bytes, float *out_xy, int cap, int *count_dev, cudaStream_t st)
+                        int maxCorners, double qualityLevel, double minDistance, int blockSize, int useHarris, double harris_k,
+                        void *workspace, size_t workspace_bytes, float *out_xy, int cap, int *count_dev, cudaStream_t st)
 {
     if (!gray || !workspace || H < 3 || W < 3 || H > 65535 || W > 65535 || (int64_t)H * W > 0x7fffffffLL ||
         cap < 0 || (cap > 0 && !out_xy) || (mask && mask_pitch < W) || qualityLevel < 0 || minDistance < 0 || minDistance > 1024 ||
-        pitch < W)
+        pitch < W || !(harris_k == harris_k))
         return IBT_E_INVALID;
     const GfttLayout L = gftt_layout(H, W);
     if (workspace_bytes < L.total) return IBT_E_WORKSPACE;
@@ -1165,7 +1185,7 @@ static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask,
     GfttCounters *cnt = reinterpret_cast<GfttCounters *>(ws + L.off_cnt);
     IBT_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(GfttCounters), st));
     unsigned long long *keys0 = reinterpret_cast<unsigned long long *>(ws + L.off_keys0);
-    int rc = launch_eig_nms(gray, H, W, pitch, blockSize, mask, mask_pitch, qualityLevel, cnt, keys0, L.cap, st);
+    int rc = launch_eig_nms(gray, H, W, pitch, blockSize, useHarris, harris_k, mask, mask_pitch, qualityLevel, cnt, keys0, L.cap, st);
     if (rc) return rc;
     SelArgs a;
     a.cnt = cnt; a.keys0 = keys0;
@@ -1214,7 +1234,14 @@ static int gftt_enqueue(const uint8_t *gray, int64_t pitch, const uint8_t *mask,
 IBT_API int ibt_min_eigen_f32(const uint8_t *gray, int H, int W, int64_t pitch, int blockSize, float *eig,
                               int64_t eig_pitch, void *stream)
 {
-    return ibt::launch_eig(gray, H, W, pitch, blockSize, eig, eig_pitch, nullptr, 0, nullptr, static_cast<cudaStream_t>(stream));
+    return ibt::launch_eig(gray, H, W, pitch, blockSize, 0, 0.0, eig, eig_pitch, nullptr, 0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+IBT_API int ibt_corner_harris_f32(const uint8_t *gray, int H, int W, int64_t pitch, int blockSize, double k, float *dst,
+                                  int64_t dst_pitch, void *stream)
+{
+    if (!(k == k)) return IBT_E_INVALID;
+    return ibt::launch_eig(gray, H, W, pitch, blockSize, 1, k, dst, dst_pitch, nullptr, 0, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 IBT_API size_t ibt_gftt_workspace_bytes(int H, int W)
@@ -1224,24 +1251,26 @@ IBT_API size_t ibt_gftt_workspace_bytes(int H, int W)
 }
 
 IBT_API int ibt_gftt_async(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch, int H, int W,
-                           int maxCorners, double qualityLevel, double minDistance, int blockSize, void *workspace,
-                           size_t workspace_bytes, float *out_xy, int cap, int *count_dev, void *stream)
+                           int maxCorners, double qualityLevel, double minDistance, int blockSize, int useHarrisDetector,
+                           double k, void *workspace, size_t workspace_bytes, float *out_xy, int cap, int *count_dev,
+                           void *stream)
 {
     if (!count_dev) return IBT_E_INVALID;
-    return ibt::gftt_enqueue(gray, pitch, mask, mask_pitch, H, W, maxCorners, qualityLevel, minDistance, blockSize, workspace,
-                             workspace_bytes, out_xy, cap, count_dev, static_cast<cudaStream_t>(stream));
+    return ibt::gftt_enqueue(gray, pitch, mask, mask_pitch, H, W, maxCorners, qualityLevel, minDistance, blockSize,
+                             useHarrisDetector, k, workspace, workspace_bytes, out_xy, cap, count_dev,
+                             static_cast<cudaStream_t>(stream));
 }
 
 IBT_API int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch, int H, int W,
-                     int maxCorners, double qualityLevel, double minDistance, int blockSize, void *workspace,
-                     size_t workspace_bytes, float *out_xy, int cap, int *out_count, void *stream)
+                     int maxCorners, double qualityLevel, double minDistance, int blockSize, int useHarrisDetector, double k,
+                     void *workspace, size_t workspace_bytes, float *out_xy, int cap, int *out_count, void *stream)
 {
     using namespace ibt;
     if (!out_count) return IBT_E_INVALID;
     *out_count = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = gftt_enqueue(gray, pitch, mask, mask_pitch, H, W, maxCorners, qualityLevel, minDistance, blockSize, workspace,
-                          workspace_bytes, out_xy, cap, nullptr, st);
+    int rc = gftt_enqueue(gray, pitch, mask, mask_pitch, H, W, maxCorners, qualityLevel, minDistance, blockSize,
+                          useHarrisDetector, k, workspace, workspace_bytes, out_xy, cap, nullptr, st);
     if (rc) return rc;
     // the one host round trip of the synchronous form: the corner count decides the shapes the caller allocates next
     struct Head { uint32_t maxbits, ncand, nsel, nacc, nout; int32_t error; };

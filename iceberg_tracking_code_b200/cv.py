@@ -367,6 +367,22 @@ def cornerMinEigenVal(src, blockSize, ksize=3):
     return _out(eig, as_np)
 
 
+def cornerHarris(src, blockSize, ksize=3, k=0.04):
+    """cv2.cornerHarris(u8 (H,W), blockSize, 3, k) -> (H,W) f32: the response goodFeaturesToTrack(useHarrisDetector=True)
+    ranks.  The reference leaves useHarrisDetector at False (s1:240-243); cv2's signature carries it."""
+    if ksize != 3:
+        raise error("cornerHarris: only ksize=3 is implemented (the value goodFeaturesToTrack uses)")
+    as_np = _is_np(src)
+    s = _to_dev(src, np.uint8, "cornerHarris src")
+    if s.ndim != 2:
+        raise error("cornerHarris: expected a single-channel (H,W) u8 image")
+    H, W = s.shape
+    dst = torch.empty((H, W), dtype=torch.float32, device=s.device)
+    N.check(N.lib().ibt_corner_harris_f32(_ptr(s), H, W, W, int(blockSize), float(k), _ptr(dst), W * 4, _stream()),
+            "ibt_corner_harris_f32")
+    return _out(dst, as_np)
+
+
 _gftt_ws = {}
 _gftt_lock = __import__("threading").Lock()
 
@@ -389,9 +405,8 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None,
                         useHarrisDetector=False, k=0.04):
     """cv2.goodFeaturesToTrack(frame_gray, mask=mask, **feature_params) (s1:437).
     Returns (K,1,2) float32 integer-valued (x, y) ordered by response, or None when there is no corner
-    (callers test `if p is not None`, s1:445)."""
-    if useHarrisDetector:
-        raise error("goodFeaturesToTrack: useHarrisDetector=True is not implemented (the reference never sets it)")
+    (callers test `if p is not None`, s1:445).  useHarrisDetector=True ranks cv2.cornerHarris(image, blockSize, 3, k)
+    instead of the minimal eigenvalue (the reference never sets it)."""
     if not (qualityLevel > 0) or minDistance < 0:
         raise error("goodFeaturesToTrack: qualityLevel must be > 0 and minDistance >= 0")
     as_np = _is_np(image)
@@ -409,7 +424,8 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None,
     ws, out = _gftt_workspace(img.device, H, W)
     cnt = C.c_int(0)
     rc = N.lib().ibt_gftt(_ptr(img), W, _ptr(m), W, H, W, int(maxCorners), float(qualityLevel), float(minDistance),
-                          int(blockSize), _ptr(ws), ws.numel(), _ptr(out), out.shape[0], C.byref(cnt), _stream())
+                          int(blockSize), 1 if useHarrisDetector else 0, float(k), _ptr(ws), ws.numel(), _ptr(out), out.shape[0],
+                          C.byref(cnt), _stream())
     N.check(rc, "ibt_gftt")
     if cnt.value == 0:
         return None

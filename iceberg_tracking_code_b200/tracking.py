@@ -262,8 +262,7 @@ class SequenceTracker:
         group, on the CURRENT stream, without waiting for it (ibt_gftt_async): returns the handle seed(prefetched=) takes.
         track_sequence issues it on the side stream one frame ahead, so the corners are ready when the group starts."""
         fp = self.feature_params
-        if fp.get("useHarrisDetector", False):
-            raise cv.error("goodFeaturesToTrack: useHarrisDetector=True is not implemented (the reference never sets it)")
+        harris, hk = (1 if fp.get("useHarrisDetector", False) else 0), float(fp.get("k", 0.04))
         q, md, bs = float(fp["qualityLevel"]), float(fp["minDistance"]), int(fp.get("blockSize", 3))
         if not (q > 0) or md < 0:
             raise cv.error("goodFeaturesToTrack: qualityLevel must be > 0 and minDistance >= 0")
@@ -286,7 +285,8 @@ class SequenceTracker:
         out = torch.empty((cap, 2), dtype=torch.float32, device=self.device)
         cnt = torch.zeros((1,), dtype=torch.int32, device=self.device)
         p = cv._ptr
-        N.check(N.lib().ibt_gftt_async(p(img), img.stride(0), p(m), W, H, W, maxc, q, md, bs, p(self._ws), self._ws.numel(),
+        N.check(N.lib().ibt_gftt_async(p(img), img.stride(0), p(m), W, H, W, maxc, q, md, bs, harris, hk, p(self._ws),
+                                       self._ws.numel(),
                                        p(out), cap, p(cnt), cv._stream()), "ibt_gftt_async")
         # (nout, error) of the workspace counters (GfttCounters: maxbits, ncand, nsel, nacc, nout, error): a capacity overflow
         # raised on the device must not pass as "no corners"

@@ -119,18 +119,23 @@ int ibt_lk_fb(const ibt_pyramid_t *prev, const ibt_pyramid_t *next,
 int ibt_lk_set_max_ctas_per_sm(int ctas);
 
 /* ---- K2: cv2.goodFeaturesToTrack(frame_gray, mask=mask, **feature_params)  s1:437; s0_1:167.
- * cornerMinEigenVal test hook (Sobel3 -> products -> blockSize^2 box sum -> lambda_min). */
+ * cornerMinEigenVal / cornerHarris test hooks (Sobel3 -> products -> blockSize^2 box sum -> lambda_min, or OpenCV's Harris
+ * response (a*c - b*b) - k*(a + c)^2 in float). */
 int ibt_min_eigen_f32(const uint8_t *gray, int H, int W, int64_t pitch, int blockSize,
                       float *eig, int64_t eig_pitch, void *stream);
+int ibt_corner_harris_f32(const uint8_t *gray, int H, int W, int64_t pitch, int blockSize, double k,
+                          float *dst, int64_t dst_pitch, void *stream);
 
 size_t ibt_gftt_workspace_bytes(int H, int W);
 /* mask may be NULL (all allowed).  out_xy (cap,2) f32 receives integer-valued x,y ordered by
  * response (ties: higher linear address first), culled by minDistance on cv2's cell grid and
- * truncated to maxCorners (<= 0: unlimited).  out_count: HOST int*.  SYNCHRONISES `stream`
- * (the corner count decides the shapes the caller allocates next, like cv2's return value).
+ * truncated to maxCorners (<= 0: unlimited).  useHarrisDetector / k: cv2's arguments of the same name (the reference leaves
+ * them at False / 0.04, s1:240-243): non-zero ranks the Harris response instead of lambda_min.  out_count: HOST int*.
+ * SYNCHRONISES `stream` (the corner count decides the shapes the caller allocates next, like cv2's return value).
  * Returns IBT_E_CAPACITY (and the full count) if cap was too small. */
 int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
              int H, int W, int maxCorners, double qualityLevel, double minDistance, int blockSize,
+             int useHarrisDetector, double k,
              void *workspace, size_t workspace_bytes,
              float *out_xy, int cap, int *out_count, void *stream);
 /* Same two launches, nothing read back: count_dev (DEVICE int*) receives the corner count when the stream reaches it, out_xy
@@ -138,6 +143,7 @@ int ibt_gftt(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t ma
  * travels to ibt_lk_fb as n_dev.  A capacity overflow is reported by the next synchronous call on the workspace. */
 int ibt_gftt_async(const uint8_t *gray, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
                    int H, int W, int maxCorners, double qualityLevel, double minDistance, int blockSize,
+                   int useHarrisDetector, double k,
                    void *workspace, size_t workspace_bytes,
                    float *out_xy, int cap, int *count_dev, void *stream);
 

@@ -165,6 +165,16 @@ def cornerMinEigenVal(img, blockSize, ksize=3):
     return eig
 
 
+def cornerHarris(img, blockSize, ksize=3, k=0.04):
+    """cv2.cornerHarris(img, blockSize, 3, k): the response goodFeaturesToTrack(useHarrisDetector=True) ranks (A.6 step 3')."""
+    assert ksize == 3
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    out = np.empty((h, w), np.float32)
+    lib().orc_harris_f32(_p(img), C.c_int(h), C.c_int(w), C.c_int(blockSize), C.c_double(float(k)), _p(out))
+    return out
+
+
 def gftt_select(eig, mask, maxCorners, qualityLevel, minDistance):
     """A.6 steps 4-8 on a given eig map (not modified)."""
     eig = np.array(eig, np.float32, copy=True, order="C")
@@ -184,9 +194,10 @@ def gftt_select(eig, mask, maxCorners, qualityLevel, minDistance):
 
 def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None, blockSize=3,
                         useHarrisDetector=False, k=0.04):
-    """A.6; same call as s1:437."""
-    assert not useHarrisDetector
-    return gftt_select(cornerMinEigenVal(image, blockSize), mask, maxCorners, qualityLevel, minDistance)
+    """A.6; same call as s1:437.  useHarrisDetector=True ranks cornerHarris(image, blockSize, 3, k) instead of lambda_min (the
+    reference never sets it; cv2's signature has it)."""
+    resp = cornerHarris(image, blockSize, 3, k) if useHarrisDetector else cornerMinEigenVal(image, blockSize)
+    return gftt_select(resp, mask, maxCorners, qualityLevel, minDistance)
 
 
 def photo_to_utm(xy, cam):

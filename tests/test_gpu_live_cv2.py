@@ -88,3 +88,23 @@ def test_lk_live(ibt, seed):
         both = (r["st0"].ravel() == 1) & (r_st0.ravel() == 1) & (r["st1"].ravel() == 1) & (r_st.ravel() == 1)
         clear = both & (np.abs(d_ref - 1.0) > 0.02)          # decisions within the position tolerance of the threshold may flip
         assert np.mean((d_ref < 1.0)[clear] == r["valid"][clear]) >= 0.99, lp
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_harris_live(ibt, seed):
+    """the Harris branch of the detector (cv2's useHarrisDetector=True) against cv2: response maps and corner lists"""
+    import harris_cases as HC
+    rng = np.random.default_rng(900 + seed)                 # the seeds of the oracle's live test
+    h, w = int(rng.integers(40, 260)), int(rng.integers(40, 330))
+    img = L._texture(rng, h, w, smooth=int(rng.integers(1, 4)))
+    mask = (rng.random((h, w)) > 0.3).astype(np.uint8) * 255
+    for bs in (2, 3, 5, 10):
+        k = float(rng.choice([0.0, 0.04, 0.1]))
+        ref = cv2.cornerHarris(img, bs, 3, k)
+        assert np.abs(ibt.cornerHarris(img, bs, 3, k) - ref).max() <= HC.MAP_TOL * np.abs(ref).max(), (bs, k)
+        for q, md in ((0.01, 0), (0.05, 5), (0.01, 10)):
+            for m in (None, mask):
+                gp = dict(maxCorners=int(rng.choice([0, 300])), qualityLevel=q, minDistance=md, blockSize=bs,
+                          useHarrisDetector=True, k=k)
+                HC.check_lists(ibt.goodFeaturesToTrack(img, mask=m, **gp), cv2.goodFeaturesToTrack(img, mask=m, **gp),
+                               (seed, gp, m is not None))

@@ -236,3 +236,10 @@ def test_gftt_prefilter_fallback_and_ties_vs_oracle(ibt, oracle):
         ref = as_corners(oracle.goodFeaturesToTrack(per, **gp))
         assert got.shape == ref.shape and len(ref) > 50
         assert np.array_equal(got, ref), gp                            # order included: ties resolved like OpenCV
+
+
+def test_harris_branch_golden(ibt, golden):
+    """goodFeaturesToTrack(useHarrisDetector=True) / cornerHarris through the C-ABI vs cv2's recorded answers"""
+    import harris_cases as HC
+    HC.check_harris_golden(ibt, golden("kat_harris.npz"),
+                           {"texture": golden("kat_texture.npz"), "iceberg": golden("kat_iceberg.npz")})

@@ -110,3 +110,10 @@ def test_photo_to_utm_vs_reference(oracle, golden):
     g = golden("utm_expected.npz")
     got = oracle.photo_to_utm(g["xy"].astype(np.float64), g["cam"])
     assert np.abs(got - g["EN"]).max() <= 1e-6          # metres
+
+
+def test_harris_branch_golden(oracle, golden):
+    """goodFeaturesToTrack(useHarrisDetector=True) / cornerHarris vs cv2's recorded answers (make_harris_golden.py)"""
+    import harris_cases as HC
+    HC.check_harris_golden(oracle, golden("kat_harris.npz"),
+                           {"texture": golden("kat_texture.npz"), "iceberg": golden("kat_iceberg.npz")})

@@ -138,3 +138,24 @@ def test_min_eigen_live(oracle):
         ref = cv2.cornerMinEigenVal(img, bs, ksize=3)
         got = oracle.cornerMinEigenVal(img, bs)
         assert np.abs(got - ref).max() <= 3e-4 * np.abs(ref).max(), (h, w, bs)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_harris_live(oracle, seed):
+    """the Harris branch (useHarrisDetector=True; never set by the reference, part of cv2's signature): response maps and
+    corner lists against cv2 for random sizes, block sizes, k and masks"""
+    import harris_cases as HC
+    rng = np.random.default_rng(900 + seed)
+    h, w = int(rng.integers(40, 260)), int(rng.integers(40, 330))
+    img = _texture(rng, h, w, smooth=int(rng.integers(1, 4)))
+    mask = (rng.random((h, w)) > 0.3).astype(np.uint8) * 255
+    for bs in (2, 3, 5, 10):
+        k = float(rng.choice([0.0, 0.04, 0.1]))
+        ref = cv2.cornerHarris(img, bs, 3, k)
+        assert np.abs(oracle.cornerHarris(img, bs, 3, k) - ref).max() <= HC.MAP_TOL * np.abs(ref).max(), (bs, k)
+        for q, md in ((0.01, 0), (0.05, 5), (0.01, 10)):
+            for m in (None, mask):
+                gp = dict(maxCorners=int(rng.choice([0, 300])), qualityLevel=q, minDistance=md, blockSize=bs,
+                          useHarrisDetector=True, k=k)
+                HC.check_lists(oracle.goodFeaturesToTrack(img, mask=m, **gp), cv2.goodFeaturesToTrack(img, mask=m, **gp),
+                               (seed, gp, m is not None))
