@@ -761,6 +761,193 @@ lk_kernel(const __grid_constant__ LKArgs a, const __grid_constant__ LKMaps maps)
     }
 }
 
+// ---- multi-channel images ------------------------------------------------------------------------------------------
+// cv2.calcOpticalFlowPyrLK also takes 3- (or 4-) channel 8-bit images; the reference never does -- it converts
+// to gray first (s1:311) -- so this is the plain form of the solver, not the tuned one: no tensor maps, the generic
+// (runtime window) helpers, one pass.  OpenCV builds the pyramid and the Scharr planes per channel and sums every window
+// quantity (structure tensor, mismatch vector, residual) over the window pixels AND the channels; min-eigenvalue test and
+// Newton update are unchanged, err is divided by 32 * winW * cn * winH.  Channel planes arrive as cn single-channel
+// pyramids (the kernels that build them are the single-channel ones); channel c owns the c-th slab of a.warp_smem bytes.
+constexpr int LK_MC_MAX = 4;
+struct LKMcPyr {
+    LKPyr I[LK_MC_MAX], J[LK_MC_MAX];
+    int cn;
+};
+
+__device__ __noinline__ void lk_point_mc(const LKMcPyr &mc, const LKArgs &a, float ptx, float pty, bool use_init, bool want_status,
+                                         bool want_err, float &ox, float &oy, int &status, float &err, int &iters,
+                                         unsigned char *slab, int rowbase, int cq, bool lane_on, int lane)
+{
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const int cn = mc.cn;
+    const int winW = a.winW, winH = a.winH;
+    const int IPITCH = a.ipitch, JPITCH = a.jpitch;
+    const int JROWS = winH + 1 + 2 * LK_MARGIN;
+    const float halfx = (winW - 1) * 0.5f, halfy = (winH - 1) * 0.5f;
+    status = 1; err = 0.f;
+    const int L = mc.I[0].nlevels;
+    for (int level = L - 1; level >= 0; --level) {
+        const int rows = mc.I[0].lv[level].rows, cols = mc.I[0].lv[level].cols;
+        const float sc = __int_as_float((127 - level) << 23);       // 2^-level
+        float ppx = __fmul_rn(ptx, sc), ppy = __fmul_rn(pty, sc);
+        float nx, ny;
+        if (level == L - 1) {
+            if (use_init) { nx = __fmul_rn(ox, sc); ny = __fmul_rn(oy, sc); }
+            else { nx = ppx; ny = ppy; }
+        } else { nx = __fmul_rn(ox, 2.f); ny = __fmul_rn(oy, 2.f); }
+        ox = nx; oy = ny;
+        ppx = __fsub_rn(ppx, halfx); ppy = __fsub_rn(ppy, halfy);
+        const int ipx = cv_floor(ppx), ipy = cv_floor(ppy);
+        if (window_oob(ipx, ipy, winW, winH, rows, cols)) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        nx = __fsub_rn(nx, halfx); ny = __fsub_rn(ny, halfy);
+        const int ipxa = ipx & ~3;
+        int px0 = 0, py0 = 0, vx0 = 0;
+        bool staged = false;
+        const int jnx = cv_floor(nx), jny = cv_floor(ny);
+        const bool j_ok = !window_oob(jnx, jny, winW, winH, rows, cols);
+        if (j_ok) { vx0 = jnx - LK_MARGIN; px0 = vx0 & ~3; py0 = jny - LK_MARGIN; staged = true; }
+        __syncwarp();
+        for (int c = 0; c < cn; c++) {
+            unsigned char *sl = slab + (size_t)c * a.warp_smem;
+            stage_bytes(mc.I[c].lv[level], ipxa, ipy, winH + 1, IPITCH, lane, sl + a.off_ipatch);
+            stage_deriv<0, 0>(mc.I[c].lv[level], a, ipx, ipy, reinterpret_cast<uint32_t *>(sl), lane);
+        }
+        cp_async_commit();
+        if (j_ok)
+            for (int c = 0; c < cn; c++)
+                stage_bytes(mc.J[c].lv[level], px0, py0, JROWS, JPITCH, lane, slab + (size_t)c * a.warp_smem + a.off_jpatch);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+
+        uint32_t wtop, wbot;
+        int iw00, iw01, iw10, iw11;
+        bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), wtop, wbot, iw00, iw01, iw10, iw11);
+        const uint32_t iwtop = wtop, iwbot = wbot;
+        long long sA11 = 0, sA12 = 0, sA22 = 0, sC1 = 0, sC2 = 0;
+        for (int c = 0; c < cn; c++) {
+            unsigned char *sl = slab + (size_t)c * a.warp_smem;
+            long long t11, t12, t22, tc1, tc2;
+            build_template<0, 0>(a, sl + a.off_ipatch + (ipx - ipxa), reinterpret_cast<uint32_t *>(sl), reinterpret_cast<uint32_t *>(sl),
+                                 wtop, wbot, iw00, iw01, iw10, iw11, lane, t11, t12, t22, tc1, tc2);
+            sA11 += t11; sA12 += t12; sA22 += t22; sC1 += tc1; sC2 += tc2;
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        const float A11 = __fmul_rn(__ll2float_rn(sA11), FLT_SCALE);
+        const float A12 = __fmul_rn(__ll2float_rn(sA12), FLT_SCALE);
+        const float A22 = __fmul_rn(__ll2float_rn(sA22), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * winW * winH));
+        if (a.flags & IBT_LK_GET_MIN_EIGENVALS) err = minEig;
+        if (minEig < a.minEigThr || D < 1.1920929e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < a.maxCount; j++) {
+            const int inx = cv_floor(nx), iny = cv_floor(ny);
+            if (window_oob(inx, iny, winW, winH, rows, cols)) {
+                if (level == 0) status = 0;
+                break;
+            }
+            if (!staged || (unsigned)(inx - vx0) > 2u * LK_MARGIN || (unsigned)(iny - py0) > 2u * LK_MARGIN) {
+                vx0 = inx - LK_MARGIN; px0 = vx0 & ~3; py0 = iny - LK_MARGIN;
+                for (int c = 0; c < cn; c++)
+                    restage_sync(mc.J[c].lv[level], px0, py0, JROWS, JPITCH, slab + (size_t)c * a.warp_smem + a.off_jpatch, lane);
+                staged = true;
+            }
+            bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wtop, wbot, iw00, iw01, iw10, iw11);
+            long long sb1 = 0, sb2 = 0;
+            for (int c = 0; c < cn; c++) {
+                const unsigned char *sl = slab + (size_t)c * a.warp_smem;
+                long long t1, t2;
+                newton_sums<0, 0>(a, sl + a.off_jpatch, inx - px0, iny - py0, wtop, wbot, reinterpret_cast<const uint32_t *>(sl),
+                                  rowbase, cq, lane_on, t1, t2);
+                sb1 += t1; sb2 += t2;
+            }
+            ++iters;
+            const float b1 = __fmul_rn(__ll2float_rn(sb1 - sC1), FLT_SCALE);
+            const float b2 = __fmul_rn(__ll2float_rn(sb2 - sC2), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            ox = __fadd_rn(nx, halfx); oy = __fadd_rn(ny, halfy);
+            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= a.eps2) break;
+            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) < 0.01f && fabsf(__fadd_rn(dy, pdy)) < 0.01f) {
+                ox = __fsub_rn(ox, __fmul_rn(dx, 0.5f)); oy = __fsub_rn(oy, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0 && !(a.flags & IBT_LK_GET_MIN_EIGENVALS) && (want_status || want_err)) {
+            const float qx = __fsub_rn(ox, halfx), qy = __fsub_rn(oy, halfy);
+            const int iqx = cv_floor(qx), iqy = cv_floor(qy);
+            if (window_oob(iqx, iqy, winW, winH, rows, cols)) { status = 0; err = 0.f; continue; }
+            if (!want_err) continue;
+            if (!staged || (unsigned)(iqx - vx0) > 2u * LK_MARGIN || (unsigned)(iqy - py0) > 2u * LK_MARGIN) {
+                vx0 = iqx - LK_MARGIN; px0 = vx0 & ~3; py0 = iqy - LK_MARGIN;
+                for (int c = 0; c < cn; c++)
+                    restage_sync(mc.J[c].lv[level], px0, py0, JROWS, JPITCH, slab + (size_t)c * a.warp_smem + a.off_jpatch, lane);
+            }
+            bilinear_weights(__fsub_rn(qx, (float)iqx), __fsub_rn(qy, (float)iqy), wtop, wbot, iw00, iw01, iw10, iw11);
+            long long s = 0;
+            for (int c = 0; c < cn; c++) {
+                const unsigned char *sl = slab + (size_t)c * a.warp_smem;
+                s += window_err<0, 0>(a, sl + a.off_jpatch, iqx - px0, iqy - py0, wtop, wbot, sl + a.off_ipatch, ipx - ipxa, iwtop, iwbot,
+                                      rowbase, cq, lane_on);
+            }
+            err = __fdiv_rn(__ll2float_rn(s), (float)(32 * winW * cn * winH));
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    if (!status && !(a.flags & IBT_LK_GET_MIN_EIGENVALS)) err = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+lk_mc_kernel(const __grid_constant__ LKArgs a, const __grid_constant__ LKMcPyr mc)
+{
+    extern __shared__ __align__(128) unsigned char lk_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *slab = lk_smem + (size_t)wib * a.warp_smem * mc.cn;
+    const int grp = lane / a.nl;
+    const bool lane_on = grp < a.ng;
+    const int rowbase = lane_on ? grp * a.rg : 0, cq = lane_on ? lane - grp * a.nl : 0;
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = (int)atomicAdd(a.work_counter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= a.n) break;
+        float ox = 0.f, oy = 0.f, err;
+        int status, iters = 0;
+        const bool use_init = (a.flags & IBT_LK_USE_INITIAL_FLOW) != 0;
+        if (use_init) { ox = a.p1[2 * k]; oy = a.p1[2 * k + 1]; }
+        lk_point_mc(mc, a, a.p0[2 * k], a.p0[2 * k + 1], use_init, a.st1 != nullptr, a.err1 != nullptr, ox, oy, status, err, iters,
+                    slab, rowbase, cq, lane_on, lane);
+        if (lane == 0) {
+            a.p1[2 * k] = ox; a.p1[2 * k + 1] = oy;
+            if (a.st1) a.st1[k] = (uint8_t)status;
+            if (a.err1) a.err1[k] = err;
+            if (a.iters) a.iters[k] = iters;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {                                       // the last warp to leave re-arms the work queue (see lk_kernel)
+        __threadfence();
+        if (atomicAdd(a.work_counter + 1, 1u) == a.total_warps - 1u) {
+            a.work_counter[0] = 0u; a.work_counter[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
 static int fill_pyr(const ibt_pyramid_t *p, LKPyr &o, bool need_deriv)
 {
     if (!p || p->nlevels < 1 || p->nlevels > IBT_MAX_LEVELS) return IBT_E_INVALID;
@@ -915,6 +1102,77 @@ static int launch_lk(LKArgs &a, const ibt_pyramid_t *A, const ibt_pyramid_t *B, 
     return check_launch("ibt_lk");
 }
 
+// cv2.calcOpticalFlowPyrLK on multi-channel images: cn single-channel pyramids per image (channel planes)
+static int launch_lk_mc(LKArgs &a, const ibt_pyramid_t *const *A, const ibt_pyramid_t *const *B, int cn, int winW, int winH,
+                        int max_count, double epsilon, double min_eig, cudaStream_t st)
+{
+    if (a.n < 0 || winW < 3 || winH < 3 || winW > IBT_MAX_WIN || winH > IBT_MAX_WIN || cn < 1 || cn > LK_MC_MAX || !A || !B)
+        return IBT_E_INVALID;
+    if (a.n == 0) return IBT_OK;
+    if (!a.p0 || !a.p1) return IBT_E_INVALID;
+    static thread_local LKMcPyr mc;
+    mc.cn = cn;
+    for (int c = 0; c < cn; c++) {
+        int rc = fill_pyr(A[c], mc.I[c], true);
+        if (rc) return rc;
+        rc = fill_pyr(B[c], mc.J[c], false);
+        if (rc) return rc;
+        if (A[c]->nlevels != A[0]->nlevels || B[c]->nlevels != A[0]->nlevels) return IBT_E_INVALID;
+        for (int l = 0; l < A[0]->nlevels; l++)
+            if (A[c]->rows[l] != A[0]->rows[l] || A[c]->cols[l] != A[0]->cols[l] || B[c]->rows[l] != A[0]->rows[l] ||
+                B[c]->cols[l] != A[0]->cols[l])
+                return IBT_E_INVALID;
+    }
+    a.winW = winW; a.winH = winH;
+    a.nl = lk_nl(winW); a.ng = lk_ng(winW, winH); a.rg = lk_rg(winW, winH);
+    a.trows = lk_trows(winW, winH); a.tcols = lk_tcols(winW);
+    a.nstrips = lk_nstrips(winW);
+    a.strip_cols = lk_strip_cols(winW);
+    a.dpitch = lk_dpitch(winW);
+    a.ipitch = lk_ipitch(winW);
+    a.jpitch = lk_jpitch(winW);
+    a.jrows = winH + 1 + 2 * LK_MARGIN;
+    size_t off = (size_t)a.trows * a.tcols * 4;                  // per-channel slab: the layout of launch_lk
+    const size_t dbytes = (size_t)(winH + 1) * a.dpitch * 4;
+    if (off < dbytes) off = dbytes;
+    off = (off + 127) & ~(size_t)127;
+    a.off_ipatch = (int)off; off += (size_t)(winH + 1) * a.ipitch; off = (off + 127) & ~(size_t)127;
+    a.off_jpatch = (int)off; off += (size_t)(a.trows + 1 + 2 * LK_MARGIN) * a.jpitch;
+    a.warp_smem = (int)((off + 127) & ~(size_t)127);
+    a.maxCount = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
+    if (epsilon < 0) epsilon = 0;
+    if (epsilon > 10) epsilon = 10;
+    a.eps2 = (float)(epsilon * epsilon);
+    a.minEigThr = (float)min_eig;
+    const size_t per_warp = (size_t)a.warp_smem * cn;
+    int wpc = (int)((200 * 1024) / per_warp);
+    if (wpc < 1) return IBT_E_INVALID;
+    if (wpc > 8) wpc = 8;
+    const size_t smem = per_warp * wpc;
+    int ctas = (int)((227 * 1024) / (smem + 1024));
+    if (ctas < 1) ctas = 1;
+    if (ctas * wpc > 16) ctas = 16 / wpc > 0 ? 16 / wpc : 1;
+    int dev_id = 0;
+    IBT_CUDA_TRY(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64) return IBT_E_INVALID;
+    {
+        std::lock_guard<std::mutex> lock(lk_mu);
+        static bool mc_attr_set[64] = {false};
+        if (!mc_attr_set[dev_id]) {
+            IBT_CUDA_TRY(cudaFuncSetAttribute(lk_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            mc_attr_set[dev_id] = true;
+        }
+        const int rc = lk_queue_for(dev_id, st, &a.work_counter);
+        if (rc) return rc;
+    }
+    int blocks = kNumSMs * ctas;
+    const int need = (a.n + wpc - 1) / wpc;
+    if (blocks > need) blocks = need;
+    a.total_warps = (unsigned)(blocks * wpc);
+    lk_mc_kernel<<<blocks, wpc * 32, smem, st>>>(a, mc);
+    return check_launch("ibt_lk_multichannel");
+}
+
 } // namespace ibt
 
 IBT_API int ibt_lk_set_max_ctas_per_sm(int ctas)
@@ -947,4 +1205,15 @@ IBT_API int ibt_lk_fb(const ibt_pyramid_t *prev, const ibt_pyramid_t *next, cons
     a.p1 = p1; a.st1 = st1; a.err1 = err1; a.p0r = p0r; a.st0 = st0; a.err0 = err0;
     a.fbdist = fbdist; a.alive = alive; a.iters = iters; a.iter_total = iter_total;
     return ibt::launch_lk(a, prev, next, winW, winH, max_count, epsilon, min_eig_threshold, static_cast<cudaStream_t>(stream));
+}
+
+IBT_API int ibt_lk_multichannel(const ibt_pyramid_t *const *pyrI, const ibt_pyramid_t *const *pyrJ, int cn, const float *pts,
+                                float *next_pts, int N, int winW, int winH, int max_count, double epsilon,
+                                double min_eig_threshold, int flags, uint8_t *status, float *err, int32_t *iters, void *stream)
+{
+    ibt::LKArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p0 = pts; a.n = N; a.flags = flags; a.fb = 0;
+    a.p1 = next_pts; a.st1 = status; a.err1 = err; a.iters = iters;
+    return ibt::launch_lk_mc(a, pyrI, pyrJ, cn, winW, winH, max_count, epsilon, min_eig_threshold, static_cast<cudaStream_t>(stream));
 }

@@ -241,7 +241,48 @@ def _as_pyramid(img, winSize, maxLevel, need_derivs, what):
         if need_derivs and not img.with_derivs:
             raise error("%s: pyramid has no derivative planes" % what)
         return img
+    if hasattr(img, "ndim") and img.ndim == 3 and img.shape[2] == 1:      # (H,W,1) is a single-channel image for cv2 as well
+        img = img[..., 0]
     return FramePyramid(img, winSize, maxLevel, need_derivs)
+
+
+def _channels(img):
+    """1 for a FramePyramid or an (H,W) / (H,W,1) image, C for an (H,W,C) image"""
+    if isinstance(img, FramePyramid) or not hasattr(img, "ndim") or img.ndim != 3:
+        return 1
+    return int(img.shape[2])
+
+
+def _lk_multichannel(prevImg, nextImg, cn, pts, shp, nextPts, w, maxLevel, cnt, eps, flags, minEigThreshold, return_iters, as_np):
+    """calcOpticalFlowPyrLK on (H,W,C) u8 images, C = 2..4 (cv2 takes 3-channel frames; the reference converts to gray first,
+    s1:311): one single-channel pyramid per channel plane, window sums taken over pixels and channels (ibt_lk_multichannel)."""
+    if cn > 4:
+        raise error("calcOpticalFlowPyrLK: at most 4 channels")
+    a = _to_dev(prevImg, np.uint8, "calcOpticalFlowPyrLK prevImg")
+    b = _to_dev(nextImg, np.uint8, "calcOpticalFlowPyrLK nextImg")
+    if tuple(a.shape) != tuple(b.shape):
+        raise error("calcOpticalFlowPyrLK: prevImg and nextImg differ in size")
+    pI = [FramePyramid(a[..., c].contiguous(), w, maxLevel, True) for c in range(cn)]
+    pJ = [FramePyramid(b[..., c].contiguous(), w, maxLevel, False) for c in range(cn)]
+    n = pts.shape[0]
+    if flags & OPTFLOW_USE_INITIAL_FLOW:
+        if nextPts is None:
+            raise error("calcOpticalFlowPyrLK: OPTFLOW_USE_INITIAL_FLOW needs nextPts")
+        nxt = _to_dev(nextPts, np.float32, "calcOpticalFlowPyrLK nextPts").reshape(-1, 2).clone()
+        if nxt.shape[0] != n:
+            raise error("calcOpticalFlowPyrLK: nextPts and prevPts differ in length")
+    else:
+        nxt = torch.empty((n, 2), dtype=torch.float32, device=pts.device)
+    st = torch.empty((n,), dtype=torch.uint8, device=pts.device)
+    err = torch.empty((n,), dtype=torch.float32, device=pts.device)
+    iters = torch.empty((n,), dtype=torch.int32, device=pts.device) if return_iters else None
+    PP = C.POINTER(N.ibt_pyramid_t)
+    arrI = (PP * cn)(*[C.pointer(p.c) for p in pI])
+    arrJ = (PP * cn)(*[C.pointer(p.c) for p in pJ])
+    N.check(N.lib().ibt_lk_multichannel(arrI, arrJ, cn, _ptr(pts), _ptr(nxt), n, w[0], w[1], cnt, eps, float(minEigThreshold),
+                                        flags, _ptr(st), _ptr(err), _ptr(iters), _stream()), "ibt_lk_multichannel")
+    res = (_out(nxt.reshape(shp), as_np), _out(st.reshape(n, 1), as_np), _out(err.reshape(n, 1), as_np))
+    return res + ((_out(iters, as_np),) if return_iters else ())
 
 
 def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, winSize=(21, 21), maxLevel=3,
@@ -267,13 +308,19 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, winSize=(21, 2
         raise error("calcOpticalFlowPyrLK: winSize components must be in [3, %d]" % N.IBT_MAX_WIN)
     if maxLevel < 0:
         raise error("calcOpticalFlowPyrLK: maxLevel must be >= 0")
+    cnt, eps = _criteria(criteria)
+    cn = _channels(prevImg)
+    if cn != _channels(nextImg):
+        raise error("calcOpticalFlowPyrLK: prevImg and nextImg differ in the number of channels")
+    if cn > 1:
+        return _lk_multichannel(prevImg, nextImg, cn, pts, shp, nextPts, w, maxLevel, cnt, eps, int(flags), minEigThreshold,
+                                return_iters, as_np)
     pI = _as_pyramid(prevImg, w, maxLevel, True, "calcOpticalFlowPyrLK prevImg")
     pJ = _as_pyramid(nextImg, w, maxLevel, False, "calcOpticalFlowPyrLK nextImg")
     if pI.sizes[0] != pJ.sizes[0]:
         raise error("calcOpticalFlowPyrLK: prevImg and nextImg differ in size")
     if pI.maxLevel != pJ.maxLevel:
         raise error("calcOpticalFlowPyrLK: pyramids differ in depth")
-    cnt, eps = _criteria(criteria)
     flags = int(flags)
     if flags & OPTFLOW_USE_INITIAL_FLOW:
         if nextPts is None:

@@ -113,6 +113,15 @@ int ibt_lk_fb(const ibt_pyramid_t *prev, const ibt_pyramid_t *next,
               float *p0r, uint8_t *st0, float *err0,
               float *fbdist, uint8_t *alive, int32_t *iters, unsigned long long *iter_total,
               void *stream);
+/* cv2.calcOpticalFlowPyrLK on multi-channel 8-bit images (cv2 takes 3-channel frames as well; the reference converts
+ * to gray first, s1:311, so this is the plain form of the solver): pyrI / pyrJ are HOST arrays of cn (1..4) pointers to
+ * single-channel pyramids, one per channel plane (pyrI with Scharr planes).  OpenCV sums the structure tensor, the mismatch
+ * vector and the residual over the window pixels and the channels; err is divided by 32 * winW * cn * winH.  Same arguments
+ * and outputs as ibt_lk otherwise. */
+int ibt_lk_multichannel(const ibt_pyramid_t *const *pyrI, const ibt_pyramid_t *const *pyrJ, int cn,
+                        const float *pts, float *next_pts, int N,
+                        int winW, int winH, int max_count, double epsilon, double min_eig_threshold, int flags,
+                        uint8_t *status, float *err, int32_t *iters, void *stream);
 /* Process-wide occupancy cap of the persistent LK launches: at most `ctas` resident CTAs (of 8 warps) per SM, 0 = fill the SM
  * (default, 3 for the usual window sizes).  With 2 the launch leaves a third of every SM's shared memory and registers to
  * kernels of other streams -- e.g. the JPEG decode of the next frame (measured: LK 7 % slower, decode fully overlapped). */

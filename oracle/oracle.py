@@ -126,18 +126,29 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, winSize=(21, 2
     n = pts.shape[0]
     if n == 0:
         return (None, None, None) + ((None,) if return_iters else ())
-    ml, pI = buildOpticalFlowPyramid(prevImg, winSize, maxLevel, True)
-    ml2, pJ = buildOpticalFlowPyramid(nextImg, winSize, maxLevel, False)
-    assert ml == ml2
+    prevImg, nextImg = np.asarray(prevImg), np.asarray(nextImg)
+    assert prevImg.shape == nextImg.shape and prevImg.ndim in (2, 3)
+    if prevImg.ndim == 3 and prevImg.shape[2] == 1:
+        prevImg, nextImg = prevImg[..., 0], nextImg[..., 0]
+    # multi-channel images (cv2 accepts 3 channels; the reference always converts to gray first, s1:311): OpenCV builds the
+    # pyramid and the Scharr planes per channel and sums every window quantity over the channels as well
+    chI = [prevImg] if prevImg.ndim == 2 else [np.ascontiguousarray(prevImg[..., c]) for c in range(prevImg.shape[2])]
+    chJ = [nextImg] if nextImg.ndim == 2 else [np.ascontiguousarray(nextImg[..., c]) for c in range(nextImg.shape[2])]
+    cn = len(chI)
+    lvI, dvI, lvJ = [], [], []
+    for c in range(cn):
+        ml, pI = buildOpticalFlowPyramid(chI[c], winSize, maxLevel, True)
+        ml2, pJ = buildOpticalFlowPyramid(chJ[c], winSize, maxLevel, False)
+        assert ml == ml2
+        lvI += [pI[2 * l] for l in range(ml + 1)]
+        dvI += [pI[2 * l + 1] for l in range(ml + 1)]
+        lvJ += list(pJ)
     L = ml + 1
-    lvI = [pI[2 * l] for l in range(L)]
-    dvI = [pI[2 * l + 1] for l in range(L)]
-    lvJ = pJ
-    arrI = (C.c_void_p * L)(*[a.ctypes.data for a in lvI])
-    arrJ = (C.c_void_p * L)(*[a.ctypes.data for a in lvJ])
-    arrD = (C.c_void_p * L)(*[a.ctypes.data for a in dvI])
-    hs = (C.c_int * L)(*[a.shape[0] for a in lvI])
-    ws = (C.c_int * L)(*[a.shape[1] for a in lvI])
+    arrI = (C.c_void_p * (L * cn))(*[a.ctypes.data for a in lvI])
+    arrJ = (C.c_void_p * (L * cn))(*[a.ctypes.data for a in lvJ])
+    arrD = (C.c_void_p * (L * cn))(*[a.ctypes.data for a in dvI])
+    hs = (C.c_int * L)(*[a.shape[0] for a in lvI[:L]])
+    ws = (C.c_int * L)(*[a.shape[1] for a in lvI[:L]])
     use_init = bool(flags & OPTFLOW_USE_INITIAL_FLOW)
     if use_init:
         nxt = np.ascontiguousarray(np.asarray(nextPts, np.float32).reshape(-1, 2)).copy()
@@ -147,7 +158,7 @@ def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, winSize=(21, 2
     err = np.empty(n, np.float32)
     iters = np.zeros((n, L), np.int32)
     cnt, eps = _criteria(criteria)
-    lib().orc_lk(arrI, arrJ, arrD, hs, ws, C.c_int(ml), _p(pts), _p(nxt), C.c_int(n),
+    lib().orc_lk_cn(arrI, arrJ, arrD, C.c_int(cn), hs, ws, C.c_int(ml), _p(pts), _p(nxt), C.c_int(n),
                  C.c_int(winSize[0]), C.c_int(winSize[1]), C.c_int(cnt), C.c_double(eps),
                  C.c_double(minEigThreshold), C.c_int(use_init),
                  C.c_int(bool(flags & OPTFLOW_LK_GET_MIN_EIGENVALS)), _p(st), _p(err), _p(iters))

@@ -243,3 +243,9 @@ def test_harris_branch_golden(ibt, golden):
     import harris_cases as HC
     HC.check_harris_golden(ibt, golden("kat_harris.npz"),
                            {"texture": golden("kat_texture.npz"), "iceberg": golden("kat_iceberg.npz")})
+
+
+def test_multichannel_lk_golden(ibt, golden):
+    """calcOpticalFlowPyrLK on 3- / 4-channel frames through the C-ABI (ibt_lk_multichannel) vs cv2's recorded answers"""
+    import multichannel_cases as MC
+    MC.check_multichannel_golden(ibt, golden("kat_multichannel.npz"))

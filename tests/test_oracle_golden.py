@@ -117,3 +117,9 @@ def test_harris_branch_golden(oracle, golden):
     import harris_cases as HC
     HC.check_harris_golden(oracle, golden("kat_harris.npz"),
                            {"texture": golden("kat_texture.npz"), "iceberg": golden("kat_iceberg.npz")})
+
+
+def test_multichannel_lk_golden(oracle, golden):
+    """calcOpticalFlowPyrLK on 3- / 4-channel frames vs cv2's recorded answers (make_multichannel_golden.py)"""
+    import multichannel_cases as MC
+    MC.check_multichannel_golden(oracle, golden("kat_multichannel.npz"))

@@ -159,3 +159,25 @@ def test_harris_live(oracle, seed):
                           useHarrisDetector=True, k=k)
                 HC.check_lists(oracle.goodFeaturesToTrack(img, mask=m, **gp), cv2.goodFeaturesToTrack(img, mask=m, **gp),
                                (seed, gp, m is not None))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_lk_multichannel_live(oracle, seed):
+    """3-channel frames (cv2's signature takes them; the reference converts to gray first): window sums run over pixels and
+    channels -- status, positions and err against cv2 for random windows, levels and criteria"""
+    import multichannel_cases as MC
+    rng = np.random.default_rng(700 + seed)
+    h, w = int(rng.integers(70, 260)), int(rng.integers(70, 330))
+    f0 = np.dstack([_texture(rng, h, w) for _ in range(3)])
+    dx, dy = rng.uniform(-2.5, 2.5, 2)
+    f1 = np.dstack([_shifted(f0[..., c], float(dx), float(dy)) for c in range(3)])
+    f1 = np.clip(f1.astype(np.int16) + rng.integers(-2, 3, f1.shape), 0, 255).astype(np.uint8)
+    pts = np.stack([rng.uniform(-3, w + 3, 500), rng.uniform(-3, h + 3, 500)], 1).astype(np.float32).reshape(-1, 1, 2)
+    for _ in range(3):
+        win = (int(rng.choice([5, 9, 15, 21, 31, 35])), int(rng.choice([5, 9, 15, 21, 31, 35])))
+        lp = dict(winSize=win, maxLevel=int(rng.integers(0, 5)),
+                  criteria=(3, int(rng.integers(1, 31)), float(rng.choice([0.0, 0.01, 0.03]))))
+        r_p1, r_st, r_err = cv2.calcOpticalFlowPyrLK(f0, f1, pts, None, **lp)
+        p1, st, err = oracle.calcOpticalFlowPyrLK(f0, f1, pts, None, **lp)
+        assert_lk_parity(p1, st, r_p1, r_st, "3-channel %r" % (lp,))
+        MC.check_err(err, st, p1, r_err, r_st, r_p1, win, lp)
