@@ -54,6 +54,40 @@ def test_host_only_entry_points(so_path):
     assert lib.ibt_pyramid_levels(10, 10, 35, 35, 9, sizes) == _native.IBT_E_INVALID
 
 
+def test_invalid_arguments_are_rejected_before_any_cuda_call(so_path):
+    """Argument validation comes first in every entry point: these calls return IBT_E_INVALID (or the documented no-op) on a
+    box without a GPU, i.e. without having touched the CUDA runtime -- no compute call is made here."""
+    from iceberg_tracking_code_b200 import _native as N
+    lib = N.lib()
+    null = C.c_void_p(0)
+    pyr = N.ibt_pyramid_t()                                   # zeroed: nlevels == 0
+    PP = C.POINTER(N.ibt_pyramid_t)
+    one = (PP * 1)(C.pointer(pyr))
+    # version of the ABI with cv2's useHarrisDetector / k and the multi-channel LK entry point
+    assert lib.ibt_version() >= 101
+    # goodFeaturesToTrack: null image, image smaller than the 3x3 Sobel support, NaN k
+    cnt = C.c_int(7)
+    assert lib.ibt_gftt(null, 64, null, 0, 64, 64, 0, 0.01, 1.0, 3, 0, 0.04, null, 0, null, 0, C.byref(cnt), null) == N.IBT_E_INVALID
+    assert cnt.value == 0                                     # the host count is cleared even on failure
+    assert lib.ibt_gftt_async(null, 64, null, 0, 64, 64, 0, 0.01, 1.0, 3, 0, 0.04, null, 0, null, 0, null, null) == N.IBT_E_INVALID
+    assert lib.ibt_gftt_workspace_bytes(0, 10) == 0 and lib.ibt_gftt_workspace_bytes(4000, 6000) > 0
+    assert lib.ibt_corner_harris_f32(null, 8, 8, 8, 3, 0.04, null, 32, null) == N.IBT_E_INVALID
+    assert lib.ibt_min_eigen_f32(null, 8, 8, 8, 3, null, 32, null) == N.IBT_E_INVALID
+    # LK: window outside [3, IBT_MAX_WIN], empty pyramids, channel count outside 1..4; N == 0 is a no-op
+    assert lib.ibt_lk(C.byref(pyr), C.byref(pyr), null, null, 5, 2, 21, 30, 0.01, 1e-4, 0, null, null, null, null) == N.IBT_E_INVALID
+    assert lib.ibt_lk(C.byref(pyr), C.byref(pyr), null, null, 5, 21, N.IBT_MAX_WIN + 1, 30, 0.01, 1e-4, 0, null, null, null, null) == N.IBT_E_INVALID
+    assert lib.ibt_lk(C.byref(pyr), C.byref(pyr), null, null, 0, 21, 21, 30, 0.01, 1e-4, 0, null, null, null, null) == N.IBT_OK
+    assert lib.ibt_lk(C.byref(pyr), C.byref(pyr), null, null, 5, 21, 21, 30, 0.01, 1e-4, 0, null, null, null, null) == N.IBT_E_INVALID
+    for cn in (0, 5):
+        assert lib.ibt_lk_multichannel(one, one, cn, null, null, 5, 21, 21, 30, 0.01, 1e-4, 0, null, null, null, null) == N.IBT_E_INVALID
+    assert lib.ibt_lk_multichannel(one, one, 1, null, null, 0, 21, 21, 30, 0.01, 1e-4, 0, null, null, null, null) == N.IBT_OK
+    assert lib.ibt_lk_multichannel(None, None, 3, null, null, 5, 21, 21, 30, 0.01, 1e-4, 0, null, null, null, null) == N.IBT_E_INVALID
+    # pyramid build: no levels; gray: null pointers
+    assert lib.ibt_pyramid_build(C.byref(pyr), 1, null) == N.IBT_E_INVALID
+    assert lib.ibt_pyr_level_u8(null, 8, 8, 8, null, 0, null, 0, null) == N.IBT_E_INVALID
+    assert lib.ibt_lk_set_max_ctas_per_sm(-1) == N.IBT_E_INVALID and lib.ibt_lk_set_max_ctas_per_sm(0) == N.IBT_OK
+
+
 def test_struct_layout_matches_header():
     from iceberg_tracking_code_b200 import _native
     # int32 nlevels + 2*8 int32 + pad to 8 + 4 * 8 * 8 bytes
