@@ -18,6 +18,8 @@ from . import _native as N
 
 COLOR_BGR2GRAY = 6
 COLOR_RGB2GRAY = 7
+COLOR_BGRA2GRAY = 10          # cv2 computes these exactly like 6 / 7 (3 or 4 channels in, alpha ignored)
+COLOR_RGBA2GRAY = 11
 TERM_CRITERIA_COUNT = 1
 TERM_CRITERIA_MAX_ITER = 1
 TERM_CRITERIA_EPS = 2
@@ -68,13 +70,17 @@ def _ptr(t):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cvtColor(src, code=COLOR_BGR2GRAY, coeffset=0, dst=None):
-    """cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) (s1:311).  (H,W,3|4) u8 -> (H,W) u8.  Channel 0 gets the
-    0.114 weight whatever it holds; the reference feeds PIL's RGB array under the BGR code and that quirk is kept.
-    coeffset 0 = OpenCV 4.x 15-bit coefficients, 1 = OpenCV 3.x 14-bit.
+def cvtColor(src, code=COLOR_BGR2GRAY, dst=None, dstCn=0, *, coeffset=0):
+    """cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) (s1:311), positional order of cv2's cvtColor(src, code[, dst[, dstCn]]).
+    (H,W,3|4) u8 -> (H,W) u8.  Channel 0 gets the 0.114 weight whatever it holds; the reference feeds PIL's RGB array under
+    the BGR code and that quirk is kept.
+    coeffset (keyword only) 0 = OpenCV 4.x 15-bit coefficients, 1 = OpenCV 3.x 14-bit.
     dst: preallocated contiguous (H,W) u8 CUDA tensor to write into (steady-state loops allocate nothing)."""
-    if code not in (COLOR_BGR2GRAY, COLOR_RGB2GRAY):
-        raise error("cvtColor: only COLOR_BGR2GRAY / COLOR_RGB2GRAY are implemented")
+    if dstCn not in (0, 1):
+        raise error("cvtColor: a gray conversion has one destination channel")
+    if code not in (COLOR_BGR2GRAY, COLOR_RGB2GRAY, COLOR_BGRA2GRAY, COLOR_RGBA2GRAY):
+        raise error("cvtColor: only COLOR_BGR2GRAY / COLOR_RGB2GRAY / COLOR_BGRA2GRAY / COLOR_RGBA2GRAY are implemented")
+    code = {COLOR_BGRA2GRAY: COLOR_BGR2GRAY, COLOR_RGBA2GRAY: COLOR_RGB2GRAY}.get(code, code)
     as_np = _is_np(src)
     s = _to_dev(src, np.uint8, "cvtColor src")
     if s.ndim != 3 or s.shape[2] not in (3, 4):
@@ -285,10 +291,12 @@ def _lk_multichannel(prevImg, nextImg, cn, pts, shp, nextPts, w, maxLevel, cnt, 
     return res + ((_out(iters, as_np),) if return_iters else ())
 
 
-def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, winSize=(21, 21), maxLevel=3,
+def calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts=None, status=None, err=None, winSize=(21, 21), maxLevel=3,
                          criteria=(TERM_CRITERIA_COUNT | TERM_CRITERIA_EPS, 30, 0.01), flags=0, minEigThreshold=1e-4,
-                         return_iters=False):
-    """cv2.calcOpticalFlowPyrLK(img0, img1, p0, None, **lk_params) (s1:323,326).
+                         *, return_iters=False):
+    """cv2.calcOpticalFlowPyrLK(img0, img1, p0, None, **lk_params) (s1:323,326), positional order of cv2's
+    calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, nextPts[, status[, err[, winSize[, maxLevel[, criteria[, flags[,
+    minEigThreshold]]]]]]]); status / err are cv2's optional output placeholders: results are always returned, never written there.
     Returns (nextPts, status (N,1) u8, err (N,1) f32); nextPts has prevPts' shape; N == 0 -> (None, None, None).
     err is 0 where status == 0 (cv2 leaves uninitialised memory there).  prevImg / nextImg may be FramePyramid
     objects.  return_iters=True appends the (N,) int32 count of inner iterations executed per point."""
@@ -400,8 +408,9 @@ def lk_fb_into(prev, next, p0, lk_params, p1, fbdist, alive=None, iter_total=Non
 
 
 # ---------------------------------------------------------------------------------------------------
-def cornerMinEigenVal(src, blockSize, ksize=3):
-    """cv2.cornerMinEigenVal(u8 (H,W), blockSize, ksize=3) -> (H,W) f32."""
+def cornerMinEigenVal(src, blockSize, dst=None, ksize=3):
+    """cv2.cornerMinEigenVal(src, blockSize[, dst[, ksize]]): u8 (H,W) -> (H,W) f32; dst is cv2's output
+    placeholder (the map is returned)."""
     if ksize != 3:
         raise error("cornerMinEigenVal: only ksize=3 is implemented (the value goodFeaturesToTrack uses)")
     as_np = _is_np(src)
@@ -448,14 +457,18 @@ def _gftt_workspace(dev, H, W):
     return ws
 
 
-def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None, blockSize=3,
-                        useHarrisDetector=False, k=0.04):
-    """cv2.goodFeaturesToTrack(frame_gray, mask=mask, **feature_params) (s1:437).
+def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, corners=None, mask=None, blockSize=3,
+                        useHarrisDetector=False, k=0.04, gradientSize=3):
+    """cv2.goodFeaturesToTrack(frame_gray, mask=mask, **feature_params) (s1:437), positional order of cv2's
+    goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance[, corners[, mask[, blockSize[, useHarrisDetector[, k]]]]])
+    (corners is cv2's output placeholder; gradientSize, of cv2's second overload, must be 3 = the Sobel aperture of the first).
     Returns (K,1,2) float32 integer-valued (x, y) ordered by response, or None when there is no corner
     (callers test `if p is not None`, s1:445).  useHarrisDetector=True ranks cv2.cornerHarris(image, blockSize, 3, k)
     instead of the minimal eigenvalue (the reference never sets it)."""
     if not (qualityLevel > 0) or minDistance < 0:
         raise error("goodFeaturesToTrack: qualityLevel must be > 0 and minDistance >= 0")
+    if gradientSize != 3:
+        raise error("goodFeaturesToTrack: only gradientSize=3 is implemented (cv2's default; the reference never sets it)")
     as_np = _is_np(image)
     img = _to_dev(image, np.uint8, "goodFeaturesToTrack image")
     if img.ndim != 2:

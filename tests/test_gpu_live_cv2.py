@@ -17,6 +17,9 @@ def test_gray_and_pyramid_live(ibt):
     for h, w in L.SIZES:
         rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         assert np.array_equal(ibt.cvtColor(rgb, ibt.COLOR_BGR2GRAY), cv2.cvtColor(rgb, cv2.COLOR_BGR2GRAY)), (h, w)
+        rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        for code in (cv2.COLOR_BGR2GRAY, cv2.COLOR_RGB2GRAY, cv2.COLOR_BGRA2GRAY, cv2.COLOR_RGBA2GRAY):
+            assert np.array_equal(ibt.cvtColor(rgba, code), cv2.cvtColor(rgba, code)), (h, w, code)
     for h, w in [s for s in L.SIZES if min(s) >= 3]:
         a = rng.integers(0, 256, (h, w), dtype=np.uint8)
         win = (int(rng.choice([3, 9, 21, 31, 35])), int(rng.choice([3, 9, 21, 31, 35])))

@@ -4,6 +4,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -63,6 +64,7 @@ def test_pack_unpack_roundtrip():
 _WORKER = r'''
 import os, sys
 import numpy as np
+import pytest
 import torch.distributed as dist
 sys.path.insert(0, %r)
 from iceberg_tracking_code_b200 import sharding as sh
@@ -194,3 +196,26 @@ def test_view_loader_fallbacks(tmp_path, capsys, caplog):
     ref = tmp_path / "ref.jpg"
     Image.open(prog).crop((8, 4, 88, 60)).save(ref)
     assert np.array_equal(e, np.array(Image.open(ref)))
+
+
+def test_cv_functions_take_cv2_positional_order():
+    """The drop-in functions take their arguments in the positional order cv2's Python bindings document (first line of the
+    wheel's own __doc__), so a call site written for cv2 (s1:311,323,326,437) binds the same values whether it passes them by
+    position or by keyword.  buildOpticalFlowPyramid is the stated exception (its 4th positional is withDerivatives; cv2 has the
+    output placeholder `pyramid` there)."""
+    import inspect
+    import re
+    cv2 = pytest.importorskip("cv2")
+    from iceberg_tracking_code_b200 import cv
+    for name in ("cvtColor", "goodFeaturesToTrack", "calcOpticalFlowPyrLK", "cornerMinEigenVal", "cornerHarris", "pyrDown"):
+        first = getattr(cv2, name).__doc__.splitlines()[0]
+        theirs = [p for p in re.sub(r"[\[\]]", "", first[first.index("(") + 1:first.index(")")]).replace(" ", "").split(",") if p]
+        ours = [p.name for p in inspect.signature(getattr(cv, name)).parameters.values()
+                if p.kind == inspect.Parameter.POSITIONAL_OR_KEYWORD]
+        n = min(len(ours), len(theirs))
+        assert n >= 1 and ours[:n] == theirs[:n], (name, ours, theirs)
+    assert cv.COLOR_BGR2GRAY == cv2.COLOR_BGR2GRAY and cv.COLOR_RGB2GRAY == cv2.COLOR_RGB2GRAY
+    assert cv.COLOR_BGRA2GRAY == cv2.COLOR_BGRA2GRAY and cv.COLOR_RGBA2GRAY == cv2.COLOR_RGBA2GRAY
+    assert cv.TERM_CRITERIA_EPS == cv2.TERM_CRITERIA_EPS and cv.TERM_CRITERIA_COUNT == cv2.TERM_CRITERIA_COUNT
+    assert cv.OPTFLOW_USE_INITIAL_FLOW == cv2.OPTFLOW_USE_INITIAL_FLOW
+    assert cv.OPTFLOW_LK_GET_MIN_EIGENVALS == cv2.OPTFLOW_LK_GET_MIN_EIGENVALS
