@@ -122,4 +122,12 @@ def test_harris_branch_golden(oracle, golden):
 def test_multichannel_lk_golden(oracle, golden):
     """calcOpticalFlowPyrLK on 3- / 4-channel frames vs cv2's recorded answers (make_multichannel_golden.py)"""
     import multichannel_cases as MC
-    MC.check_multichannel_golden(oracle, golden("kat_multichannel.npz"))
+    g = golden("kat_multichannel.npz")
+    MC.check_multichannel_golden(oracle, g)
+    cv2 = pytest.importorskip("cv2")                     # OPTFLOW_LK_GET_MIN_EIGENVALS on 3 channels: still divided by 2*w*h, no cn
+    lp = MC.MC_SETS[0]
+    r = cv2.calcOpticalFlowPyrLK(g["f0"], g["f1"], g["pts"], None, flags=cv2.OPTFLOW_LK_GET_MIN_EIGENVALS, **lp)
+    o = oracle.calcOpticalFlowPyrLK(g["f0"], g["f1"], g["pts"], None, flags=oracle.OPTFLOW_LK_GET_MIN_EIGENVALS, **lp)
+    assert_lk_parity(o[0], o[1], r[0], r[1], "3-channel, min eigenvalues")
+    ok = (r[1].ravel() == 1) & (o[1].ravel() == 1)
+    assert np.abs(r[2].ravel()[ok] - o[2].ravel()[ok]).max() <= 1e-5
